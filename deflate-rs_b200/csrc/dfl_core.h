@@ -1,0 +1,475 @@
+// dfl_core.h -- position-independent logic of the B200 DEFLATE encoder, written once as
+// host+device inline functions.  The CUDA kernels (dfl_kernels.cu) call these from device code;
+// tests/model/dfl_model.cpp calls the same functions from a sequential CPU harness so that the
+// algorithms can be checked against the oracle in a container without a GPU.  Nothing here touches
+// memory it is not handed, and nothing here is a CPU fallback: the product library only reaches
+// these functions from kernels.
+//
+// Reference behaviour being restated (file:line under /root/reference/src) is cited per function.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DFL_HD __host__ __device__ __forceinline__
+#else
+#define DFL_HD inline
+#endif
+
+namespace dfl {
+
+// ---------------------------------------------------------------- constants
+constexpr uint32_t kWindow = 32768;          // chained_hash_table.rs:1, huffman_table.rs:25
+constexpr uint32_t kWindowMask = kWindow - 1;
+constexpr uint32_t kMinMatch = 3;            // huffman_table.rs:20
+constexpr uint32_t kMaxMatch = 258;          // huffman_table.rs:21
+constexpr uint32_t kBlockTokens = 31744;     // output_writer.rs:19 (MAX_BUFFER_LENGTH)
+constexpr uint32_t kNumLL = 286;             // huffman_table.rs:13
+constexpr uint32_t kNumDist = 30;            // huffman_table.rs:9
+constexpr uint32_t kEob = 256;               // huffman_table.rs:28
+constexpr uint32_t kTooFar = 8192;           // lz77.rs:274-278
+constexpr uint32_t kMaxStored = 32767;       // stored_block.rs:11
+
+enum Mode : int { kGreedy = 0, kLazy = 1, kRle = 2 };   // lz77.rs:192-232 process_chunk dispatch
+enum BlockType : int { kStored = 0, kFixed = 1, kDynamic = 2 };
+
+// Parameters derived from CompressionOptions (compression_options.rs:78-120) exactly as
+// DeflateState::new does (deflate_state.rs:100-109: lazy_if_less_than clamped to 32768).
+struct Params {
+    uint32_t checks;        // max_hash_checks
+    uint32_t checks_quarter;// max_hash_checks >> 2, used when the pending match is >= 32 (lz77.rs:351-355)
+    uint32_t lazy;          // lazy_if_less_than (clamped)
+    int mode;               // Mode
+    int need_quarter;       // 1 iff a search with the quarter budget can happen (lazy > 32)
+};
+
+DFL_HD Params make_params(uint16_t max_hash_checks, uint16_t lazy_if_less_than, uint8_t matching_type) {
+    Params p;
+    p.checks = max_hash_checks;
+    p.checks_quarter = max_hash_checks >> 2;
+    p.lazy = lazy_if_less_than < 32768u ? lazy_if_less_than : 32768u;
+    if (matching_type == 0) p.mode = kGreedy;
+    else p.mode = (max_hash_checks > 0) ? kLazy : kRle;
+    p.need_quarter = (p.mode == kLazy && p.lazy > 32) ? 1 : 0;
+    return p;
+}
+
+// ---------------------------------------------------------------- hashing
+// chained_hash_table.rs:55-62: three applications of h = ((h << 5) ^ b) & 0x7fff leave exactly
+// ((b0 & 31) << 10) ^ (b1 << 5) ^ b2 -- the contribution of older bytes is shifted out.
+DFL_HD uint32_t hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
+    return ((b0 & 31u) << 10) ^ (b1 << 5) ^ b2;
+}
+// Nine bits that, together with an equal hash3, prove the three bytes are equal.
+DFL_HD uint32_t tag9(uint32_t b0, uint32_t b1) {
+    return (b0 >> 5) | ((b0 & 7u) << 3) | ((b1 & 7u) << 6);
+}
+// One entry of a per-window sorted candidate list: position inside the 32 KiB window (15 bits),
+// the 4th byte (8 bits) and the 3-byte tag (9 bits).
+DFL_HD uint32_t pack_entry(uint32_t pos_local, uint32_t b0, uint32_t b1, uint32_t b3) {
+    return pos_local | (b3 << 15) | (tag9(b0, b1) << 23);
+}
+DFL_HD uint32_t entry_pos(uint32_t e) { return e & 0x7fffu; }
+DFL_HD uint32_t entry_filter(uint32_t e) { return e >> 15; }   // b3 | tag << 8  (17 bits)
+DFL_HD uint32_t entry_tag(uint32_t e) { return e >> 23; }
+
+// ---------------------------------------------------------------- per-position match record
+// len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23.  0 == "no usable match".
+DFL_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 9); }
+DFL_HD uint32_t match_len(uint32_t m) { return m & 0x1ffu; }
+DFL_HD uint32_t match_dist(uint32_t m) { return ((m >> 9) & 0x7fffu) + 1u; }
+// lz77.rs:274-278 match_too_far applied to the result of matching.rs:87-166; results shorter than
+// MIN_MATCH are never used by either parser and are recorded as "no match".
+DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
+    if (len < kMinMatch) return 0u;
+    if (len == kMinMatch && dist > kTooFar) return 0u;
+    return pack_match(len, dist);
+}
+
+// ---------------------------------------------------------------- tokens
+// bits 0..8: literal byte, or match length (3..258); bits 9..24: distance (0 = literal).
+DFL_HD uint32_t tok_literal(uint32_t b) { return b; }
+DFL_HD uint32_t tok_match(uint32_t len, uint32_t dist) { return len | (dist << 9); }
+DFL_HD uint32_t tok_dist(uint32_t t) { return t >> 9; }
+DFL_HD uint32_t tok_lo(uint32_t t) { return t & 0x1ffu; }
+DFL_HD uint32_t tok_input_len(uint32_t t) { return (t >> 9) ? (t & 0x1ffu) : 1u; }
+
+// ---------------------------------------------------------------- symbol arithmetic
+// Closed forms of the lookup tables in huffman_table.rs:45-111 (LENGTH_CODE/BASE_LENGTH/
+// LENGTH_EXTRA_BITS_LENGTH, DISTANCE_CODES/DISTANCE_BASE and num_extra_bits_for_distance_code);
+// tests/test_model.py checks them against the tables parsed from the reference source.
+DFL_HD uint32_t ilog2(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)x);
+#else
+    return 31u - (uint32_t)__builtin_clz(x);
+#endif
+}
+// length 3..258 -> (code 257..285, extra bit count, extra value)
+DFL_HD void length_symbol(uint32_t len, uint32_t& code, uint32_t& nextra, uint32_t& extra) {
+    uint32_t l = len - kMinMatch;
+    if (l < 8u) { code = 257u + l; nextra = 0; extra = 0; return; }
+    if (l == 255u) { code = 285u; nextra = 0; extra = 0; return; }
+    uint32_t nb = ilog2(l);                     // 3..7
+    nextra = nb - 2u;
+    code = 257u + 4u * (nb - 1u) + ((l >> nextra) & 3u);
+    extra = l & ((1u << nextra) - 1u);
+}
+// distance 1..32768 -> (code 0..29, extra bit count, extra value)
+DFL_HD void dist_symbol(uint32_t dist, uint32_t& code, uint32_t& nextra, uint32_t& extra) {
+    uint32_t x = dist - 1u;
+    if (x < 4u) { code = x; nextra = 0; extra = 0; return; }
+    uint32_t nb = ilog2(x);                     // 2..14
+    nextra = nb - 1u;
+    code = 2u * nb + ((x >> nextra) & 1u);
+    extra = x & ((1u << nextra) - 1u);
+}
+DFL_HD uint32_t length_extra_bits_of_code(uint32_t c /*0..28*/) {
+    return (c < 8u || c == 28u) ? 0u : ((c - 4u) >> 2);
+}
+DFL_HD uint32_t dist_extra_bits_of_code(uint32_t c /*0..29*/) {
+    uint32_t h = c >> 1;                        // huffman_table.rs:120-126
+    return h - (h != 0u ? 1u : 0u);
+}
+DFL_HD uint32_t fixed_ll_length(uint32_t s) {   // huffman_table.rs:32-42
+    return s < 144u ? 8u : (s < 256u ? 9u : (s < 280u ? 7u : 8u));
+}
+// bit_reverse.rs:3-10
+DFL_HD uint32_t reverse_bits(uint32_t v, uint32_t nbits) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32u - nbits);
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < nbits; i++) r |= ((v >> i) & 1u) << (nbits - 1u - i);
+    return r;
+#endif
+}
+
+// ---------------------------------------------------------------- parser state machines
+// State of the reference's parsers *between* loop iterations, in absolute positions.
+// (lz77.rs:162-173 ChunkState + the locals prev_length/prev_distance/ignore_next of
+// process_chunk_lazy, lz77.rs:305-486.)  `pos` is the position the next iteration examines.
+struct ParseState {
+    uint32_t pos;
+    uint32_t prev_len;   // pending match found at pos-1 (0 = none)
+    uint32_t prev_dist;
+    uint32_t add;        // byte pos-1 is still to be emitted as a literal
+    uint32_t ign;        // ignore_next
+};
+DFL_HD ParseState parse_state_init(uint32_t pos) {
+    ParseState s; s.pos = pos; s.prev_len = 0; s.prev_dist = 0; s.add = 0; s.ign = 0; return s;
+}
+DFL_HD uint32_t parse_state_key(const ParseState& s) {
+    return s.prev_len | (s.prev_dist << 9) | (s.add << 25) | (s.ign << 26);   // prev_dist <= 32768: 16 bits
+}
+
+// One iteration of process_chunk_lazy (lz77.rs:340-480) over precomputed per-position matches.
+// mf/mq: finalize_match() records of this position for the full / quarter chain budget
+// (matching.rs:87-166 returns the longest among the first `checks` chain candidates, nearest on
+// ties, and only if it is longer than prev_length).  Emits 0..2 tokens through out[]; returns count.
+DFL_HD int lazy_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t mf, uint32_t mq,
+                     uint32_t lazy, uint32_t out[2]) {
+    const uint32_t p = s.pos;
+    int ne = 0;
+    if (p + 2u < n) {                                   // hash_it.next() is Some
+        uint32_t cur_len = 0, cur_dist = 0;
+        if (!s.ign) {
+            uint32_t m = (s.prev_len >= 32u) ? mq : mf; // lz77.rs:351-355
+            uint32_t floor_len = s.prev_len > 1u ? s.prev_len : 1u;
+            if (match_len(m) > floor_len) { cur_len = match_len(m); cur_dist = match_dist(m); }
+            if (cur_len >= lazy) s.ign = 1;             // lz77.rs:374-377
+        } else {
+            s.ign = 0;                                  // lz77.rs:380-386
+        }
+        if (s.prev_len >= cur_len && s.prev_len >= kMinMatch) {   // lz77.rs:388-426
+            out[ne++] = tok_match(s.prev_len, s.prev_dist);
+            s.pos = p - 1u + s.prev_len;
+            s.add = 0; s.prev_len = 0; s.prev_dist = 0; s.ign = 0;
+        } else {
+            if (s.add) out[ne++] = tok_literal(data[p - 1u]);     // lz77.rs:427-431
+            else s.add = 1;                                        // lz77.rs:432-434
+            s.prev_len = cur_len; s.prev_dist = cur_dist;
+            s.pos = p + 1u;
+        }
+    } else {                                            // last two bytes, lz77.rs:440-482
+        if (s.prev_len >= kMinMatch) {
+            out[ne++] = tok_match(s.prev_len, s.prev_dist);
+            s.pos = n; s.add = 0; s.prev_len = 0; s.prev_dist = 0;
+        } else {
+            if (s.add) { s.add = 0; out[ne++] = tok_literal(data[p - 1u]); }
+            out[ne++] = tok_literal(data[p]);
+            s.pos = p + 1u;
+        }
+    }
+    return ne;
+}
+
+// One iteration of process_chunk_greedy (lz77.rs:502-544).
+DFL_HD int greedy_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t mf, uint32_t out[2]) {
+    const uint32_t p = s.pos;
+    if (p + 2u < n && match_len(mf) >= kMinMatch) {
+        out[0] = tok_match(match_len(mf), match_dist(mf));
+        s.pos = p + match_len(mf);
+    } else {
+        out[0] = tok_literal(data[p]);
+        s.pos = p + 1u;
+    }
+    return 1;
+}
+
+// One iteration of process_chunk_greedy_rle (rle.rs:23-71): distance-1 runs only.
+DFL_HD int rle_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t out[2]) {
+    const uint32_t p = s.pos;
+    if (p == 0u) { out[0] = tok_literal(data[0]); s.pos = 1; return 1; }
+    const uint8_t prev = data[p - 1u];
+    uint32_t len = 0;
+    if (data[p] == prev) {
+        uint32_t maxl = n - p < kMaxMatch ? n - p : kMaxMatch;
+        while (len < maxl && data[p + len] == prev) len++;
+    }
+    if (len >= kMinMatch) { out[0] = tok_match(len, 1u); s.pos = p + len; }
+    else { out[0] = tok_literal(data[p]); s.pos = p + 1u; }
+    return 1;
+}
+
+// ---------------------------------------------------------------- Huffman code construction
+// length_encode.rs:347-415 in_place_lengths: stable sort by frequency, Moffat-Katajainen in-place
+// (step_1/step_2, :218-278), miniz-style limiter (:290-327), then lengths handed out from the
+// highest-frequency leaf down (:402-408).  `key` scratch must hold n_freq entries.  A leaf is
+// (freq << 9) | symbol, so an ordinary sort of the keys is the reference's stable sort.
+DFL_HD void huffman_lengths(const uint32_t* freqs, uint32_t n_freq, uint32_t max_len,
+                            uint8_t* lens /*n_lens*/, uint32_t n_lens, uint32_t* key) {
+    for (uint32_t i = 0; i < n_lens; i++) lens[i] = 0;
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_freq; i++)
+        if (freqs[i] > 0) key[n++] = (freqs[i] << 9) | i;
+    if (n == 0) return;
+    if (n == 1) { lens[key[0] & 0x1ffu] = 1; return; }
+    // insertion sort on unique keys == stable sort by freq (symbols were appended in index order)
+    for (uint32_t i = 1; i < n; i++) {
+        uint32_t k = key[i];
+        uint32_t j = i;
+        while (j > 0 && key[j - 1] > k) { key[j] = key[j - 1]; j--; }
+        key[j] = k;
+    }
+    // From here `key[i] >> 9` plays the role of leaves[i].value and `key[i] & 511` of .symbol.
+#define DFL_VAL(i) (key[(i)] >> 9)
+#define DFL_SETVAL(i, v) (key[(i)] = ((uint32_t)(v) << 9) | (key[(i)] & 0x1ffu))
+    {   // step_1
+        uint32_t root = 0, leaf = 2;
+        DFL_SETVAL(0, DFL_VAL(0) + DFL_VAL(1));
+        for (uint32_t next = 1; next + 1 < n; next++) {
+            uint32_t v;
+            if (leaf >= n || DFL_VAL(root) < DFL_VAL(leaf)) { v = DFL_VAL(root); DFL_SETVAL(root, next); root++; }
+            else { v = DFL_VAL(leaf); leaf++; }
+            if (leaf >= n || (root < next && DFL_VAL(root) < DFL_VAL(leaf))) { v += DFL_VAL(root); DFL_SETVAL(root, next); root++; }
+            else { v += DFL_VAL(leaf); leaf++; }
+            DFL_SETVAL(next, v);
+        }
+    }
+    {   // step_2
+        DFL_SETVAL(n - 2, 0);
+        for (uint32_t t = n - 2; t-- > 0;) DFL_SETVAL(t, DFL_VAL(DFL_VAL(t)) + 1);
+        uint32_t available = 1, used = 0, depth = 0;
+        int root = (int)n - 2, next = (int)n - 1;
+        while (available > 0) {
+            while (root >= 0 && DFL_VAL(root) == depth) { used++; root--; }
+            while (available > used) { DFL_SETVAL(next, depth); next--; available--; }
+            available = 2 * used; depth++; used = 0;
+        }
+    }
+    uint32_t num_codes[33];
+    for (int i = 0; i < 33; i++) num_codes[i] = 0;
+    for (uint32_t i = 0; i < n; i++) { uint32_t d = DFL_VAL(i); num_codes[d < 32u ? d : 32u]++; }
+    {   // enforce_max_code_lengths
+        uint32_t above = 0;
+        for (uint32_t i = max_len + 1; i < 33; i++) above += num_codes[i];
+        num_codes[max_len] += above;
+        uint32_t total = 0;
+        for (uint32_t i = max_len; i >= 1; i--) total += num_codes[i] << (max_len - i);
+        while (total != (1u << max_len)) {
+            num_codes[max_len]--;
+            for (uint32_t i = max_len - 1; i >= 1; i--)
+                if (num_codes[i] != 0) { num_codes[i]--; num_codes[i + 1] += 2; break; }
+            total--;
+        }
+    }
+    uint32_t it = n;
+    for (uint32_t len = 1; len <= max_len; len++)
+        for (uint32_t c = 0; c < num_codes[len]; c++) { it--; lens[key[it] & 0x1ffu] = (uint8_t)len; }
+#undef DFL_VAL
+#undef DFL_SETVAL
+}
+// NB: the weight of an internal node can reach the sum of all frequencies (<= 31744 + 1 per
+// block, output_writer.rs:19), far below 2^23, so packing value and symbol in 32 bits is exact.
+
+// huffman_table.rs:253-278 create_codes_in_place: canonical codes, bit-reversed for LSB-first output.
+DFL_HD void canonical_codes(const uint8_t* lens, uint32_t n, uint16_t* codes) {
+    uint32_t cnt[16];
+    for (int i = 0; i < 16; i++) cnt[i] = 0;
+    for (uint32_t i = 0; i < n; i++) if (lens[i]) cnt[lens[i]]++;
+    uint32_t next_code[16];
+    uint32_t code = 0;
+    next_code[0] = 0;
+    for (uint32_t b = 1; b < 16; b++) { code = (code + cnt[b - 1]) << 1; next_code[b] = code; }
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t l = lens[i];
+        codes[i] = l ? (uint16_t)reverse_bits(next_code[l]++ & 0xffffu, l) : (uint16_t)0;
+    }
+}
+
+// length_encode.rs:82-155 encode_lengths_m, restated as explicit run handling but emitting exactly
+// the reference's symbol sequence (tests compare against the oracle's literal port on random and
+// adversarial inputs).  Output symbols: low 5 bits = symbol 0..18, bits 8.. = repeat count.
+// Returns the number of symbols; freqs19 is incremented.
+DFL_HD uint32_t rle_not_max(uint32_t l, uint32_t repeats) { return (l == 0u && repeats < 138u) || repeats < 6u; }
+DFL_HD uint32_t encode_lengths(const uint8_t* lengths, uint32_t n, uint16_t* out, uint32_t* freqs19) {
+    uint32_t no = 0;
+    uint32_t repeat = 0;
+    uint32_t prev = (uint32_t)(uint8_t)~lengths[0];
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t l = lengths[i];
+        const bool at_end = (i + 1 == n);
+        if (l == prev && rle_not_max(l, repeat)) repeat++;
+        if (l != prev || at_end || !rle_not_max(l, repeat)) {
+            if (repeat >= 3u) {
+                uint32_t sym = (prev == 0u) ? (repeat <= 10u ? 17u : 18u) : 16u;
+                out[no++] = (uint16_t)(sym | (repeat << 8)); freqs19[sym]++;
+                repeat = 0;
+                if (l != prev) {
+                    if (l != 0u || at_end) { out[no++] = (uint16_t)l; freqs19[l]++; repeat = 0; }
+                    else repeat = 1;
+                }
+            } else {
+                uint32_t extra_skip = (at_end && l == prev) ? 1u : 0u;
+                uint32_t skip = i + extra_skip - repeat;
+                uint32_t extra = (l != 0u || at_end) ? 1u : 0u;
+                uint32_t take = repeat + extra;
+                for (uint32_t k = skip; k < n && k < skip + take; k++) { out[no++] = lengths[k]; freqs19[lengths[k]]++; }
+                repeat = 1u - extra;
+            }
+        }
+        prev = l;
+    }
+    return no;
+}
+
+// Everything gen_huffman_lengths (huffman_lengths.rs:167-287) derives from one block's histograms,
+// except the final Stored decision which needs the bit position of the block (see choose_block).
+struct BlockCodes {
+    uint8_t ll_len[288];
+    uint8_t d_len[32];
+    uint16_t ll_code[288];
+    uint16_t d_code[32];
+    uint8_t cl_len[19];
+    uint16_t cl_code[19];
+    uint16_t hdr_sym[320];      // encoded lengths of ll||dist (symbol | repeat << 8)
+    uint32_t n_hdr_sym;
+    uint32_t hlit, hdist;       // number of ll / dist lengths transmitted
+    uint32_t used_hclens;
+    uint32_t tiny;              // num_input_bytes <= 4  -> Fixed without any cost computation
+    uint64_t dynamic_cost;      // the reference's *estimate* (symbol 16 counted with 3 extra bits)
+    uint64_t static_cost;       // ditto (distance symbols costed with the literal table)
+    uint64_t stored_cost;       // stored_length(n) without the position-dependent padding
+    uint64_t dynamic_bits;      // bits actually emitted after the 3-bit block header
+    uint64_t fixed_bits;
+    uint64_t input_bytes;
+};
+
+DFL_HD uint64_t stored_padding(uint32_t pending_bits /*0..7*/) {   // huffman_lengths.rs:113-124
+    uint32_t free_space = 8u - pending_bits;
+    return free_space >= 3u ? free_space - 3u : 8u - (3u - free_space);
+}
+DFL_HD uint64_t stored_length(uint64_t n) {                         // huffman_lengths.rs:132-143
+    uint64_t k = (n - 1u) / kMaxStored + 1u;
+    return (n + 4u * k + (k - 1u)) * 8u;
+}
+
+DFL_HD void build_block_codes(const uint32_t* ll_freq /*286*/, const uint32_t* d_freq /*30*/,
+                              uint64_t input_bytes, BlockCodes& bc, uint32_t* scratch /*>=288*/) {
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    bc.input_bytes = input_bytes;
+    bc.tiny = input_bytes <= 4u ? 1u : 0u;
+    // fixed-code body size is needed for every block type decision and for tiny blocks
+    {
+        uint64_t fb = 0;
+        for (uint32_t c = 0; c < kNumLL; c++) {
+            uint32_t eb = c >= 257u ? length_extra_bits_of_code(c - 257u) : 0u;
+            fb += (uint64_t)ll_freq[c] * (fixed_ll_length(c) + eb);
+        }
+        for (uint32_t c = 0; c < kNumDist; c++) fb += (uint64_t)d_freq[c] * (5u + dist_extra_bits_of_code(c));
+        bc.fixed_bits = fb;
+    }
+    if (bc.tiny) {
+        bc.dynamic_cost = bc.static_cost = bc.stored_cost = bc.dynamic_bits = 0;
+        bc.n_hdr_sym = 0; bc.hlit = 257; bc.hdist = 1; bc.used_hclens = 4;
+        return;
+    }
+    uint32_t nl = kNumLL; while (nl > 257u && ll_freq[nl - 1] == 0) nl--;   // remove_trailing_zeroes
+    uint32_t nd = kNumDist; while (nd > 1u && d_freq[nd - 1] == 0) nd--;
+    bc.hlit = nl; bc.hdist = nd;
+    huffman_lengths(ll_freq, nl, 15, bc.ll_len, 288, scratch);
+    huffman_lengths(d_freq, nd, 15, bc.d_len, 32, scratch);
+    uint32_t f19[19];
+    for (int i = 0; i < 19; i++) f19[i] = 0;
+    uint8_t chained[288 + 32];
+    for (uint32_t i = 0; i < nl; i++) chained[i] = bc.ll_len[i];
+    for (uint32_t i = 0; i < nd; i++) chained[nl + i] = bc.d_len[i];
+    bc.n_hdr_sym = encode_lengths(chained, nl + nd, bc.hdr_sym, f19);
+    huffman_lengths(f19, 19, 7, bc.cl_len, 19, scratch);
+    uint32_t trailing = 0;
+    while (trailing < 19u && bc.cl_len[order[18u - trailing]] == 0) trailing++;
+    bc.used_hclens = 19u - trailing;
+    canonical_codes(bc.ll_len, 288, bc.ll_code);
+    canonical_codes(bc.d_len, 32, bc.d_code);
+    canonical_codes(bc.cl_len, 19, bc.cl_code);
+    // calculate_block_length (:75-107): the distance pass zips with the literal FIXED table too.
+    uint64_t d_ll = 0, s_ll = 0, d_dist = 0, s_dist = 0;
+    for (uint32_t c = 0; c < nl; c++) {
+        uint64_t eb = c >= 257u ? length_extra_bits_of_code(c - 257u) : 0u;
+        d_ll += (uint64_t)ll_freq[c] * (bc.ll_len[c] + eb);
+        s_ll += (uint64_t)ll_freq[c] * (fixed_ll_length(c) + eb);
+    }
+    for (uint32_t c = 0; c < nd; c++) {
+        uint64_t eb = dist_extra_bits_of_code(c);
+        d_dist += (uint64_t)d_freq[c] * (bc.d_len[c] + eb);
+        s_dist += (uint64_t)d_freq[c] * (fixed_ll_length(c) + eb);
+    }
+    uint64_t table_est = 0, table_bits = 0;
+    for (uint32_t i = 0; i < 19; i++) {
+        uint32_t est_extra = (i == 16u || i == 17u) ? 3u : (i == 18u ? 7u : 0u);   // :50-56
+        uint32_t real_extra = i == 16u ? 2u : (i == 17u ? 3u : (i == 18u ? 7u : 0u));
+        table_est += (uint64_t)f19[i] * (bc.cl_len[i] + est_extra);
+        table_bits += (uint64_t)f19[i] * (bc.cl_len[i] + real_extra);
+    }
+    bc.dynamic_cost = d_ll + d_dist + table_est + (uint64_t)bc.used_hclens * 3u + 14u;
+    bc.static_cost = s_ll + s_dist;
+    bc.stored_cost = stored_length(input_bytes);
+    bc.dynamic_bits = d_ll + d_dist + table_bits + (uint64_t)bc.used_hclens * 3u + 14u;
+}
+
+// The tail of gen_huffman_lengths (huffman_lengths.rs:265-286): pick the cheapest representation,
+// ties Fixed > Stored > Dynamic.  `pending` = bit position of the block start modulo 8.
+// Returns the type and the number of bits the block occupies including its 3-bit header.
+DFL_HD int choose_block(const BlockCodes& bc, uint32_t pending, uint64_t& total_bits) {
+    if (bc.tiny) { total_bits = 3u + bc.fixed_bits; return kFixed; }
+    uint64_t stored_len = bc.stored_cost + stored_padding(pending);
+    uint64_t used = bc.dynamic_cost < bc.static_cost ? bc.dynamic_cost : bc.static_cost;
+    if (stored_len < used) used = stored_len;
+    if (used == bc.static_cost) { total_bits = 3u + bc.fixed_bits; return kFixed; }
+    if (used == stored_len) { total_bits = 3u + stored_len; return kStored; }
+    total_bits = 3u + bc.dynamic_bits;
+    return kDynamic;
+}
+
+// ---------------------------------------------------------------- Adler-32 (RFC 1950)
+constexpr uint32_t kAdlerMod = 65521;
+// combine(adler of A, adler of B, len(B)) -> adler of A||B
+DFL_HD uint32_t adler32_combine(uint32_t ad1, uint32_t ad2, uint64_t len2) {
+    uint32_t a1 = ad1 & 0xffffu, b1 = ad1 >> 16, a2 = ad2 & 0xffffu, b2 = ad2 >> 16;
+    uint32_t rem = (uint32_t)(len2 % kAdlerMod);
+    uint32_t a = (a1 + a2 + kAdlerMod - 1u) % kAdlerMod;
+    uint64_t b = (uint64_t)b1 + b2 + (uint64_t)rem * ((a1 + kAdlerMod - 1u) % kAdlerMod);
+    return (uint32_t)((b % kAdlerMod) << 16) | a;
+}
+
+}  // namespace dfl

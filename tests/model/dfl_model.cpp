@@ -1,0 +1,359 @@
+// dfl_model.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Sequential CPU walk-through of the *GPU pipeline's* algorithms (not of the reference): it calls
+// the same host+device functions from deflate-rs_b200/csrc/dfl_core.h that the CUDA kernels call,
+// in the same stage order and with the same data layouts (per-window sorted candidate lists,
+// per-position match records, speculative parse segments with hand-off verification, fixed
+// 31744-token blocks, per-block code construction, bit-offset scan, scatter bit packing).
+// tests/test_model.py checks its output byte-for-byte against the oracle, which lets the
+// algorithmic claims of DESIGN.md be verified in a container that has no GPU.  It is never linked
+// into the product library.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../deflate-rs_b200/csrc/dfl_core.h"
+
+using namespace dfl;
+
+namespace {
+
+struct Cfg {
+    uint32_t pseg;   // parse segment length
+    uint32_t warm;   // speculative warm-up
+    uint32_t rounds; // parallel repair rounds before the sequential fallback
+};
+
+// ---- stage 1: per-window stable counting sort by hash3 (kernel k_window_sort)
+void window_sort(const uint8_t* d, uint32_t n, std::vector<uint32_t>& S, std::vector<uint16_t>& off,
+                 std::vector<uint32_t>& cnt) {
+    uint32_t nseg = (n + kWindow - 1) / kWindow;
+    S.assign((size_t)nseg * kWindow, 0);
+    off.assign((size_t)nseg * kWindow, 0);
+    cnt.assign(nseg, 0);
+    uint32_t hashable = n >= 2 ? n - 2 : 0;   // positions p with p + 2 < n
+    for (uint32_t s = 0; s < nseg; s++) {
+        uint32_t base = s * kWindow;
+        uint32_t c = hashable > base ? std::min(kWindow, hashable - base) : 0;
+        cnt[s] = c;
+        std::vector<uint32_t> hist(kWindow + 1, 0);
+        for (uint32_t i = 0; i < c; i++) hist[hash3(d[base + i], d[base + i + 1], d[base + i + 2]) + 1]++;
+        for (uint32_t h = 0; h < kWindow; h++) hist[h + 1] += hist[h];
+        for (uint32_t h = 0; h < kWindow; h++) off[(size_t)s * kWindow + h] = (uint16_t)hist[h];
+        std::vector<uint32_t> cur(hist.begin(), hist.end() - 1);
+        for (uint32_t i = 0; i < c; i++) {
+            uint32_t p = base + i;
+            uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
+            uint32_t b3 = p + 3 < n ? d[p + 3] : 0;
+            S[(size_t)s * kWindow + cur[h]++] = pack_entry(i, d[p], d[p + 1], b3);
+        }
+    }
+}
+
+uint32_t common_prefix(const uint8_t* d, uint32_t p, uint32_t q, uint32_t maxl) {
+    uint32_t l = 0;
+    while (l < maxl && d[p + l] == d[q + l]) l++;
+    return l;
+}
+
+// ---- stage 2: candidate walk per sorted entry (kernel k_match)
+void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<uint32_t>& S,
+               const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
+               std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
+    Mf.assign(n, 0);
+    if (prm.need_quarter) Mq.assign(n, 0);
+    uint32_t nseg = (uint32_t)cnt.size();
+    for (uint32_t s = 0; s < nseg; s++) {
+        const uint32_t* Sj = &S[(size_t)s * kWindow];
+        const uint16_t* oj = &off[(size_t)s * kWindow];
+        for (uint32_t i = 0; i < cnt[s]; i++) {
+            uint32_t e = Sj[i];
+            uint32_t pl = entry_pos(e);
+            uint32_t p = s * kWindow + pl;
+            uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
+            uint32_t my_filter = entry_filter(e);
+            uint32_t my_tag = entry_tag(e);
+            uint32_t maxl = std::min(kMaxMatch, n - p);
+            uint32_t best_len = 1, best_dist = 0;   // matching.rs:108: prev_length floor of 1
+            uint32_t q_len = 0, q_dist = 0;         // snapshot after checks_quarter candidates
+            uint32_t budget = prm.checks, k = 0;
+            bool done = false;
+            auto consider = [&](uint32_t ce, uint32_t q) {
+                // necessary conditions first (filters), then the byte compare
+                if (entry_tag(ce) != my_tag) return;             // first three bytes differ
+                if (best_len >= 3 && maxl > 3 && entry_filter(ce) != my_filter) return;  // 4th byte differs
+                if (best_len >= maxl) return;
+                if (d[q + best_len] != d[p + best_len]) return;
+                uint32_t l = common_prefix(d, p, q, maxl);
+                if (l > best_len) {
+                    best_len = l; best_dist = p - q;
+                    if (l == maxl) done = true;                   // matching.rs:152-156
+                }
+            };
+            // own window, most recent first
+            uint32_t s0 = oj[h];
+            for (uint32_t j = i; j > s0 && k < budget && !done; ) {
+                j--;
+                if (prm.need_quarter && k == prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
+                k++;
+                consider(Sj[j], s * kWindow + entry_pos(Sj[j]));
+            }
+            // previous window: only positions at distance <= 32768 (matching.rs:102-106,127)
+            if (s > 0 && !done && k < budget) {
+                const uint32_t* Sp = &S[(size_t)(s - 1) * kWindow];
+                const uint16_t* op = &off[(size_t)(s - 1) * kWindow];
+                uint32_t ps = op[h];
+                uint32_t pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
+                for (uint32_t j = pe; j > ps && k < budget && !done; ) {
+                    j--;
+                    uint32_t ql = entry_pos(Sp[j]);
+                    if (ql < pl) break;
+                    if (prm.need_quarter && k == prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
+                    k++;
+                    consider(Sp[j], (s - 1) * kWindow + ql);
+                }
+            }
+            if (prm.need_quarter && k <= prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
+            Mf[p] = finalize_match(best_len, best_dist);
+            if (prm.need_quarter) Mq[p] = finalize_match(q_len, q_dist);
+        }
+    }
+}
+
+// ---- stage 3: speculative segment parse + hand-off verification + repair (k_parse*, k_verify)
+struct SegRec {
+    uint32_t e_pos, e_key, e_tok;   // first iteration at or after the segment start
+    uint32_t x_pos, x_key, x_tok;   // first iteration at or after the segment end (exclusive count)
+    std::vector<uint32_t> toks;
+};
+
+int step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const std::vector<uint32_t>& Mf,
+         const std::vector<uint32_t>& Mq, uint32_t out[2]) {
+    uint32_t p = st.pos;
+    uint32_t mf = (prm.mode != kRle && p + 2 < n && !Mf.empty()) ? Mf[p] : 0;
+    if (prm.mode == kLazy) {
+        uint32_t mq = (prm.need_quarter && p + 2 < n) ? Mq[p] : 0;
+        return lazy_step(st, n, d, mf, mq, prm.lazy, out);
+    }
+    if (prm.mode == kGreedy) return greedy_step(st, n, d, mf, out);
+    return rle_step(st, n, d, out);
+}
+
+void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const std::vector<uint32_t>& Mf,
+                   const std::vector<uint32_t>& Mq, ParseState st, uint32_t a, uint32_t b, SegRec& r) {
+    // runs from `st` until the first iteration position >= b (or the end of data)
+    r.toks.clear();
+    bool have_e = false;
+    uint32_t out[2];
+    while (st.pos < n) {
+        if (!have_e && st.pos >= a) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); have_e = true; }
+        if (st.pos >= b) break;
+        int ne = step(prm, st, n, d, Mf, Mq, out);
+        for (int i = 0; i < ne; i++) r.toks.push_back(out[i]);
+    }
+    if (!have_e) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); }
+    r.x_pos = st.pos; r.x_key = parse_state_key(st); r.x_tok = (uint32_t)r.toks.size();
+}
+
+ParseState state_from(uint32_t pos, uint32_t key) {
+    ParseState s; s.pos = pos; s.prev_len = key & 0x1ff; s.prev_dist = (key >> 9) & 0xffff; s.add = (key >> 25) & 1; s.ign = (key >> 26) & 1;
+    return s;
+}
+
+uint32_t g_last_repairs = 0, g_last_seq_repairs = 0;
+
+void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, const std::vector<uint32_t>& Mf,
+               const std::vector<uint32_t>& Mq, std::vector<uint32_t>& tokens) {
+    tokens.clear();
+    g_last_repairs = g_last_seq_repairs = 0;
+    if (n == 0) return;
+    uint32_t nseg = (n + cfg.pseg - 1) / cfg.pseg;
+    std::vector<SegRec> seg(nseg);
+    for (uint32_t s = 0; s < nseg; s++) {
+        uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+        uint32_t start = a > cfg.warm ? a - cfg.warm : 0;
+        parse_segment(prm, d, n, Mf, Mq, parse_state_init(start), a, b, seg[s]);
+    }
+    auto bad = [&](uint32_t s) {
+        return s > 0 && (seg[s - 1].x_pos != seg[s].e_pos || seg[s - 1].x_key != seg[s].e_key);
+    };
+    for (uint32_t round = 0; round < cfg.rounds; round++) {
+        std::vector<uint32_t> list;
+        for (uint32_t s = 1; s < nseg; s++) if (bad(s)) list.push_back(s);
+        if (list.empty()) break;
+        // all repairs of one round read the *previous* round's exits, like a parallel kernel would
+        std::vector<SegRec> fixed(list.size());
+        for (size_t i = 0; i < list.size(); i++) {
+            uint32_t s = list[i];
+            uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+            parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, fixed[i]);
+        }
+        for (size_t i = 0; i < list.size(); i++) { seg[list[i]] = fixed[i]; g_last_repairs++; }
+    }
+    for (uint32_t s = 1; s < nseg; s++) {   // sequential fallback
+        if (bad(s)) {
+            uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+            SegRec r;
+            parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, r);
+            seg[s] = r; g_last_seq_repairs++;
+        }
+    }
+    for (uint32_t s = 0; s < nseg; s++)
+        tokens.insert(tokens.end(), seg[s].toks.begin() + seg[s].e_tok, seg[s].toks.begin() + seg[s].x_tok);
+}
+
+// ---- stage 4..7: blocks
+void or_bits(std::vector<uint8_t>& out, uint64_t bitpos, uint64_t v, uint32_t nbits) {
+    for (uint32_t i = 0; i < nbits; i++)
+        if ((v >> i) & 1) out[(bitpos + i) >> 3] |= (uint8_t)(1u << ((bitpos + i) & 7));
+}
+
+void emit_blocks(const uint8_t* d, uint32_t n, const std::vector<uint32_t>& tokens, std::vector<uint8_t>& out,
+                 int final_stream) {
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint64_t T = tokens.size();
+    uint32_t nblocks = (uint32_t)(T / kBlockTokens) + 1;
+    std::vector<BlockCodes> bc(nblocks);
+    std::vector<uint64_t> in_start(nblocks + 1, 0);
+    std::vector<uint32_t> scratch(512);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint32_t ll[kNumLL] = {0}, dd[kNumDist] = {0};
+        ll[kEob] = 1;
+        uint64_t bytes = 0;
+        uint64_t t0 = (uint64_t)b * kBlockTokens, t1 = std::min<uint64_t>(T, t0 + kBlockTokens);
+        for (uint64_t t = t0; t < t1; t++) {
+            uint32_t tk = tokens[t];
+            if (tok_dist(tk)) {
+                uint32_t c, ne, ev;
+                length_symbol(tok_lo(tk), c, ne, ev); ll[c]++;
+                dist_symbol(tok_dist(tk), c, ne, ev); dd[c]++;
+            } else ll[tok_lo(tk)]++;
+            bytes += tok_input_len(tk);
+        }
+        in_start[b + 1] = in_start[b] + bytes;
+        build_block_codes(ll, dd, bytes, bc[b], scratch.data());
+    }
+    // sequential bit-offset scan (kernel k_block_scan)
+    std::vector<uint64_t> bitpos(nblocks + 1, 0);
+    std::vector<int> type(nblocks);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint64_t bits;
+        type[b] = choose_block(bc[b], (uint32_t)(bitpos[b] & 7), bits);
+        bitpos[b + 1] = bitpos[b] + bits;
+    }
+    out.assign((size_t)((bitpos[nblocks] + 7) / 8), 0);
+    (void)n;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint64_t bp = bitpos[b];
+        int last = (b + 1 == nblocks) && final_stream;
+        uint64_t t0 = (uint64_t)b * kBlockTokens, t1 = std::min<uint64_t>(T, t0 + kBlockTokens);
+        if (type[b] == kStored) {
+            uint64_t pos = in_start[b], left = bc[b].input_bytes;
+            while (left > 0) {
+                uint32_t chunk = (uint32_t)std::min<uint64_t>(left, kMaxStored);
+                int lastchunk = (left == chunk);
+                or_bits(out, bp, (last && lastchunk) ? 1 : 0, 3); bp += 3;
+                bp = (bp + 7) & ~7ull;
+                or_bits(out, bp, chunk, 16); bp += 16;
+                or_bits(out, bp, (~chunk) & 0xffff, 16); bp += 16;
+                for (uint32_t i = 0; i < chunk; i++) out[(size_t)(bp >> 3) + i] = d[pos + i];
+                bp += 8ull * chunk; pos += chunk; left -= chunk;
+            }
+            continue;
+        }
+        const BlockCodes& c = bc[b];
+        uint8_t fl[288], fd[32]; uint16_t fcl[288], fcd[32];
+        const uint8_t* ll_len = c.ll_len; const uint8_t* d_len = c.d_len;
+        const uint16_t* ll_code = c.ll_code; const uint16_t* d_code = c.d_code;
+        if (type[b] == kFixed) {
+            for (int i = 0; i < 288; i++) fl[i] = (uint8_t)fixed_ll_length(i);
+            for (int i = 0; i < 32; i++) fd[i] = 5;
+            canonical_codes(fl, 288, fcl); canonical_codes(fd, 32, fcd);
+            ll_len = fl; d_len = fd; ll_code = fcl; d_code = fcd;
+            or_bits(out, bp, last ? 3 : 2, 3); bp += 3;
+        } else {
+            or_bits(out, bp, last ? 5 : 4, 3); bp += 3;
+            or_bits(out, bp, c.hlit - 257, 5); bp += 5;
+            or_bits(out, bp, c.hdist - 1, 5); bp += 5;
+            or_bits(out, bp, c.used_hclens - 4, 4); bp += 4;
+            for (uint32_t i = 0; i < c.used_hclens; i++) { or_bits(out, bp, c.cl_len[order[i]], 3); bp += 3; }
+            for (uint32_t i = 0; i < c.n_hdr_sym; i++) {
+                uint32_t sym = c.hdr_sym[i] & 31, rep = c.hdr_sym[i] >> 8;
+                or_bits(out, bp, c.cl_code[sym], c.cl_len[sym]); bp += c.cl_len[sym];
+                if (sym == 16) { or_bits(out, bp, rep - 3, 2); bp += 2; }
+                else if (sym == 17) { or_bits(out, bp, rep - 3, 3); bp += 3; }
+                else if (sym == 18) { or_bits(out, bp, rep - 11, 7); bp += 7; }
+            }
+        }
+        for (uint64_t t = t0; t < t1; t++) {
+            uint32_t tk = tokens[t];
+            if (tok_dist(tk)) {
+                uint32_t cc, ne, ev;
+                length_symbol(tok_lo(tk), cc, ne, ev);
+                or_bits(out, bp, ll_code[cc], ll_len[cc]); bp += ll_len[cc];
+                or_bits(out, bp, ev, ne); bp += ne;
+                dist_symbol(tok_dist(tk), cc, ne, ev);
+                or_bits(out, bp, d_code[cc], d_len[cc]); bp += d_len[cc];
+                or_bits(out, bp, ev, ne); bp += ne;
+            } else {
+                or_bits(out, bp, ll_code[tok_lo(tk)], ll_len[tok_lo(tk)]); bp += ll_len[tok_lo(tk)];
+            }
+        }
+        or_bits(out, bp, ll_code[kEob], ll_len[kEob]); bp += ll_len[kEob];
+        if (bp != bitpos[b + 1]) abort();   // the scan and the packer must agree
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Raw deflate stream for `in` as the GPU pipeline's algorithm produces it.
+int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, uint8_t mtype, uint32_t pseg,
+                  uint32_t warm, uint32_t rounds, uint8_t** out, size_t* out_len, uint32_t* stats /*[4]*/) {
+    Params prm = make_params(checks, lazy, mtype);
+    Cfg cfg{pseg, warm, rounds};
+    std::vector<uint32_t> S, cnt, Mf, Mq, tokens;
+    std::vector<uint16_t> off;
+    if (prm.mode != kRle && prm.checks > 0) {
+        window_sort(in, n, S, off, cnt);
+        match_all(in, n, prm, S, off, cnt, Mf, Mq);
+    }
+    parse_all(prm, cfg, in, n, Mf, Mq, tokens);
+    std::vector<uint8_t> o;
+    emit_blocks(in, n, tokens, o, 1);
+    *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
+    memcpy(*out, o.data(), o.size());
+    *out_len = o.size();
+    if (stats) { stats[0] = g_last_repairs; stats[1] = g_last_seq_repairs; stats[2] = (uint32_t)tokens.size(); stats[3] = 0; }
+    return 0;
+}
+
+// tokens only (for token-level comparison with the oracle)
+int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, uint8_t mtype, uint32_t pseg,
+                uint32_t warm, uint32_t rounds, uint32_t** toks, size_t* ntoks) {
+    Params prm = make_params(checks, lazy, mtype);
+    Cfg cfg{pseg, warm, rounds};
+    std::vector<uint32_t> S, cnt, Mf, Mq, tokens;
+    std::vector<uint16_t> off;
+    if (prm.mode != kRle && prm.checks > 0) {
+        window_sort(in, n, S, off, cnt);
+        match_all(in, n, prm, S, off, cnt, Mf, Mq);
+    }
+    parse_all(prm, cfg, in, n, Mf, Mq, tokens);
+    *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
+    memcpy(*toks, tokens.data(), tokens.size() * 4);
+    *ntoks = tokens.size();
+    return 0;
+}
+
+void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
+    length_symbol(len, o[0], o[1], o[2]);
+    dist_symbol(dist, o[3], o[4], o[5]);
+}
+
+void dflm_free(void* p) { free(p); }
+}
