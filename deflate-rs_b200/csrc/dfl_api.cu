@@ -1,0 +1,596 @@
+// dfl_api.cu -- C ABI of libdeflate_b200.so (see include/deflate_b200.h).
+//
+// Host side of the boundary only: argument marshalling, device buffer ownership, container
+// framing decisions, the streaming handle.  All arithmetic on the data happens in the kernels of
+// dfl_kernels.cu; there is no CPU implementation to fall back to.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/deflate_b200.h"
+#include "dfl_internal.h"
+
+using namespace dfl;
+
+namespace {
+
+thread_local std::string t_cuda_err;
+thread_local int t_profiling = 0;
+thread_local std::vector<std::pair<const char*, float>> t_stage_ms;
+thread_local uint64_t t_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+int cuda_fail(cudaError_t e, const char* where) {
+    t_cuda_err = std::string(where) + ": " + cudaGetErrorString(e);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return DFL_E_NODEVICE;
+    if (e == cudaErrorMemoryAllocation) return DFL_E_NOMEM;
+    return DFL_E_CUDA;
+}
+#define CK(expr)                                           \
+    do {                                                   \
+        cudaError_t e_ = (expr);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
+    } while (0)
+
+int device_count_cached() {
+    static int count = -1;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess) { c = 0; (void)cudaGetLastError(); }
+        count = c;
+    });
+    return count;
+}
+
+template <typename T>
+int dev_alloc(T*& p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    p = reinterpret_cast<T*>(q);
+    return DFL_OK;
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+struct Context {
+    cudaStream_t stream = nullptr;
+    Buffers buf;
+    uint8_t* d_in = nullptr;    // staging for host-buffer calls
+    size_t d_in_cap = 0;
+    uint8_t* d_out = nullptr;
+    size_t d_out_cap = 0;
+    uint32_t* d_tok_in = nullptr;   // staging for dfl_encode_tokens
+    size_t d_tok_cap = 0;
+    DevMeta* h_meta = nullptr;  // pinned
+    bool ok = false;
+
+    int init() {
+        if (ok) return DFL_OK;
+        if (device_count_cached() <= 0) {
+            t_cuda_err = "no CUDA device";
+            return DFL_E_NODEVICE;
+        }
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&h_meta), sizeof(DevMeta)));
+        int rc = dev_alloc(buf.meta, 1);
+        if (rc) return rc;
+        ok = true;
+        return DFL_OK;
+    }
+    void free_buffers() {
+        Buffers& b = buf;
+        dev_free(b.S); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
+        dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
+        dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
+        dev_free(b.seg_cnt); dev_free(b.seg_off); dev_free(b.hist); dev_free(b.cost); dev_free(b.tables);
+        dev_free(b.blk_type); dev_free(b.blk_bit); dev_free(b.blk_in); dev_free(b.adler_part);
+        b.tok = nullptr;
+        b.cap_n = 0;
+        b.cap_quarter = false;
+    }
+    ~Context() {
+        if (!ok) return;
+        free_buffers();
+        dev_free(buf.meta);
+        dev_free(d_in); dev_free(d_out); dev_free(d_tok_in);
+        if (h_meta) cudaFreeHost(h_meta);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // Scratch for inputs of up to n bytes (history + payload).
+    int ensure(size_t n, bool quarter) {
+        Buffers& b = buf;
+        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter)) return DFL_OK;
+        size_t cap = n + n / 8 + 65536;
+        if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
+        if (cap < n) return DFL_E_ARG;
+        cudaStreamSynchronize(stream);
+        quarter = quarter || b.cap_quarter;
+        free_buffers();
+        size_t n_win = (cap + kWindow - 1) / kWindow + 1;
+        size_t n_seg = (cap + kParseSeg - 1) / kParseSeg + 1;
+        size_t n_blk = max_blocks_for((uint32_t)cap) + 1;
+        size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
+        int rc = 0;
+        if ((rc = dev_alloc(b.S, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.Mf, cap))) return rc;
+        if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
+        if ((rc = dev_alloc(b.segtok, n_seg * kParseTokCap))) return rc;
+        if ((rc = dev_alloc(b.seg_e_pos, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_e_key, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_e_tok, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_x_pos, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_x_key, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_x_tok, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_start_pos, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_start_key, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_bad, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_cnt, n_seg))) return rc;
+        if ((rc = dev_alloc(b.seg_off, n_seg))) return rc;
+        if ((rc = dev_alloc(b.hist, n_blk * 320))) return rc;
+        if ((rc = dev_alloc(b.cost, n_blk))) return rc;
+        if ((rc = dev_alloc(b.tables, n_blk))) return rc;
+        if ((rc = dev_alloc(b.blk_type, n_blk))) return rc;
+        if ((rc = dev_alloc(b.blk_bit, n_blk + 1))) return rc;
+        if ((rc = dev_alloc(b.blk_in, n_blk + 1))) return rc;
+        if ((rc = dev_alloc(b.adler_part, 2 * n_chunk))) return rc;
+        b.tok = b.S;   // the candidate lists are dead once k_match has run; the token stream reuses them
+        b.cap_n = cap;
+        b.cap_quarter = quarter;
+        return DFL_OK;
+    }
+    int ensure_stage(uint8_t*& p, size_t& cap, size_t need) {
+        if (cap >= need) return DFL_OK;
+        cudaStreamSynchronize(stream);
+        dev_free(p);
+        cap = 0;
+        size_t c = need + need / 8 + 4096;
+        int rc = dev_alloc(p, c);
+        if (rc) return rc;
+        cap = c;
+        return DFL_OK;
+    }
+};
+
+Context& tls_context() {
+    thread_local std::unique_ptr<Context> ctx;
+    if (!ctx) ctx.reset(new Context());
+    return *ctx;
+}
+
+struct StageTimer {
+    cudaStream_t st;
+    bool on;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    StageTimer(cudaStream_t s, bool enabled) : st(s), on(enabled) {
+        if (on) mark("start");
+    }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    void finish() {
+        if (!on) return;
+        t_stage_ms.clear();
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            t_stage_ms.push_back({names[i], ms});
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+};
+
+uint32_t wrap_header_bytes(int wrap, size_t gz_hdr_len) {
+    if (wrap == DFL_ZLIB) return 2;
+    if (wrap == DFL_GZIP) return gz_hdr_len ? (uint32_t)gz_hdr_len : 10;
+    return 0;
+}
+
+// Runs the kernel pipeline for one piece of a stream.  d_in holds `n` bytes of which the first
+// `begin` are dictionary only.  On success *out_bytes is the number of bytes produced in d_out
+// (container header included when hdr_bytes > 0, trailer included when final && wrap == zlib).
+int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, size_t begin, const dfl_options* opt, int wrap,
+                 uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out, size_t out_cap, size_t* out_bytes,
+                 const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0) {
+    if (n >= 0xfffffff0ull) return DFL_E_UNSUPPORTED;   // 32-bit positions; see DESIGN.md "limits"
+    if (opt->special != 0) return DFL_E_UNSUPPORTED;    // compression_options.rs:52-59: placeholders
+    EncodeJob j;
+    j.d_in = d_in;
+    j.n = (uint32_t)n;
+    j.begin = (uint32_t)begin;
+    j.prm = make_params(opt->max_hash_checks, opt->lazy_if_less_than, opt->matching_type);
+    j.final_block = final_block;
+    j.sync_marker = sync_marker;
+    j.d_out = d_out;
+    j.out_cap = out_cap & ~(size_t)15;
+    j.hdr_bytes = hdr_bytes;
+    j.d_tokens_override = d_tokens_override;
+    j.n_tokens_override = n_tokens_override;
+    j.stop_after_tokens = stop_after_tokens;
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
+
+    int rc = c.ensure(n, j.prm.need_quarter != 0);
+    if (rc) return rc;
+    Buffers& b = c.buf;
+    g_launch_count = 0;
+    StageTimer tm(st, t_profiling != 0);
+    CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
+    const bool need_lz = (d_tokens_override == nullptr);
+    const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
+    if (wrap == DFL_ZLIB && final_block && !stop_after_tokens) {
+        CK(launch_adler32(d_in + begin, n - begin, b, st));
+        tm.mark("adler32");
+    }
+    if (need_match) {
+        CK(launch_window_sort(j, b, st));
+        tm.mark("window_sort");
+        CK(launch_match(j, b, st));
+        tm.mark("match");
+    }
+    if (need_lz) {
+        CK(launch_parse(j, b, st));
+        tm.mark("parse");
+        CK(launch_token_layout(j, b, st));
+        tm.mark("token_layout");
+    }
+    if (!stop_after_tokens) {
+        CK(launch_block_stats(j, b, st));
+        tm.mark("block_stats");
+        CK(launch_block_codes(j, b, st));
+        tm.mark("block_codes");
+        CK(launch_block_scan(j, b, st));
+        tm.mark("block_scan");
+        CK(launch_pack(j, b, st));
+        tm.mark("pack");
+        CK(launch_finalize(j, b, wrap, st));
+        tm.mark("finalize");
+    }
+    CK(cudaMemcpyAsync(c.h_meta, b.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    tm.finish();
+    const DevMeta& m = *c.h_meta;
+    t_counters[0] = m.n_tokens;
+    t_counters[1] = m.n_blocks;
+    t_counters[2] = (n - begin + kParseSeg - 1) / kParseSeg;
+    t_counters[3] = m.n_repaired_par;
+    t_counters[4] = m.n_repaired_seq;
+    t_counters[5] = (uint64_t)g_launch_count;
+    t_counters[6] = m.n_stored;
+    t_counters[7] = m.n_fixed;
+    if (out_bytes) *out_bytes = (size_t)m.out_bytes;
+    if (m.err == 100) return DFL_E_OVERFLOW;
+    if (m.err != 0) {
+        t_cuda_err = "device invariant violated, code " + std::to_string(m.err);
+        return DFL_E_INTERNAL;
+    }
+    return DFL_OK;
+}
+
+bool valid_wrap(int wrap) { return wrap == DFL_RAW || wrap == DFL_ZLIB || wrap == DFL_GZIP; }
+
+}  // namespace
+
+// ============================================================================ misc
+extern "C" const char* dfl_strerror(int status) {
+    switch (status) {
+        case DFL_OK: return "ok";
+        case DFL_AGAIN: return "internal buffer full, call again";
+        case DFL_E_ARG: return "invalid argument";
+        case DFL_E_NOMEM: return "out of (device) memory";
+        case DFL_E_CUDA: return "CUDA error";
+        case DFL_E_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case DFL_E_OVERFLOW: return "output buffer too small";
+        case DFL_E_STATE: return "encoder is in the wrong state for this call";
+        case DFL_E_UNSUPPORTED: return "not supported";
+        case DFL_E_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+extern "C" const char* dfl_last_cuda_error(void) { return t_cuda_err.c_str(); }
+extern "C" int dfl_version(void) { return DFL_VERSION; }
+extern "C" int dfl_device_count(void) { return device_count_cached(); }
+
+extern "C" int dfl_options_preset(int preset, dfl_options* out) {
+    if (!out) return DFL_E_ARG;
+    switch (preset) {   // compression_options.rs:14-20,126-178
+        case DFL_PRESET_FAST: *out = {1, 0, 0, 0}; return DFL_OK;
+        case DFL_PRESET_DEFAULT: *out = {128, 32, 1, 0}; return DFL_OK;
+        case DFL_PRESET_BEST: *out = {1768, 128, 1, 0}; return DFL_OK;
+        case DFL_PRESET_HUFFMAN_ONLY: *out = {0, 0, 0, 0}; return DFL_OK;
+        case DFL_PRESET_RLE: *out = {0, 0, 1, 0}; return DFL_OK;
+        default: return DFL_E_ARG;
+    }
+}
+
+extern "C" size_t dfl_bound(size_t n, int wrap) {
+    // Every block costs at most its stored form (+1 bit of slack), 5 bytes per 32767-byte chunk,
+    // at most n/31744 + 1 blocks, plus the largest container (gzip: 10 + 8) and write slack.
+    return n + 5 * (n / 32767 + 1) + 6 * (n / 31744 + 2) + 64 + (wrap == DFL_GZIP ? 320 : 0);
+}
+
+extern "C" int dfl_set_profiling(int enabled) {
+    int old = t_profiling;
+    t_profiling = enabled;
+    return old;
+}
+extern "C" int dfl_last_stage_times(const char** names, float* ms, int cap) {
+    int n = (int)t_stage_ms.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (names) names[i] = t_stage_ms[i].first;
+        if (ms) ms[i] = t_stage_ms[i].second;
+    }
+    return n;
+}
+extern "C" int dfl_last_counters(uint64_t* out, int cap) {
+    for (int i = 0; i < 8 && i < cap; i++) out[i] = t_counters[i];
+    return 8;
+}
+
+// ============================================================================ one-shot
+extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
+                                   size_t gz_hdr_len, void* d_out, size_t out_cap, size_t* out_len, void* stream) {
+    if (!opt || !d_out || !out_len || (!d_in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
+    if (wrap == DFL_GZIP) return DFL_E_UNSUPPORTED;   // CRC-32 kernel: SURVEY 8(f) rank 2
+    (void)gz_hdr; (void)gz_hdr_len;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
+    return run_pipeline(c, st, reinterpret_cast<const uint8_t*>(d_in), n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1,
+                        0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+}
+
+extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
+                            size_t gz_hdr_len, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!opt || !out || !out_len || (!in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
+    if (wrap == DFL_GZIP) return DFL_E_UNSUPPORTED;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
+    size_t bound = dfl_bound(n, wrap);
+    if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound + 64))) return rc;
+    if (n) CK(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, c.stream));
+    size_t produced = 0;
+    rc = run_pipeline(c, c.stream, c.d_in, n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1, 0, c.d_out, c.d_out_cap,
+                      &produced);
+    if (rc) return rc;
+    *out_len = produced;
+    if (produced > out_cap) return DFL_E_OVERFLOW;
+    CK(cudaMemcpyAsync(out, c.d_out, produced, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return DFL_OK;
+}
+
+extern "C" int dfl_adler32_device(const void* d_in, size_t n, uint32_t* adler, void* stream) {
+    if (!adler || (!d_in && n)) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.ensure(n ? n : 1, false))) return rc;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
+    CK(launch_adler32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
+    CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *adler = c.h_meta->adler;
+    return DFL_OK;
+}
+
+extern "C" int dfl_encode_tokens(const uint8_t* in, size_t n, const uint32_t* tokens, size_t n_tokens, uint8_t* out,
+                                 size_t out_cap, size_t* out_len) {
+    if (!out || !out_len || (!in && n) || (!tokens && n_tokens) || n_tokens > n) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
+    if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, dfl_bound(n, DFL_RAW) + 64))) return rc;
+    if (c.d_tok_cap < n_tokens + 16) {
+        dev_free(c.d_tok_in);
+        c.d_tok_cap = 0;
+        if ((rc = dev_alloc(c.d_tok_in, n_tokens + 4096))) return rc;
+        c.d_tok_cap = n_tokens + 4096;
+    }
+    if (n) CK(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, c.stream));
+    if (n_tokens) CK(cudaMemcpyAsync(c.d_tok_in, tokens, n_tokens * 4, cudaMemcpyHostToDevice, c.stream));
+    dfl_options opt = {0, 0, 0, 0};
+    size_t produced = 0;
+    rc = run_pipeline(c, c.stream, c.d_in, n, 0, &opt, DFL_RAW, 0, 1, 0, c.d_out, c.d_out_cap, &produced, c.d_tok_in, n_tokens);
+    if (rc) return rc;
+    *out_len = produced;
+    if (produced > out_cap) return DFL_E_OVERFLOW;
+    CK(cudaMemcpyAsync(out, c.d_out, produced, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return DFL_OK;
+}
+
+extern "C" int dfl_lz77_tokens(const uint8_t* in, size_t n, const dfl_options* opt, uint32_t* tokens, size_t tokens_cap,
+                               size_t* n_tokens) {
+    if (!opt || !n_tokens || (!in && n) || (!tokens && tokens_cap)) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
+    if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, 4096))) return rc;
+    if (n) CK(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, c.stream));
+    size_t produced = 0;
+    rc = run_pipeline(c, c.stream, c.d_in, n, 0, opt, DFL_RAW, 0, 1, 0, c.d_out, c.d_out_cap, &produced, nullptr, 0, 1);
+    if (rc) return rc;
+    size_t T = (size_t)c.h_meta->n_tokens;
+    *n_tokens = T;
+    if (T > tokens_cap) return DFL_E_OVERFLOW;
+    if (T) CK(cudaMemcpyAsync(tokens, c.buf.tok, T * 4, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return DFL_OK;
+}
+
+// ============================================================================ streaming
+struct dfl_encoder {
+    dfl_options opt;
+    int wrap;
+    Context ctx;                 // per-handle stream and device buffers
+    std::vector<uint8_t> data;   // retained dictionary (<= 32 KiB) followed by unencoded input
+    size_t pending_from = 0;     // data[pending_from..] has not been encoded yet
+    std::vector<uint8_t> out;    // produced bytes not yet handed to the caller
+    size_t out_pos = 0;
+    bool header_written = false;
+    bool finished = false;
+    uint32_t adler = 1;          // Adler-32 of everything encoded so far (device-computed per piece)
+    size_t adler_upto = 0;       // data[pending_from..adler_upto) is already folded into `adler`
+    uint64_t total_in = 0;
+};
+
+namespace {
+
+// Adler-32 of data[from..to) on the device, folded into e->adler.
+int encoder_fold_checksum(dfl_encoder* e, size_t to) {
+    if (e->wrap != DFL_ZLIB) return DFL_OK;
+    size_t from = e->adler_upto < e->pending_from ? e->pending_from : e->adler_upto;
+    if (to <= from) return DFL_OK;
+    Context& c = e->ctx;
+    int rc = c.init();
+    if (rc) return rc;
+    size_t len = to - from;
+    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, e->data.size() + 64))) return rc;
+    if ((rc = c.ensure(len, false))) return rc;
+    CK(cudaMemcpyAsync(c.d_in, e->data.data() + from, len, cudaMemcpyHostToDevice, c.stream));
+    CK(launch_adler32(c.d_in, len, c.buf, c.stream));
+    CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    e->adler = adler32_combine(e->adler, c.h_meta->adler, len);   // arithmetic on two device results
+    e->adler_upto = to;
+    return DFL_OK;
+}
+
+int encoder_emit(dfl_encoder* e, int mode) {
+    Context& c = e->ctx;
+    int rc = c.init();
+    if (rc) return rc;
+    const size_t n = e->data.size();
+    const size_t begin = e->pending_from;
+    if ((rc = encoder_fold_checksum(e, n))) return rc;
+    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
+    size_t bound = dfl_bound(n - begin, e->wrap) + 64;
+    if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
+    if (n) CK(cudaMemcpyAsync(c.d_in, e->data.data(), n, cudaMemcpyHostToDevice, c.stream));
+    uint32_t hdr = 0;
+    if (!e->header_written) hdr = wrap_header_bytes(e->wrap, 0);
+    size_t produced = 0;
+    // The trailer is appended here from the running checksum, so the kernels see wrap == RAW
+    // unless the header still has to be written.
+    rc = run_pipeline(c, c.stream, c.d_in, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr, mode == DFL_FLUSH_FINISH ? 1 : 0,
+                      mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, &produced);
+    if (rc) return rc;
+    size_t stream_part = (size_t)c.h_meta->stream_bytes + hdr;
+    size_t old = e->out.size();
+    e->out.resize(old + stream_part);
+    if (stream_part) CK(cudaMemcpyAsync(e->out.data() + old, c.d_out, stream_part, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    e->header_written = true;
+    if (mode == DFL_FLUSH_FINISH) {
+        if (e->wrap == DFL_ZLIB) {   // lib.rs:192-196 / writer.rs:235-245: Adler-32, big endian
+            uint32_t a = e->adler;
+            uint8_t t[4] = {(uint8_t)(a >> 24), (uint8_t)(a >> 16), (uint8_t)(a >> 8), (uint8_t)a};
+            e->out.insert(e->out.end(), t, t + 4);
+        }
+        e->finished = true;
+    }
+    // keep the last 32 KiB as dictionary for the next piece
+    if (n > kWindow) {
+        e->data.erase(e->data.begin(), e->data.begin() + (n - kWindow));
+    }
+    e->pending_from = e->data.size();
+    e->adler_upto = e->pending_from;
+    return DFL_OK;
+}
+
+}  // namespace
+
+extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const uint8_t* gz_hdr, size_t gz_hdr_len) {
+    (void)gz_hdr; (void)gz_hdr_len;
+    if (!opt || !valid_wrap(wrap) || wrap == DFL_GZIP) return nullptr;
+    dfl_encoder* e = new (std::nothrow) dfl_encoder();
+    if (!e) return nullptr;
+    e->opt = *opt;
+    e->wrap = wrap;
+    return e;
+}
+
+extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, size_t* consumed) {
+    if (!e || (!buf && n)) return DFL_E_ARG;
+    if (e->finished) return DFL_E_STATE;
+    if (e->data.size() + n >= 0xfff00000ull) return DFL_E_UNSUPPORTED;
+    try {
+        e->data.insert(e->data.end(), buf, buf + n);
+    } catch (const std::bad_alloc&) {
+        return DFL_E_NOMEM;
+    }
+    e->total_in += n;
+    if (consumed) *consumed = n;
+    return DFL_OK;
+}
+
+extern "C" int dfl_encoder_flush(dfl_encoder* e, int mode) {
+    if (!e || (mode != DFL_FLUSH_SYNC && mode != DFL_FLUSH_FINISH)) return DFL_E_ARG;
+    if (e->finished) return mode == DFL_FLUSH_FINISH ? DFL_OK : DFL_E_STATE;
+    return encoder_emit(e, mode);
+}
+
+extern "C" int dfl_encoder_take_output(dfl_encoder* e, const uint8_t** p, size_t* len) {
+    if (!e || !p || !len) return DFL_E_ARG;
+    *p = e->out.data() + e->out_pos;
+    *len = e->out.size() - e->out_pos;
+    return DFL_OK;
+}
+
+extern "C" void dfl_encoder_advance_output(dfl_encoder* e, size_t n) {
+    if (!e) return;
+    e->out_pos += n;
+    if (e->out_pos >= e->out.size()) {
+        e->out.clear();
+        e->out_pos = 0;
+    }
+}
+
+extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
+    if (!e || e->wrap != DFL_ZLIB) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
+    if (encoder_fold_checksum(e, e->data.size()) != DFL_OK) return 0;
+    return e->adler;
+}
+
+extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t gz_hdr_len) {
+    (void)gz_hdr; (void)gz_hdr_len;
+    if (!e) return DFL_E_ARG;
+    if (!e->finished) {
+        int rc = encoder_emit(e, DFL_FLUSH_FINISH);   // output_all() (writer.rs:112-115,218-223)
+        if (rc) return rc;
+    }
+    e->data.clear();
+    e->pending_from = 0;
+    e->header_written = false;
+    e->finished = false;
+    e->adler = 1;
+    e->adler_upto = 0;
+    e->total_in = 0;
+    return DFL_OK;
+}
+
+extern "C" void dfl_encoder_free(dfl_encoder* e) { delete e; }

@@ -1,0 +1,116 @@
+// dfl_internal.h -- private interface between the C-ABI layer (dfl_api.cu) and the kernels
+// (dfl_kernels.cu).  Not installed; include/deflate_b200.h is the public boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dfl_core.h"
+
+namespace dfl {
+
+// Tunables of the parse stage (see DESIGN.md "parse").
+constexpr uint32_t kParseSeg = 8192;     // positions owned by one parse thread
+constexpr uint32_t kParseWarm = 1024;    // speculative warm-up before the segment start
+constexpr uint32_t kParseTokCap = kParseSeg + kParseWarm + 264;   // tokens one thread can emit
+constexpr uint32_t kRepairRounds = 3;    // parallel repair rounds before the sequential fallback
+
+// Device-resident bookkeeping of one encode call (one instance per context).
+struct DevMeta {
+    unsigned long long n_tokens;
+    unsigned long long stream_bits;   // bits of the raw deflate stream (incl. sync marker)
+    unsigned long long stream_bytes;  // ceil(stream_bits / 8)
+    unsigned long long out_bytes;     // container size: header + stream + trailer
+    uint32_t n_blocks;
+    uint32_t adler;
+    uint32_t n_bad;                   // segments whose hand-off check failed in the latest verify
+    uint32_t n_repaired_par;
+    uint32_t n_repaired_seq;
+    uint32_t n_stored;
+    uint32_t n_fixed;
+    uint32_t err;                     // nonzero = internal invariant violated on the device
+};
+
+// Per-block cost summary (SoA-friendly, read by the bit-offset scan).
+struct BlockCost {
+    unsigned long long dynamic_cost, static_cost, stored_cost;   // reference's estimates
+    unsigned long long dynamic_bits, fixed_bits;                  // bits actually emitted (body)
+    unsigned long long input_bytes;
+    uint32_t tiny;
+    uint32_t hdr_bits;   // dynamic header bits after the 3-bit block marker
+};
+
+// Per-block code tables and header symbol stream (written by k_block_codes, read by k_pack).
+struct BlockTables {
+    uint16_t ll_code[288];
+    uint16_t d_code[32];
+    uint16_t cl_code[19];
+    uint16_t hdr_sym[322];
+    uint8_t ll_len[288];
+    uint8_t d_len[32];
+    uint8_t cl_len[19];
+    uint8_t pad_;
+    uint32_t n_hdr_sym, hlit, hdist, used_hclens;
+};
+
+struct Buffers {   // device scratch of one context, grown on demand
+    uint32_t* S = nullptr;          // sorted candidate entries, n_windows * 32768
+    uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
+    uint32_t* Mf = nullptr;         // per-position match (full chain budget)
+    uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
+    uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * kParseTokCap
+    uint32_t* seg_e_pos = nullptr;  // hand-off records (SoA), n_pseg each
+    uint32_t* seg_e_key = nullptr;
+    uint32_t* seg_e_tok = nullptr;
+    uint32_t* seg_x_pos = nullptr;
+    uint32_t* seg_x_key = nullptr;
+    uint32_t* seg_x_tok = nullptr;
+    uint32_t* seg_start_pos = nullptr;   // repair start states
+    uint32_t* seg_start_key = nullptr;
+    uint8_t* seg_bad = nullptr;
+    uint32_t* seg_cnt = nullptr;    // valid tokens per segment
+    unsigned long long* seg_off = nullptr;   // exclusive prefix of seg_cnt
+    uint32_t* tok = nullptr;        // compacted token stream
+    uint32_t* hist = nullptr;       // per block 320 counters (286 ll + 30 dist + pad)
+    BlockCost* cost = nullptr;
+    BlockTables* tables = nullptr;
+    int* blk_type = nullptr;
+    unsigned long long* blk_bit = nullptr;   // bit offset of each block in the stream
+    unsigned long long* blk_in = nullptr;    // input offset of each block
+    unsigned long long* adler_part = nullptr;// per chunk (A, B) sums
+    DevMeta* meta = nullptr;
+    size_t cap_n = 0;               // input size the buffers were sized for
+    bool cap_quarter = false;
+};
+
+struct EncodeJob {
+    const uint8_t* d_in;     // device input (history + payload)
+    uint32_t n;              // bytes available at d_in
+    uint32_t begin;          // first byte to encode (bytes before it are dictionary only)
+    Params prm;
+    int final_block;         // set BFINAL on the last block (Flush::Finish)
+    int sync_marker;         // append an empty stored block (Flush::Sync)
+    uint8_t* d_out;          // device output, zero-filled by the pipeline
+    size_t out_cap;
+    uint32_t hdr_bytes;      // container header already accounted for at the start of d_out
+    const uint32_t* d_tokens_override;   // test hook: skip the LZ77 stage, use these tokens
+    unsigned long long n_tokens_override;
+    int stop_after_tokens;   // test hook: run only the LZ77 stage
+};
+
+constexpr uint32_t kAdlerChunk = 1u << 16;
+
+// Stage launchers (dfl_kernels.cu).  All asynchronous on `st`.
+cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_block_scan(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_pack(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_adler32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st);
+cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st);
+uint32_t max_blocks_for(uint32_t n_payload);
+extern int g_launch_count;   // kernels launched since the last reset (host-side counter)
+
+}  // namespace dfl

@@ -1,0 +1,989 @@
+// dfl_kernels.cu -- sm_100a kernels of the DEFLATE encode pipeline.
+//
+// Stage order (one encode call; all launches on one stream, no host round trips):
+//   k_window_sort   per 32 KiB window: stable counting sort of positions by the reference's 15-bit
+//                   3-byte hash -> contiguous most-recent-first candidate lists (replaces the
+//                   head/prev chains of chained_hash_table.rs)
+//   k_match         per sorted entry: longest match among the first `max_hash_checks` candidates,
+//                   nearest wins ties (matching.rs:87-166), too-far rule (lz77.rs:274-278)
+//   k_parse*        greedy / lazy / RLE token selection (lz77.rs:305-547, rle.rs:23-71) run
+//                   speculatively per 8 KiB segment, hand-offs verified, mismatches re-parsed
+//   k_seg_scan, k_compact   token stream layout
+//   k_block_stats   286+30 bin histograms per 31744-token block (output_writer.rs:19,47-65)
+//   k_block_codes   code lengths, canonical codes, header RLE, costs (huffman_lengths.rs:167-287)
+//   k_block_scan    block type per bit alignment + exclusive scan of block bit lengths
+//   k_pack          Huffman-code the tokens and scatter the bits (encoder_state.rs:58-105,
+//                   bitstream.rs:76-86, stored_block.rs:13-40)
+//   k_adler32*      Adler-32 of the input (checksum.rs:33-57), k_finalize container bytes
+#include <stdio.h>
+
+#include "dfl_internal.h"
+
+namespace dfl {
+
+int g_launch_count = 0;
+
+#define DFL_LAUNCH_CHECK()                         \
+    do {                                           \
+        g_launch_count++;                          \
+        cudaError_t e__ = cudaGetLastError();      \
+        if (e__ != cudaSuccess) return e__;        \
+    } while (0)
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if ((int)lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one value per thread across the CTA (blockDim.x multiple of 32, <= 1024).
+// `total` receives the CTA-wide sum.  `ws` is 33 words of shared scratch.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* ws, uint32_t& total) {
+    uint32_t incl = warp_incl_scan(v);
+    uint32_t nw = blockDim.x >> 5;
+    if (lane_id() == 31) ws[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        uint32_t x = lane_id() < nw ? ws[lane_id()] : 0;
+        uint32_t xi = warp_incl_scan(x);
+        ws[lane_id()] = xi - x;
+        if (lane_id() == 31) ws[32] = xi;
+    }
+    __syncthreads();
+    uint32_t r = ws[warp_id()] + incl - v;
+    total = ws[32];
+    __syncthreads();
+    return r;
+}
+
+// Unaligned little-endian 32-bit read from a shared byte array viewed as words.
+__device__ __forceinline__ uint32_t lds32(const uint32_t* w, uint32_t byte_idx) {
+    uint32_t a = byte_idx >> 2;
+    uint32_t lo = w[a], hi = w[a + 1];
+    return __funnelshift_r(lo, hi, (byte_idx & 3u) * 8u);
+}
+
+// Copy in[src_lo .. src_lo+count) into shared bytes, zero-filling positions outside [0, n).
+__device__ __forceinline__ void stage_bytes(uint8_t* dst, const uint8_t* __restrict__ in, long long src_lo,
+                                            uint32_t count, uint32_t n) {
+    // count and dst are multiples of 16; src_lo is a multiple of 16 (windows are 32 KiB aligned).
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+    for (uint32_t i = threadIdx.x * 16u; i < count; i += blockDim.x * 16u) {
+        long long a = src_lo + (long long)i;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (a >= 0 && a + 16 <= (long long)n && aligned) {
+            v = __ldg(reinterpret_cast<const uint4*>(in + a));
+        } else if (a + 16 > 0 && a < (long long)n) {
+            uint8_t tmp[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                long long x = a + k;
+                tmp[k] = (x >= 0 && x < (long long)n) ? in[x] : (uint8_t)0;
+            }
+            v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
+            v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
+            v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
+            v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+        }
+        *reinterpret_cast<uint4*>(dst + i) = v;
+    }
+}
+
+__host__ __device__ inline uint32_t window_count(uint32_t n, uint32_t w) {
+    // number of hashable positions (p + 2 < n) in window w
+    uint32_t hashable = n >= 2u ? n - 2u : 0u;
+    uint32_t base = w * kWindow;
+    if (hashable <= base) return 0u;
+    uint32_t c = hashable - base;
+    return c < kWindow ? c : kWindow;
+}
+
+// =====================================================================================
+// k_window_sort: one CTA per 32 KiB window.
+//   shared: 32 KiB + 16 of input bytes, 64 KiB of u16 counters/cursors (viewed as u32 pairs)
+// =====================================================================================
+constexpr uint32_t kSortThreads = 256;
+constexpr uint32_t kSortStage = kWindow + 16;
+constexpr uint32_t kSortSmem = kSortStage + kWindow * 2 + 64;
+
+__global__ void __launch_bounds__(kSortThreads) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
+                                                              uint32_t w_first, uint32_t* __restrict__ S,
+                                                              uint16_t* __restrict__ off) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* sdata = smem;                                             // kSortStage bytes
+    uint32_t* hist32 = reinterpret_cast<uint32_t*>(smem + kSortStage); // 16384 words = 32768 u16
+    uint16_t* cur16 = reinterpret_cast<uint16_t*>(hist32);
+    uint32_t* wtot = hist32 + kWindow / 2;                             // 8 warp totals (+ spare)
+
+    const uint32_t w = w_first + blockIdx.x;
+    const uint32_t base = w * kWindow;
+    const uint32_t cnt = window_count(n, w);
+
+    stage_bytes(sdata, in, (long long)base, kSortStage, n);
+    for (uint32_t i = threadIdx.x; i < kWindow / 2; i += blockDim.x) hist32[i] = 0;
+    __syncthreads();
+
+    // phase 1: bucket sizes (two u16 counters per word; a counter never exceeds 32768)
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        uint32_t h = hash3(sdata[i], sdata[i + 1], sdata[i + 2]);
+        atomicAdd(&hist32[h >> 1], 1u << ((h & 1u) * 16u));
+    }
+    __syncthreads();
+
+    // phase 2: exclusive scan of the 32768 counters; each warp owns 4096 bins (2048 words)
+    const uint32_t nwarps = kSortThreads / 32;   // 8
+    const uint32_t words_per_warp = (kWindow / 2) / nwarps;
+    {
+        uint32_t s = 0;
+        for (uint32_t k = lane_id(); k < words_per_warp; k += 32) {
+            uint32_t v = hist32[warp_id() * words_per_warp + k];
+            s += (v & 0xffffu) + (v >> 16);
+        }
+        s = warp_incl_scan(s);
+        if (lane_id() == 31) wtot[warp_id()] = s;
+    }
+    __syncthreads();
+    uint32_t running = 0;
+    for (uint32_t k = 0; k < warp_id(); k++) running += wtot[k];
+    __syncthreads();   // wtot lives right after the counters; keep it intact until everyone has read it
+    uint32_t* off32 = reinterpret_cast<uint32_t*>(off + (size_t)w * kWindow);
+    for (uint32_t k = 0; k < words_per_warp; k += 32) {
+        uint32_t idx = warp_id() * words_per_warp + k + lane_id();
+        uint32_t v = hist32[idx];
+        uint32_t c0 = v & 0xffffu, c1 = v >> 16;
+        uint32_t incl = warp_incl_scan(c0 + c1);
+        uint32_t o0 = running + incl - (c0 + c1);
+        uint32_t o1 = o0 + c0;
+        uint32_t packed = o0 | (o1 << 16);
+        hist32[idx] = packed;
+        off32[idx] = packed;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncthreads();
+
+    // phase 3: ordered scatter by one warp (order inside a bucket == position order)
+    if (warp_id() == 0) {
+        uint32_t* Sw = S + (size_t)w * kWindow;
+        for (uint32_t r = 0; r < cnt; r += 32) {
+            uint32_t i = r + lane_id();
+            bool act = i < cnt;
+            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (act) { b0 = sdata[i]; b1 = sdata[i + 1]; b2 = sdata[i + 2]; b3 = sdata[i + 3]; }
+            uint32_t h = act ? hash3(b0, b1, b2) : (0x10000u + lane_id());
+            uint32_t peers = __match_any_sync(0xffffffffu, h);
+            uint32_t rank = __popc(peers & ((1u << lane_id()) - 1u));
+            uint32_t npeers = __popc(peers);
+            uint32_t dst = act ? cur16[h] : 0u;
+            __syncwarp();
+            if (act && rank == npeers - 1u) cur16[h] = (uint16_t)(dst + npeers);
+            __syncwarp();
+            if (act) Sw[dst + rank] = pack_entry(i, b0, b1, b3);
+        }
+    }
+}
+
+// =====================================================================================
+// k_match: one CTA per window; a thread walks the candidate list of one sorted entry.
+//   shared: the previous and the current window plus 258 bytes of look-ahead
+// =====================================================================================
+constexpr uint32_t kMatchThreads = 512;
+constexpr uint32_t kMatchStage = 2 * kWindow + 272;   // multiple of 16
+constexpr uint32_t kMatchSmem = kMatchStage + 16;
+
+__device__ __forceinline__ uint32_t smem_common_prefix(const uint32_t* w, uint32_t a, uint32_t b, uint32_t from,
+                                                       uint32_t maxl) {
+    uint32_t l = from;
+    while (l < maxl) {
+        uint32_t x = lds32(w, a + l) ^ lds32(w, b + l);
+        if (x) { l += (__ffs((int)x) - 1) >> 3; break; }
+        l += 4;
+    }
+    return l < maxl ? l : maxl;
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 2)
+k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
+        const uint32_t* __restrict__ S, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
+        uint32_t* __restrict__ Mq) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
+    const uint32_t w = w_first + blockIdx.x;
+    const uint32_t base = w * kWindow;
+    const uint32_t cnt = window_count(n, w);
+    // shared index of absolute position a is a - base + 32768
+    stage_bytes(smem, in, (long long)base - (long long)kWindow, kMatchStage, n);
+    __syncthreads();
+
+    const uint32_t* Sj = S + (size_t)w * kWindow;
+    const uint16_t* oj = off + (size_t)w * kWindow;
+    const uint32_t* Sp = w > 0 ? S + (size_t)(w - 1) * kWindow : nullptr;
+    const uint16_t* op = w > 0 ? off + (size_t)(w - 1) * kWindow : nullptr;
+    const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
+    const uint32_t budget = prm.checks;
+    const uint32_t qbudget = prm.checks_quarter;
+    const bool need_q = prm.need_quarter != 0;
+
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t e = Sj[i];
+        const uint32_t pl = entry_pos(e);
+        const uint32_t p = base + pl;
+        if (p < begin) continue;
+        const uint32_t sp = pl + kWindow;
+        const uint32_t w0 = lds32(sw, sp);
+        const uint32_t h = hash3(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+        const uint32_t my_filter = entry_filter(e);
+        const uint32_t my_tag = entry_tag(e);
+        const uint32_t maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+        uint32_t best_len = 1, best_dist = 0, q_len = 0, q_dist = 0, k = 0;
+        bool done = false;
+
+#define DFL_CONSIDER(CE, SQ)                                                                      \
+    do {                                                                                          \
+        const uint32_t ce__ = (CE);                                                               \
+        if (entry_tag(ce__) == my_tag && !(best_len >= 3u && maxl > 3u && entry_filter(ce__) != my_filter) && \
+            best_len < maxl) {                                                                    \
+            const uint32_t sq__ = (SQ);                                                           \
+            if (smem[sq__ + best_len] == smem[sp + best_len]) {                                   \
+                uint32_t l__ = smem_common_prefix(sw, sp, sq__, 3u, maxl);                        \
+                if (l__ > best_len) {                                                             \
+                    best_len = l__;                                                               \
+                    best_dist = sp - sq__;                                                        \
+                    if (l__ == maxl) done = true;                                                 \
+                }                                                                                 \
+            }                                                                                     \
+        }                                                                                         \
+    } while (0)
+
+        const uint32_t s0 = oj[h];
+        uint32_t j = i;
+        while (j > s0 && k < budget && !done) {
+            j--;
+            if (need_q && k == qbudget) { q_len = best_len; q_dist = best_dist; }
+            k++;
+            const uint32_t ce = Sj[j];
+            DFL_CONSIDER(ce, entry_pos(ce) + kWindow);
+        }
+        if (w > 0 && !done && k < budget) {
+            const uint32_t ps = op[h];
+            const uint32_t pe = (h + 1u < kWindow) ? op[h + 1u] : cnt_prev;
+            j = pe;
+            while (j > ps && k < budget && !done) {
+                j--;
+                const uint32_t ce = Sp[j];
+                const uint32_t ql = entry_pos(ce);
+                if (ql < pl) break;              // distance would exceed 32768 (matching.rs:102-106,127)
+                if (need_q && k == qbudget) { q_len = best_len; q_dist = best_dist; }
+                k++;
+                DFL_CONSIDER(ce, ql);
+            }
+        }
+#undef DFL_CONSIDER
+        if (need_q && k <= qbudget) { q_len = best_len; q_dist = best_dist; }
+        Mf[p] = finalize_match(best_len, best_dist);
+        if (need_q) Mq[p] = finalize_match(q_len, q_dist);
+    }
+}
+
+// =====================================================================================
+// parse
+// =====================================================================================
+__device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key) {
+    ParseState s;
+    s.pos = pos; s.prev_len = key & 0x1ffu; s.prev_dist = (key >> 9) & 0xffffu; s.add = (key >> 25) & 1u; s.ign = (key >> 26) & 1u;
+    return s;
+}
+
+struct ParseArgs {
+    const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
+    const uint32_t* Mf; const uint32_t* Mq;
+    uint32_t* segtok;
+    uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
+    uint32_t n_seg;
+};
+
+// Runs the reference's token selection from `st` until the first iteration position >= b.
+__device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
+    uint32_t* tk = A.segtok + (size_t)s * kParseTokCap;
+    uint32_t nt = 0;
+    bool have_e = false;
+    uint32_t epos = 0, ekey = 0, etok = 0;
+    const uint32_t n = A.n;
+    const int mode = A.prm.mode;
+    const bool has_m = (mode != kRle) && (A.prm.checks > 0);
+    uint32_t out[2];
+    while (st.pos < n) {
+        if (!have_e && st.pos >= a) { epos = st.pos; ekey = parse_state_key(st); etok = nt; have_e = true; }
+        if (st.pos >= b) break;
+        const uint32_t p = st.pos;
+        int ne;
+        if (mode == kLazy) {
+            uint32_t mf = 0, mq = 0;
+            if (p + 2u < n && !st.ign) {
+                if (st.prev_len >= 32u) mq = A.prm.need_quarter ? A.Mq[p] : 0u;
+                else mf = A.Mf[p];
+            }
+            ne = lazy_step(st, n, A.in, mf, mq, A.prm.lazy, out);
+        } else if (mode == kGreedy) {
+            uint32_t mf = (has_m && p + 2u < n) ? A.Mf[p] : 0u;
+            ne = greedy_step(st, n, A.in, mf, out);
+        } else {
+            // rle.rs runs over the buffer from its first byte; relative to `begin` for a resumed stream
+            ne = rle_step(st, n, A.in, out);
+        }
+        if (nt + (uint32_t)ne <= kParseTokCap) {
+            if (ne > 0) tk[nt] = out[0];
+            if (ne > 1) tk[nt + 1] = out[1];
+        }
+        nt += (uint32_t)ne;
+    }
+    if (!have_e) { epos = st.pos; ekey = parse_state_key(st); etok = nt; }
+    A.e_pos[s] = epos; A.e_key[s] = ekey; A.e_tok[s] = etok;
+    A.x_pos[s] = st.pos; A.x_key[s] = parse_state_key(st); A.x_tok[s] = nt;
+}
+
+__global__ void __launch_bounds__(128) k_parse_spec(ParseArgs A) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_seg) return;
+    uint32_t a = A.begin + s * kParseSeg;
+    uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
+    uint32_t start = (s == 0) ? A.begin : (a - A.begin > kParseWarm ? a - kParseWarm : A.begin);
+    parse_segment(A, s, parse_state_init(start), a, b);
+}
+
+__global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* start_pos,
+                                                      uint32_t* start_key, DevMeta* meta) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_seg) return;
+    uint8_t is_bad = 0;
+    if (s > 0) {
+        uint32_t xp = A.x_pos[s - 1], xk = A.x_key[s - 1];
+        if (xp != A.e_pos[s] || xk != A.e_key[s]) {
+            is_bad = 1;
+            start_pos[s] = xp;
+            start_key[s] = xk;
+            atomicAdd(&meta->n_bad, 1u);
+        }
+    }
+    bad[s] = is_bad;
+}
+
+__global__ void __launch_bounds__(128) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
+                                                      const uint32_t* start_key, DevMeta* meta) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_seg || !bad[s]) return;
+    uint32_t a = A.begin + s * kParseSeg;
+    uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
+    parse_segment(A, s, state_from_key(start_pos[s], start_key[s]), a, b);
+    atomicAdd(&meta->n_repaired_par, 1u);
+}
+
+// Sequential fallback: walks the segments in order and re-parses every one whose entry does not
+// continue its predecessor's exit.  Exact for any input; only slow on inputs whose speculative
+// parses never resynchronise (e.g. megabytes of a single repeated byte).
+__global__ void k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
+    if (meta->n_bad == 0) return;
+    for (uint32_t s = 1; s < A.n_seg; s++) {
+        uint32_t xp = A.x_pos[s - 1], xk = A.x_key[s - 1];
+        if (xp != A.e_pos[s] || xk != A.e_key[s]) {
+            uint32_t a = A.begin + s * kParseSeg;
+            uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
+            parse_segment(A, s, state_from_key(xp, xk), a, b);
+            meta->n_repaired_seq++;
+            __threadfence();
+        }
+    }
+    meta->n_bad = 0;
+}
+
+__global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; }
+
+// =====================================================================================
+// token layout: exclusive scan of per-segment token counts (single CTA), then compaction
+// =====================================================================================
+__global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_t* e_tok, const uint32_t* x_tok,
+                                                   uint32_t* seg_cnt, unsigned long long* seg_off, DevMeta* meta) {
+    __shared__ unsigned long long part[1024];
+    uint32_t per = (n_seg + blockDim.x - 1) / blockDim.x;
+    uint32_t lo = threadIdx.x * per, hi = lo + per < n_seg ? lo + per : n_seg;
+    unsigned long long s = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t c = x_tok[i] - e_tok[i];
+        seg_cnt[i] = c;
+        s += c;
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t t = 0; t < blockDim.x; t++) { unsigned long long v = part[t]; part[t] = run; run += v; }
+        meta->n_tokens = run;
+        meta->n_blocks = (uint32_t)(run / kBlockTokens) + 1u;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) { seg_off[i] = run; run += seg_cnt[i]; }
+}
+
+__global__ void __launch_bounds__(128) k_compact(const uint32_t* __restrict__ segtok, const uint32_t* __restrict__ e_tok,
+                                                 const uint32_t* __restrict__ seg_cnt,
+                                                 const unsigned long long* __restrict__ seg_off, uint32_t* __restrict__ tok,
+                                                 DevMeta* meta) {
+    uint32_t s = blockIdx.x;
+    uint32_t c = seg_cnt[s];
+    if (e_tok[s] + c > kParseTokCap) { if (threadIdx.x == 0) meta->err = 1; return; }
+    const uint32_t* src = segtok + (size_t)s * kParseTokCap + e_tok[s];
+    uint32_t* dst = tok + seg_off[s];
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_set_tokens(DevMeta* meta, unsigned long long n_tokens) {
+    meta->n_tokens = n_tokens;
+    meta->n_blocks = (uint32_t)(n_tokens / kBlockTokens) + 1u;
+}
+
+// =====================================================================================
+// k_block_stats: literal/length and distance histograms + input bytes of one deflate block
+// =====================================================================================
+constexpr uint32_t kHistStride = 320;
+
+__global__ void __launch_bounds__(256) k_block_stats(const uint32_t* __restrict__ tok, const DevMeta* meta,
+                                                     uint32_t* __restrict__ hist, BlockCost* __restrict__ cost) {
+    __shared__ uint32_t h[kHistStride];
+    __shared__ uint32_t ws[33];
+    const uint32_t b = blockIdx.x;
+    if (b >= meta->n_blocks) return;
+    const unsigned long long T = meta->n_tokens;
+    const unsigned long long t0 = (unsigned long long)b * kBlockTokens;
+    const uint32_t ntok = (uint32_t)((T - t0) < kBlockTokens ? (T - t0) : kBlockTokens);
+    for (uint32_t i = threadIdx.x; i < kHistStride; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    uint32_t bytes = 0;
+    for (uint32_t i = threadIdx.x; i < ntok; i += blockDim.x) {
+        uint32_t t = tok[t0 + i];
+        uint32_t d = tok_dist(t);
+        if (d) {
+            uint32_t c, ne, ev;
+            length_symbol(tok_lo(t), c, ne, ev);
+            atomicAdd(&h[c], 1u);
+            dist_symbol(d, c, ne, ev);
+            atomicAdd(&h[kNumLL + c], 1u);
+            bytes += tok_lo(t);
+        } else {
+            atomicAdd(&h[tok_lo(t)], 1u);
+            bytes += 1u;
+        }
+    }
+    uint32_t total;
+    block_excl_scan(bytes, ws, total);
+    if (threadIdx.x == 0) {
+        h[kEob] = 1;   // output_writer.rs:83,107: exactly one end-of-block symbol per block
+        cost[b].input_bytes = total;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kHistStride; i += blockDim.x) hist[(size_t)b * kHistStride + i] = h[i];
+}
+
+// =====================================================================================
+// k_block_codes: one thread per block builds the three Huffman codes and the cost summary
+// =====================================================================================
+__global__ void __launch_bounds__(32) k_block_codes(const DevMeta* meta, const uint32_t* __restrict__ hist,
+                                                    BlockCost* __restrict__ cost, BlockTables* __restrict__ tables) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= meta->n_blocks) return;
+    uint32_t ll[kNumLL], dd[kNumDist], scratch[288];
+    for (uint32_t i = 0; i < kNumLL; i++) ll[i] = hist[(size_t)b * kHistStride + i];
+    for (uint32_t i = 0; i < kNumDist; i++) dd[i] = hist[(size_t)b * kHistStride + kNumLL + i];
+    BlockCodes bc;
+    build_block_codes(ll, dd, cost[b].input_bytes, bc, scratch);
+    BlockCost c;
+    c.dynamic_cost = bc.dynamic_cost; c.static_cost = bc.static_cost; c.stored_cost = bc.stored_cost;
+    c.dynamic_bits = bc.dynamic_bits; c.fixed_bits = bc.fixed_bits; c.input_bytes = bc.input_bytes;
+    c.tiny = bc.tiny;
+    BlockTables& t = tables[b];
+    uint64_t body = 0;
+    if (!bc.tiny) {
+        for (uint32_t i = 0; i < 288; i++) { t.ll_code[i] = bc.ll_code[i]; t.ll_len[i] = bc.ll_len[i]; }
+        for (uint32_t i = 0; i < 32; i++) { t.d_code[i] = bc.d_code[i]; t.d_len[i] = bc.d_len[i]; }
+        for (uint32_t i = 0; i < 19; i++) { t.cl_code[i] = bc.cl_code[i]; t.cl_len[i] = bc.cl_len[i]; }
+        for (uint32_t i = 0; i < bc.n_hdr_sym; i++) t.hdr_sym[i] = bc.hdr_sym[i];
+        for (uint32_t i = 0; i < bc.hlit; i++) {
+            uint32_t eb = i >= 257u ? length_extra_bits_of_code(i - 257u) : 0u;
+            body += (uint64_t)ll[i] * (bc.ll_len[i] + eb);
+        }
+        for (uint32_t i = 0; i < bc.hdist; i++) body += (uint64_t)dd[i] * (bc.d_len[i] + dist_extra_bits_of_code(i));
+    }
+    t.n_hdr_sym = bc.n_hdr_sym; t.hlit = bc.hlit; t.hdist = bc.hdist; t.used_hclens = bc.used_hclens;
+    c.hdr_bits = bc.tiny ? 0u : (uint32_t)(bc.dynamic_bits - body);
+    cost[b] = c;
+}
+
+// =====================================================================================
+// k_block_scan: block type for every possible bit alignment, then an exclusive scan of block sizes.
+// The Stored candidate's cost depends on the bit position of the block start modulo 8
+// (huffman_lengths.rs:113-124,262), so each thread first summarises its run of blocks as a map
+// alignment -> bits consumed, the maps are composed across the CTA, and the run is replayed.
+// =====================================================================================
+__device__ __forceinline__ int choose_block_dev(const BlockCost& c, uint32_t pending, unsigned long long& bits) {
+    if (c.tiny) { bits = 3ull + c.fixed_bits; return kFixed; }
+    unsigned long long stored_len = c.stored_cost + stored_padding(pending);
+    unsigned long long used = c.dynamic_cost < c.static_cost ? c.dynamic_cost : c.static_cost;
+    if (stored_len < used) used = stored_len;
+    if (used == c.static_cost) { bits = 3ull + c.fixed_bits; return kFixed; }
+    if (used == stored_len) { bits = 3ull + stored_len; return kStored; }
+    bits = 3ull + c.dynamic_bits;
+    return kDynamic;
+}
+
+__global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCost* __restrict__ cost, int* blk_type,
+                                                    unsigned long long* blk_bit, unsigned long long* blk_in,
+                                                    int sync_marker, uint32_t in_begin) {
+    __shared__ unsigned long long tot[256 * 8];   // bits consumed by a thread's run per entry alignment
+    __shared__ unsigned long long inb[256];
+    __shared__ unsigned long long entry_bit[256];
+    const uint32_t nb = meta->n_blocks;
+    const uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per < nb ? threadIdx.x * per : nb;
+    const uint32_t hi = lo + per < nb ? lo + per : nb;
+    unsigned long long ib = 0;
+    unsigned long long abit[8];
+#pragma unroll
+    for (uint32_t a = 0; a < 8; a++) abit[a] = a;
+    for (uint32_t b = lo; b < hi; b++) {
+        const BlockCost c = cost[b];
+        ib += c.input_bytes;
+#pragma unroll
+        for (uint32_t a = 0; a < 8; a++) {
+            unsigned long long bits;
+            choose_block_dev(c, (uint32_t)(abit[a] & 7ull), bits);
+            abit[a] += bits;
+        }
+    }
+#pragma unroll
+    for (uint32_t a = 0; a < 8; a++) tot[threadIdx.x * 8 + a] = abit[a] - a;
+    inb[threadIdx.x] = ib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long bit = 0, in_off = in_begin;
+        for (uint32_t t = 0; t < blockDim.x; t++) {
+            entry_bit[t] = bit;
+            bit += tot[t * 8 + (bit & 7ull)];
+            unsigned long long v = inb[t];
+            inb[t] = in_off;
+            in_off += v;
+        }
+        if (sync_marker) {            // compress.rs:258-261: empty stored block 00 00 FF FF, byte aligned
+            bit += 3ull;
+            bit = (bit + 7ull) & ~7ull;
+            bit += 32ull;
+        }
+        meta->stream_bits = bit;
+        meta->stream_bytes = (bit + 7ull) >> 3;
+    }
+    __syncthreads();
+    unsigned long long bit = entry_bit[threadIdx.x], in_off = inb[threadIdx.x];
+    uint32_t n_st = 0, n_fx = 0;
+    for (uint32_t b = lo; b < hi; b++) {
+        unsigned long long bits;
+        const BlockCost c = cost[b];
+        int t = choose_block_dev(c, (uint32_t)(bit & 7ull), bits);
+        blk_type[b] = t;
+        blk_bit[b] = bit;
+        blk_in[b] = in_off;
+        bit += bits;
+        in_off += c.input_bytes;
+        n_st += (t == kStored);
+        n_fx += (t == kFixed);
+        if (b + 1 == nb) blk_bit[nb] = bit;
+    }
+    if (n_st) atomicAdd(&meta->n_stored, n_st);
+    if (n_fx) atomicAdd(&meta->n_fixed, n_fx);
+}
+
+// Zero exactly the output words the stream will occupy (bits are ORed in by k_pack).
+__global__ void __launch_bounds__(256) k_zero_out(const DevMeta* meta, uint4* out, unsigned long long out_cap,
+                                                  uint32_t hdr_bytes) {
+    unsigned long long need = hdr_bytes + meta->stream_bytes + 16ull;
+    if (need > out_cap) need = out_cap;
+    unsigned long long n16 = (need + 15ull) >> 4;
+    if (n16 * 16ull > out_cap) n16 = out_cap >> 4;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = make_uint4(0, 0, 0, 0);
+}
+
+// =====================================================================================
+// k_pack: one CTA per deflate block.  Output words are pre-zeroed; bits are ORed in.
+// =====================================================================================
+__device__ __forceinline__ void put_bits(uint32_t* out32, unsigned long long bitpos, unsigned long long v, uint32_t nbits) {
+    if (nbits == 0) return;
+    unsigned long long w = bitpos >> 5;
+    uint32_t s = (uint32_t)(bitpos & 31ull);
+    unsigned long long lo = v << s;
+    uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)(lo >> 32);
+    uint32_t x2 = s ? (uint32_t)(v >> (64u - s)) : 0u;
+    if (x0) atomicOr(&out32[w], x0);
+    if (x1) atomicOr(&out32[w + 1], x1);
+    if (x2) atomicOr(&out32[w + 2], x2);
+}
+__device__ __forceinline__ void put_byte(uint32_t* out32, unsigned long long byte_idx, uint32_t v) {
+    if (v) atomicOr(&out32[byte_idx >> 2], v << ((uint32_t)(byte_idx & 3ull) * 8u));
+}
+
+constexpr uint32_t kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads)
+k_pack(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, DevMeta* meta, const BlockCost* __restrict__ cost,
+       const BlockTables* __restrict__ tables, const int* __restrict__ blk_type,
+       const unsigned long long* __restrict__ blk_bit, const unsigned long long* __restrict__ blk_in,
+       uint32_t* __restrict__ out32, unsigned long long out_bit_base, int final_block, unsigned long long out_cap) {
+    __shared__ uint32_t ll_cl[288];   // code | len << 16
+    __shared__ uint32_t d_cl[32];
+    __shared__ uint32_t ws[33];
+    const uint32_t b = blockIdx.x;
+    const uint32_t nb = meta->n_blocks;
+    if (b >= nb) return;
+    if ((out_bit_base >> 3) + meta->stream_bytes + 16ull > out_cap) {   // would not fit: write nothing
+        if (threadIdx.x == 0) meta->err = 100;
+        return;
+    }
+    const unsigned long long T = meta->n_tokens;
+    const unsigned long long t0 = (unsigned long long)b * kBlockTokens;
+    const uint32_t ntok = (uint32_t)((T - t0) < kBlockTokens ? (T - t0) : kBlockTokens);
+    const int type = blk_type[b];
+    const int last = (b + 1 == nb) && final_block;
+    unsigned long long bp = blk_bit[b] + out_bit_base;
+
+    if (type == kStored) {
+        unsigned long long pos = blk_in[b], left = cost[b].input_bytes;
+        while (left > 0) {
+            uint32_t chunk = left < kMaxStored ? (uint32_t)left : kMaxStored;
+            int lastchunk = (left == chunk);
+            if (threadIdx.x == 0 && last && lastchunk) put_bits(out32, bp, 1ull, 3);
+            bp += 3ull;
+            bp = (bp + 7ull) & ~7ull;
+            unsigned long long byte0 = bp >> 3;
+            if (threadIdx.x == 0) {
+                put_byte(out32, byte0, chunk & 0xffu);
+                put_byte(out32, byte0 + 1, chunk >> 8);
+                put_byte(out32, byte0 + 2, (~chunk) & 0xffu);
+                put_byte(out32, byte0 + 3, ((~chunk) >> 8) & 0xffu);
+            }
+            for (uint32_t i = threadIdx.x; i < chunk; i += blockDim.x) put_byte(out32, byte0 + 4 + i, in[pos + i]);
+            bp += 32ull + 8ull * chunk;
+            pos += chunk;
+            left -= chunk;
+        }
+        if (threadIdx.x == 0 && bp != blk_bit[b + 1] + out_bit_base) meta->err = 2;
+        return;
+    }
+
+    const BlockTables& tb = tables[b];
+    if (type == kFixed) {
+        // huffman_table.rs:32-42 fixed lengths -> canonical codes, bit-reversed (RFC 1951 3.2.6)
+        for (uint32_t s = threadIdx.x; s < 288; s += blockDim.x) {
+            uint32_t len = fixed_ll_length(s);
+            uint32_t code = s < 144u ? 0x30u + s : (s < 256u ? 0x190u + (s - 144u) : (s < 280u ? s - 256u : 0xc0u + (s - 280u)));
+            ll_cl[s] = reverse_bits(code, len) | (len << 16);
+        }
+        if (threadIdx.x < 32) d_cl[threadIdx.x] = reverse_bits(threadIdx.x, 5) | (5u << 16);
+    } else {
+        for (uint32_t s = threadIdx.x; s < 288; s += blockDim.x) ll_cl[s] = tb.ll_code[s] | ((uint32_t)tb.ll_len[s] << 16);
+        if (threadIdx.x < 32) d_cl[threadIdx.x] = tb.d_code[threadIdx.x] | ((uint32_t)tb.d_len[threadIdx.x] << 16);
+    }
+    __syncthreads();
+
+    unsigned long long body = bp + 3ull;
+    if (type == kDynamic) body += cost[b].hdr_bits;
+    if (threadIdx.x == 0) {
+        // encoder_state.rs:85-99 block marker, then huffman_lengths.rs:290-369 header
+        if (type == kFixed) put_bits(out32, bp, last ? 3ull : 2ull, 3);
+        else {
+            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            unsigned long long q = bp;
+            put_bits(out32, q, last ? 5ull : 4ull, 3); q += 3;
+            put_bits(out32, q, tb.hlit - 257u, 5); q += 5;
+            put_bits(out32, q, tb.hdist - 1u, 5); q += 5;
+            put_bits(out32, q, tb.used_hclens - 4u, 4); q += 4;
+            for (uint32_t i = 0; i < tb.used_hclens; i++) { put_bits(out32, q, tb.cl_len[order[i]], 3); q += 3; }
+            for (uint32_t i = 0; i < tb.n_hdr_sym; i++) {
+                uint32_t sym = tb.hdr_sym[i] & 31u, rep = tb.hdr_sym[i] >> 8;
+                put_bits(out32, q, tb.cl_code[sym], tb.cl_len[sym]); q += tb.cl_len[sym];
+                if (sym == 16u) { put_bits(out32, q, rep - 3u, 2); q += 2; }
+                else if (sym == 17u) { put_bits(out32, q, rep - 3u, 3); q += 3; }
+                else if (sym == 18u) { put_bits(out32, q, rep - 11u, 7); q += 7; }
+            }
+            if (q != body) meta->err = 3;
+        }
+    }
+
+    unsigned long long running = body;
+    for (uint32_t base = 0; base < ntok; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        unsigned long long v = 0;
+        uint32_t nbits = 0;
+        if (i < ntok) {
+            uint32_t t = tok[t0 + i];
+            uint32_t d = tok_dist(t);
+            if (d) {
+                uint32_t c, ne, ev;
+                length_symbol(tok_lo(t), c, ne, ev);
+                uint32_t cl = ll_cl[c];
+                v = cl & 0xffffu; nbits = cl >> 16;
+                v |= (unsigned long long)ev << nbits; nbits += ne;
+                dist_symbol(d, c, ne, ev);
+                cl = d_cl[c];
+                v |= (unsigned long long)(cl & 0xffffu) << nbits; nbits += cl >> 16;
+                v |= (unsigned long long)ev << nbits; nbits += ne;
+            } else {
+                uint32_t cl = ll_cl[tok_lo(t)];
+                v = cl & 0xffffu; nbits = cl >> 16;
+            }
+        }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(nbits, ws, total);
+        put_bits(out32, running + ex, v, nbits);
+        running += total;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t cl = ll_cl[kEob];
+        put_bits(out32, running, cl & 0xffffu, cl >> 16);
+        running += cl >> 16;
+        if (running != blk_bit[b + 1] + out_bit_base) meta->err = 4;
+    }
+}
+
+// =====================================================================================
+// Adler-32 (RFC 1950): per 64 KiB chunk sums, then an ordered combine in one CTA
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_adler32_chunks(const uint8_t* __restrict__ in, unsigned long long n,
+                                                        unsigned long long* __restrict__ part) {
+    __shared__ unsigned long long sa[256], sb[256];
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * kAdlerChunk;
+    const uint32_t L = (uint32_t)((n - c0) < kAdlerChunk ? (n - c0) : kAdlerChunk);
+    const uint8_t* p = in + c0;
+    unsigned long long a = 0, bsum = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+    uint32_t vec_end = aligned ? (L & ~15u) : 0u;
+    for (uint32_t i = threadIdx.x * 16u; i < vec_end; i += blockDim.x * 16u) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+        uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t byte = (wv[k] >> (8 * q)) & 0xffu;
+                a += byte;
+                bsum += (unsigned long long)(L - (i + 4 * k + q)) * byte;
+            }
+        }
+    }
+    for (uint32_t i = vec_end + threadIdx.x; i < L; i += blockDim.x) {
+        uint32_t byte = p[i];
+        a += byte;
+        bsum += (unsigned long long)(L - i) * byte;
+    }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = bsum;
+    __syncthreads();
+    for (uint32_t s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t A = (uint32_t)((1ull + sa[0]) % kAdlerMod);
+        uint32_t B = (uint32_t)(((unsigned long long)L + sb[0]) % kAdlerMod);
+        part[2ull * blockIdx.x] = ((unsigned long long)B << 16) | A;
+        part[2ull * blockIdx.x + 1] = L;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_adler32_combine(const unsigned long long* __restrict__ part, uint32_t n_chunks,
+                                                          DevMeta* meta) {
+    __shared__ uint32_t ad[1024];
+    __shared__ unsigned long long ln[1024];
+    uint32_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
+    uint32_t lo = threadIdx.x * per, hi = lo + per < n_chunks ? lo + per : n_chunks;
+    uint32_t a = 1;
+    unsigned long long len = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        a = adler32_combine(a, (uint32_t)part[2ull * i], part[2ull * i + 1]);
+        len += part[2ull * i + 1];
+    }
+    ad[threadIdx.x] = a; ln[threadIdx.x] = len;
+    __syncthreads();
+    for (uint32_t s = 1; s < blockDim.x; s <<= 1) {
+        uint32_t i = threadIdx.x;
+        if ((i & (2 * s - 1)) == 0 && i + s < blockDim.x) {
+            ad[i] = adler32_combine(ad[i], ad[i + s], ln[i + s]);
+            ln[i] += ln[i + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) meta->adler = ad[0];
+}
+
+// =====================================================================================
+// k_finalize: sync marker bytes, container header and trailer (zlib.rs:59-62, lib.rs:192-196)
+// =====================================================================================
+__global__ void k_finalize(DevMeta* meta, uint8_t* out, unsigned long long out_cap, uint32_t hdr_bytes, int wrap,
+                           int sync_marker, int write_trailer) {
+    unsigned long long end = hdr_bytes + meta->stream_bytes;
+    if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = end + (wrap == 1 && write_trailer ? 4ull : 0ull); return; }
+    if (sync_marker && end >= 4 && end <= out_cap) {
+        out[end - 2] = 0xff;
+        out[end - 1] = 0xff;
+    }
+    if (wrap == 1) {   // zlib
+        if (hdr_bytes == 2) { out[0] = 0x78; out[1] = 0x9c; }
+        if (write_trailer && end + 4 <= out_cap) {
+            uint32_t a = meta->adler;
+            out[end] = (uint8_t)(a >> 24); out[end + 1] = (uint8_t)(a >> 16); out[end + 2] = (uint8_t)(a >> 8); out[end + 3] = (uint8_t)a;
+        }
+        if (write_trailer) end += 4;
+    }
+    meta->out_bytes = end;
+}
+
+// =====================================================================================
+// host-side launchers
+// =====================================================================================
+uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 2u; }
+
+static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
+    ParseArgs A;
+    A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
+    A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
+    A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
+    A.n_seg = (j.n - j.begin + kParseSeg - 1) / kParseSeg;
+    return A;
+}
+
+static bool g_attr_done = false;
+static cudaError_t ensure_attrs() {
+    if (g_attr_done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    if (e != cudaSuccess) return e;
+    g_attr_done = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    uint32_t n_win = (j.n + kWindow - 1) / kWindow;
+    uint32_t w_begin = j.begin / kWindow;
+    uint32_t w_first = w_begin > 0 ? w_begin - 1 : 0;
+    if (n_win <= w_first) return cudaSuccess;
+    k_window_sort<<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.S, b.off);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    uint32_t n_win = (j.n + kWindow - 1) / kWindow;
+    uint32_t w_first = j.begin / kWindow;
+    if (n_win <= w_first) return cudaSuccess;
+    k_match<<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.S, b.off, b.Mf, b.Mq);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    ParseArgs A = make_parse_args(j, b);
+    if (A.n_seg == 0) return cudaSuccess;
+    uint32_t grid = (A.n_seg + 127) / 128;
+    k_parse_spec<<<grid, 128, 0, st>>>(A);
+    DFL_LAUNCH_CHECK();
+    if (A.n_seg == 1) return cudaSuccess;
+    for (uint32_t r = 0; r < kRepairRounds; r++) {
+        k_reset_bad<<<1, 1, 0, st>>>(b.meta);
+        DFL_LAUNCH_CHECK();
+        k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
+        DFL_LAUNCH_CHECK();
+        k_parse_repair<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
+        DFL_LAUNCH_CHECK();
+    }
+    k_reset_bad<<<1, 1, 0, st>>>(b.meta);
+    DFL_LAUNCH_CHECK();
+    k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
+    DFL_LAUNCH_CHECK();
+    k_parse_repair_seq<<<1, 1, 0, st>>>(A, b.meta);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    uint32_t n_seg = (j.n - j.begin + kParseSeg - 1) / kParseSeg;
+    k_seg_scan<<<1, 1024, 0, st>>>(n_seg, b.seg_e_tok, b.seg_x_tok, b.seg_cnt, b.seg_off, b.meta);
+    DFL_LAUNCH_CHECK();
+    if (n_seg > 0) {
+        k_compact<<<n_seg, 128, 0, st>>>(b.segtok, b.seg_e_tok, b.seg_cnt, b.seg_off, b.tok, b.meta);
+        DFL_LAUNCH_CHECK();
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    const uint32_t* tok = j.d_tokens_override ? j.d_tokens_override : b.tok;
+    if (j.d_tokens_override) {
+        k_set_tokens<<<1, 1, 0, st>>>(b.meta, j.n_tokens_override);
+        DFL_LAUNCH_CHECK();
+    }
+    k_block_stats<<<max_blocks_for(j.n - j.begin), 256, 0, st>>>(tok, b.meta, b.hist, b.cost);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    uint32_t mb = max_blocks_for(j.n - j.begin);
+    k_block_codes<<<(mb + 31) / 32, 32, 0, st>>>(b.meta, b.hist, b.cost, b.tables);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_block_scan(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    k_block_scan<<<1, 256, 0, st>>>(b.meta, b.cost, b.blk_type, b.blk_bit, b.blk_in, j.sync_marker, j.begin);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_pack(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    const uint32_t* tok = j.d_tokens_override ? j.d_tokens_override : b.tok;
+    k_zero_out<<<148 * 8, 256, 0, st>>>(b.meta, reinterpret_cast<uint4*>(j.d_out), (unsigned long long)j.out_cap, j.hdr_bytes);
+    DFL_LAUNCH_CHECK();
+    k_pack<<<max_blocks_for(j.n - j.begin), kPackThreads, 0, st>>>(j.d_in, tok, b.meta, b.cost, b.tables, b.blk_type, b.blk_bit,
+                                                                    b.blk_in, reinterpret_cast<uint32_t*>(j.d_out),
+                                                                    (unsigned long long)j.hdr_bytes * 8ull, j.final_block,
+                                                                    (unsigned long long)j.out_cap);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_adler32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st) {
+    uint32_t n_chunks = (uint32_t)((n + kAdlerChunk - 1) / kAdlerChunk);
+    if (n_chunks > 0) {
+        k_adler32_chunks<<<n_chunks, 256, 0, st>>>(d_in, (unsigned long long)n, b.adler_part);
+        DFL_LAUNCH_CHECK();
+    }
+    k_adler32_combine<<<1, 1024, 0, st>>>(b.adler_part, n_chunks, b.meta);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st) {
+    k_finalize<<<1, 1, 0, st>>>(b.meta, j.d_out, (unsigned long long)j.out_cap, j.hdr_bytes, wrap, j.sync_marker,
+                                j.final_block);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace dfl

@@ -1,0 +1,153 @@
+/*
+ * deflate_b200.h -- C ABI of the B200-native DEFLATE encoder (libdeflate_b200.so).
+ *
+ * This is the drop-in boundary for the encode path of image-rs/deflate-rs (crate `deflate`
+ * 1.0.0).  Each entry point names the reference interface it replaces (file:line under the
+ * reference's src/).  The reference has no FFI of its own (pure Rust, forbid(unsafe_code));
+ * the seam is the single internal function every public encoder funnels into,
+ *     compress_data_dynamic_n(input, &mut DeflateState<W>, Flush) -> io::Result<usize>
+ * (compress.rs:80-84), reached from deflate_bytes* via compress_until_done (writer.rs:15-58,
+ * lib.rs:110-122) and from write::{DeflateEncoder,ZlibEncoder,GzEncoder} (writer.rs:124-136,
+ * 254-276).  INTEGRATION.md shows the Rust shim (extern "C" block + safe wrappers with the
+ * crate's public names) that a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; 0 = success, > 0 = retryable, < 0 = fatal; nothing
+ * throws or aborts across this boundary.  All compute runs in hand-written sm_100a CUDA kernels;
+ * there is no CPU fallback -- without a CUDA device every compute entry point returns
+ * DFL_E_NODEVICE.
+ */
+#ifndef DEFLATE_B200_H
+#define DEFLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFL_VERSION 100 /* 0.1.0 */
+
+/* ---- CompressionOptions (compression_options.rs:78-120); layout crosses the ABI --------- */
+typedef struct dfl_options {
+    uint16_t max_hash_checks;   /* compression_options.rs:85  */
+    uint16_t lazy_if_less_than; /* compression_options.rs:100 */
+    uint8_t matching_type;      /* lz77.rs:26-37: 0 = Greedy, 1 = Lazy */
+    uint8_t special;            /* compression_options.rs:52-59: 0 = Normal (others are
+                                   unimplemented placeholders in the reference too) */
+} dfl_options;
+
+/* Compression::{Fast,Default,Best} (compression_options.rs:31-42) and the named presets
+ * (compression_options.rs:126-178). */
+enum dfl_preset {
+    DFL_PRESET_FAST = 0,        /* 1 check, greedy              (:141-148) */
+    DFL_PRESET_DEFAULT = 1,     /* 128 checks, lazy < 32        (:19-20,67-72) */
+    DFL_PRESET_BEST = 2,        /* == high(): 1768, lazy < 128  (:14-15,126-133) */
+    DFL_PRESET_HUFFMAN_ONLY = 3,/* 0 checks, greedy             (:155-162) */
+    DFL_PRESET_RLE = 4          /* 0 checks, lazy => RLE        (:171-178) */
+};
+int dfl_options_preset(int preset, dfl_options *out);
+
+/* Container written around the raw DEFLATE stream. */
+enum dfl_wrap {
+    DFL_RAW = 0,  /* deflate_bytes[_conf]       lib.rs:137,163 / DeflateEncoder writer.rs:89  */
+    DFL_ZLIB = 1, /* deflate_bytes_zlib[_conf]  lib.rs:182,216 / ZlibEncoder    writer.rs:183 */
+    DFL_GZIP = 2  /* deflate_bytes_gzip[_conf]  lib.rs:242,284 / GzEncoder      writer.rs:331 */
+};
+
+/* Flush (compress.rs:17-30). */
+enum dfl_flush {
+    DFL_FLUSH_SYNC = 1,  /* Flush::Sync: close the block, append 00 00 FF FF (compress.rs:258-261) */
+    DFL_FLUSH_FINISH = 2 /* Flush::Finish */
+};
+
+enum dfl_status {
+    DFL_OK = 0,
+    DFL_AGAIN = 1,          /* io::ErrorKind::Interrupted, "internal buffer full" (compress.rs:117-120) */
+    DFL_E_ARG = -1,
+    DFL_E_NOMEM = -2,
+    DFL_E_CUDA = -3,
+    DFL_E_NODEVICE = -4,    /* no CUDA device / extension unusable: there is no CPU fallback */
+    DFL_E_OVERFLOW = -5,    /* out_cap too small; *out_len receives the size needed */
+    DFL_E_STATE = -6,       /* e.g. write after finish */
+    DFL_E_UNSUPPORTED = -7,
+    DFL_E_INTERNAL = -8
+};
+const char *dfl_strerror(int status);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char *dfl_last_cuda_error(void);
+int dfl_version(void);
+/* Number of usable CUDA devices (0 on a CPU-only box; never an error). */
+int dfl_device_count(void);
+
+/* Upper bound of the output size for n input bytes (any options, any wrapper). */
+size_t dfl_bound(size_t n, int wrap);
+
+/* ---- one-shot, host buffers: deflate_bytes_conf / _zlib_conf / _gzip_conf -------------------
+ * (lib.rs:137, 182, 242).  gz_hdr/gz_hdr_len: complete RFC 1952 member header produced by the
+ * caller (the crate's GzBuilder::into_header(), lib.rs:251); NULL/0 = the default header.
+ * Copies in -> device, encodes, copies the stream back.  Blocking. */
+int dfl_compress(const uint8_t *in, size_t n, const dfl_options *opt, int wrap,
+                 const uint8_t *gz_hdr, size_t gz_hdr_len, uint8_t *out, size_t out_cap,
+                 size_t *out_len);
+
+/* ---- one-shot, device buffers (the measured path) -----------------------------------------
+ * d_in/d_out are device pointers on the current CUDA device; `stream` is a cudaStream_t (NULL =
+ * the context's own stream).  The complete container (header, stream, trailer) is left in d_out;
+ * its size is returned in *out_len after the stream has been synchronised. */
+int dfl_compress_device(const void *d_in, size_t n, const dfl_options *opt, int wrap,
+                        const uint8_t *gz_hdr, size_t gz_hdr_len, void *d_out, size_t out_cap,
+                        size_t *out_len, void *stream);
+
+/* Per-stage device timings of the most recent dfl_compress_device call on this thread, in
+ * milliseconds (CUDA events on the launching stream): names[i] points to a static string.
+ * Returns the number of stages (0 if timing was not enabled with dfl_set_profiling(1)). */
+int dfl_set_profiling(int enabled);
+int dfl_last_stage_times(const char **names, float *ms, int cap);
+/* Counters of the most recent call: [0] tokens, [1] deflate blocks, [2] parse segments,
+ * [3] segments re-parsed in parallel rounds, [4] segments re-parsed sequentially,
+ * [5] kernels launched, [6] stored blocks, [7] fixed blocks. */
+int dfl_last_counters(uint64_t *out, int cap);
+
+/* ---- streaming: write::{DeflateEncoder,ZlibEncoder,GzEncoder} (writer.rs:89-467) ----------
+ * The generic sink W cannot cross an FFI, so output is pulled: the shim forwards the bytes lent
+ * by dfl_encoder_take_output to its `inner.write(..)` and reports progress with
+ * dfl_encoder_advance_output, which preserves the reference's partial-write bookkeeping
+ * (compress.rs:96-111,286-299). */
+typedef struct dfl_encoder dfl_encoder;
+
+dfl_encoder *dfl_encoder_new(const dfl_options *opt, int wrap, const uint8_t *gz_hdr,
+                             size_t gz_hdr_len);                     /* ::new / from_builder */
+/* Write::write (writer.rs:124-127,254-267): consumes up to n bytes, *consumed <= n. */
+int dfl_encoder_write(dfl_encoder *e, const uint8_t *buf, size_t n, size_t *consumed);
+/* Write::flush = DFL_FLUSH_SYNC (writer.rs:134-136); finish()/Drop = DFL_FLUSH_FINISH
+ * (writer.rs:103-108,139-152).  After FINISH the trailer is part of the output. */
+int dfl_encoder_flush(dfl_encoder *e, int mode);
+int dfl_encoder_take_output(dfl_encoder *e, const uint8_t **p, size_t *len);
+void dfl_encoder_advance_output(dfl_encoder *e, size_t n);
+/* ZlibEncoder::checksum (writer.rs:248) / GzEncoder::checksum (writer.rs:429): checksum of the
+ * bytes consumed so far (Adler-32 or CRC-32; 1 for DFL_RAW like NoChecksum, checksum.rs:26-28). */
+uint32_t dfl_encoder_checksum(dfl_encoder *e);
+/* reset(W) (writer.rs:112-115,218-223,394-401): finishes the current stream (its bytes stay
+ * available through take_output) and starts a new one with the same options. */
+int dfl_encoder_reset(dfl_encoder *e, const uint8_t *gz_hdr, size_t gz_hdr_len);
+void dfl_encoder_free(dfl_encoder *e);
+
+/* ---- building blocks exposed for tests and for callers that keep data on the device --------
+ * Adler-32 (checksum.rs:33-57) of a device buffer, computed on the device. */
+int dfl_adler32_device(const void *d_in, size_t n, uint32_t *adler, void *stream);
+/* Runs only the entropy stage (block cut at 31744 tokens, code construction, block-type choice,
+ * bit packing: huffman_lengths.rs:167-369, encoder_state.rs:58-105, compress.rs:187-247) on a
+ * caller-supplied token stream (host memory; token = literal byte, or len | dist << 9), so the
+ * stage can be compared bit-for-bit with the reference fed the same tokens. `in` is the
+ * uncompressed data the tokens describe (needed for stored blocks). */
+int dfl_encode_tokens(const uint8_t *in, size_t n, const uint32_t *tokens, size_t n_tokens,
+                      uint8_t *out, size_t out_cap, size_t *out_len);
+/* Runs only the LZ77 stage and returns the token stream (host memory, same encoding). */
+int dfl_lz77_tokens(const uint8_t *in, size_t n, const dfl_options *opt, uint32_t *tokens,
+                    size_t tokens_cap, size_t *n_tokens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFLATE_B200_H */

@@ -1,0 +1,73 @@
+"""CPU checks of the GPU pipeline's algorithms (tests/model = sequential walk-through built from the
+same dfl_core.h the kernels use) against the oracle.  The claim under test is DESIGN.md's central
+one: sorted per-window candidate lists + per-position match records + the reference's parser run
+over them + fixed 31744-token blocks reproduce the reference's stream bit for bit."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import model_lib as m
+import oracle_lib as o
+from conftest import FIXTURES, fixture_bytes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_symbol_arithmetic_matches_reference_tables():
+    ref = json.load(open(os.path.join(GOLDEN, "ref_tables.json")))
+    for stored in range(256):
+        code, ne, ev, *_ = m.symbols(stored + 3, 1)
+        n = ref["LENGTH_CODE"][stored]
+        assert (code, ne, ev) == (257 + n, ref["LENGTH_EXTRA_BITS_LENGTH"][n], stored - ref["BASE_LENGTH"][n])
+    for dist in range(1, 32769):
+        *_, code, ne, ev = m.symbols(3, dist)
+        want = ref["DISTANCE_CODES"][dist - 1] if dist <= 256 else ref["DISTANCE_CODES"][256 + ((dist - 1) >> 7)]
+        assert (code, ne, ev) == (want, ref["DISTANCE_EXTRA_BITS"][want], dist - 1 - ref["DISTANCE_BASE"][want])
+
+
+def _inputs(pg11):
+    rng = np.random.default_rng(1)
+    d = {
+        "pg11": pg11, "short": fixture_bytes("short.bin"), "issue18": fixture_bytes("issue_18_201911.bin"),
+        "dump": fixture_bytes("dump.bin"), "zeros65537": bytes(65537), "zeros61000": bytes(61000),
+        "lastblock": bytes([22]) * 32768 + bytes([5, 2, 55, 11, 12]), "fives": bytes([5]) * 100000,
+        "empty": b"", "one": b"\x01", "four": bytes([5, 6, 7, 8]),
+        "random": rng.integers(0, 256, 150000, dtype=np.uint8).tobytes(),
+        "random4": rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+        "period7": bytes(range(7)) * 30000,
+    }
+    for n in (2, 3, 5, 259, 32767, 32768, 32769, 65535, 65536, 65537, 65794, 65795):
+        d[f"pg{n}"] = pg11[:n]
+    for name in sorted(os.listdir(os.path.join(FIXTURES, "afl")))[:6]:
+        d["afl/" + name] = fixture_bytes("afl/" + name)
+    return d
+
+
+@pytest.mark.parametrize("preset", list(o.PRESETS))
+def test_model_is_bit_exact_with_oracle(preset, pg11):
+    opts = o.PRESETS[preset]()
+    for name, data in _inputs(pg11).items():
+        want = o.compress(data, opts, o.RAW)
+        for pseg, warm in ((8192, 1024), (512, 64)):
+            got, _ = m.compress(data, opts, pseg, warm, 3)
+            assert got == want, (name, preset, pseg, warm, len(got), len(want))
+        assert zlib.decompress(want, -15) == data
+
+
+def test_model_repairs_unsynchronised_segments():
+    """Periodic data never resynchronises a speculative parse; the repair path must still be exact."""
+    data = bytes(300000)
+    want = o.compress(data, o.opts_default(), o.RAW)
+    got, st = m.compress(data, o.opts_default(), 8192, 1024, 3)
+    assert got == want and st["repairs"] + st["seq_repairs"] > 0
+
+
+def test_model_custom_options(pg11):
+    data = pg11[:120000]
+    for checks, lazy, mt in ((4, 8, 1), (16, 258, 1), (3, 40, 1), (64, 4, 1), (7, 0, 0), (300, 64, 1), (1, 3, 1)):
+        opts = o.Options(checks, lazy, mt, 0)
+        got, _ = m.compress(data, opts, 4096, 256, 3)
+        assert got == o.compress(data, opts, o.RAW), (checks, lazy, mt)
