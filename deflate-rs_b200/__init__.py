@@ -203,8 +203,12 @@ class _Encoder:
             if n.value == 0:
                 return
             chunk = ctypes.string_at(p, n.value)
-            wrote = self._inner.write(chunk)
-            wrote = len(chunk) if wrote is None else int(wrote)   # partial writes are honoured
+            if isinstance(self._inner, bytearray):                 # the analogue of `impl Write for Vec<u8>`
+                self._inner += chunk
+                wrote = len(chunk)
+            else:
+                wrote = self._inner.write(chunk)
+                wrote = len(chunk) if wrote is None else int(wrote)   # partial writes are honoured
             if wrote <= 0:
                 raise IOError("failed to write whole buffer")       # io::ErrorKind::WriteZero
             L.dfl_encoder_advance_output(self._h, wrote)
