@@ -89,7 +89,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.S); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -123,7 +123,7 @@ struct Context {
         size_t n_blk = max_blocks_for((uint32_t)cap) + 1;
         size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
         int rc = 0;
-        if ((rc = dev_alloc(b.S, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.K, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
@@ -146,7 +146,7 @@ struct Context {
         if ((rc = dev_alloc(b.blk_bit, n_blk + 1))) return rc;
         if ((rc = dev_alloc(b.blk_in, n_blk + 1))) return rc;
         if ((rc = dev_alloc(b.adler_part, 2 * n_chunk))) return rc;
-        b.tok = b.S;   // the candidate lists are dead once k_match has run; the token stream reuses them
+        b.tok = reinterpret_cast<uint32_t*>(b.K);   // the candidate lists are dead once k_match has run; the token stream reuses them
         b.cap_n = cap;
         b.cap_quarter = quarter;
         return DFL_OK;

@@ -63,14 +63,79 @@ DFL_HD uint32_t hash3(uint32_t b0, uint32_t b1, uint32_t b2) {
 DFL_HD uint32_t tag9(uint32_t b0, uint32_t b1) {
     return (b0 >> 5) | ((b0 & 7u) << 3) | ((b1 & 7u) << 6);
 }
-// One entry of a per-window sorted candidate list: position inside the 32 KiB window (15 bits),
-// the 4th byte (8 bits) and the 3-byte tag (9 bits).
-DFL_HD uint32_t pack_entry(uint32_t pos_local, uint32_t b0, uint32_t b1, uint32_t b3) {
-    return pos_local | (b3 << 15) | (tag9(b0, b1) << 23);
+// One entry of a per-window candidate list (windows are sorted by hash3, then by position).  64 bits:
+//   lo = bytes p+3 .. p+6 (little endian), hi = byte p+7 | tag9 << 8 | position-in-window << 17.
+// Together with an equal hash3 an entry therefore proves the length of the common prefix of two
+// positions exactly up to 8 bytes without touching the data (bytes past the end of input are 0).
+struct Entry { uint32_t lo, hi; };
+constexpr uint32_t kEntryKeyHi = 0x1ffffu;   // byte 7 + tag: the part of `hi` that takes part in compares
+constexpr uint32_t kEntryTagHi = 0x1ff00u;
+constexpr uint32_t kEntryBytes = 8;          // prefix length an entry can prove
+DFL_HD Entry make_entry(uint32_t pos_local, const uint8_t b[8]) {
+    Entry e;
+    e.lo = b[3] | (b[4] << 8) | (b[5] << 16) | ((uint32_t)b[6] << 24);
+    e.hi = b[7] | (tag9(b[0], b[1]) << 8) | (pos_local << 17);
+    return e;
 }
-DFL_HD uint32_t entry_pos(uint32_t e) { return e & 0x7fffu; }
-DFL_HD uint32_t entry_filter(uint32_t e) { return e >> 15; }   // b3 | tag << 8  (17 bits)
-DFL_HD uint32_t entry_tag(uint32_t e) { return e >> 23; }
+DFL_HD uint32_t entry_pos(uint32_t hi) { return hi >> 17; }
+// Masks selecting what a candidate must share with the target to be LONGER than best_len
+// (best_len in {1 = nothing yet, 3..7}; from 8 on every key bit must agree).
+DFL_HD void entry_mask(uint32_t best_len, uint32_t& mlo, uint32_t& mhi) {
+    if (best_len < kMinMatch) { mlo = 0u; mhi = kEntryTagHi; return; }
+    uint32_t nb = best_len - 2u;             // bytes 3 .. best_len must match
+    mlo = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+    mhi = nb >= 5u ? kEntryKeyHi : kEntryTagHi;
+}
+// Common prefix length (3..8) of two positions with equal hash3 and equal tag, from the xor of their entries.
+DFL_HD uint32_t entry_lcp(uint32_t xlo, uint32_t xhi) {
+    if (xlo != 0u) {
+#if defined(__CUDA_ARCH__)
+        return 3u + ((uint32_t)(__ffs((int)xlo) - 1) >> 3);
+#else
+        return 3u + ((uint32_t)__builtin_ctz(xlo) >> 3);
+#endif
+    }
+    return (xhi & 0xffu) ? 7u : 8u;
+}
+
+// ---------------------------------------------------------------- candidate walk
+// State of one longest_match call (matching.rs:87-166) while its candidates are visited most recent
+// first.  best_len == 1 means "nothing yet" (matching.rs:108 floors the running best at 1; results
+// shorter than MIN_MATCH are discarded by both parsers, so they are never recorded here).
+struct WalkState {
+    uint32_t best_len, best_dist;
+    uint32_t mlo, mhi;    // entry_mask(best_len)
+    uint32_t done;        // the match reached max_len: the reference stops walking (matching.rs:152-156)
+};
+DFL_HD WalkState walk_init() {
+    WalkState s; s.best_len = 1; s.best_dist = 0; s.done = 0; entry_mask(1, s.mlo, s.mhi); return s;
+}
+// Necessary condition for candidate entry `ce` to beat the running best of target entry `me`.
+DFL_HD bool walk_passes(const WalkState& s, Entry me, Entry ce) {
+    return ((((ce.lo ^ me.lo) & s.mlo) | ((ce.hi ^ me.hi) & s.mhi)) == 0u);
+}
+// A candidate that passed: determine its exact length and keep it if strictly longer (so the nearest
+// candidate wins ties, matching.rs:148-157).  D gives access to the bytes: byte(i), common_prefix(a,b,from,maxl).
+// sp/sq are the data indices of the target and the candidate (sq < sp).
+template <class D>
+DFL_HD void walk_consider(WalkState& s, const D& data, uint32_t sp, uint32_t sq, Entry me, Entry ce, uint32_t maxl) {
+    uint32_t l;
+    if (s.best_len < kEntryBytes) {
+        l = entry_lcp(ce.lo ^ me.lo, ce.hi ^ me.hi);
+        if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
+    } else {
+        // the reference's quick reject looks at the byte that would extend the best match (matching.rs:141-143)
+        if (data.byte(sq + s.best_len) != data.byte(sp + s.best_len)) return;
+        l = data.common_prefix(sp, sq, kEntryBytes, maxl);
+    }
+    if (l > maxl) l = maxl;
+    if (l > s.best_len) {
+        s.best_len = l;
+        s.best_dist = sp - sq;
+        entry_mask(l, s.mlo, s.mhi);
+        if (l == maxl) s.done = 1;
+    }
+}
 
 // ---------------------------------------------------------------- per-position match record
 // len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23.  0 == "no usable match".

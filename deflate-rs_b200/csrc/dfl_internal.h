@@ -53,7 +53,7 @@ struct BlockTables {
 };
 
 struct Buffers {   // device scratch of one context, grown on demand
-    uint32_t* S = nullptr;          // sorted candidate entries, n_windows * 32768
+    uint2* K = nullptr;             // candidate entries in bucket order (dfl_core.h Entry), n_windows * 32768
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed

@@ -105,114 +105,235 @@ __host__ __device__ inline uint32_t window_count(uint32_t n, uint32_t w) {
 }
 
 // =====================================================================================
-// k_window_sort: one CTA per 32 KiB window.
-//   shared: 32 KiB + 16 of input bytes, 64 KiB of u16 counters/cursors (viewed as u32 pairs)
+// k_window_sort: one CTA (1024 threads) per 32 KiB window.
+//   A stable LSD radix sort (3 passes x 5 bits) of the window's positions by the reference's 15-bit
+//   hash; every thread owns 32 consecutive positions and private digit counters, so no atomics and
+//   no warp votes are needed and the order inside a bucket is position order by construction.
+//   Output: the window's candidate lists as 64-bit entries (dfl_core.h Entry) in bucket order, and
+//   the bucket start offsets.
+//   shared: 64 KiB of packed u16 counters (also the byte staging area) + 132 KiB of padded items
 // =====================================================================================
-constexpr uint32_t kSortThreads = 256;
-constexpr uint32_t kSortStage = kWindow + 16;
-constexpr uint32_t kSortSmem = kSortStage + kWindow * 2 + 64;
+constexpr uint32_t kSortThreads = 1024;
+constexpr uint32_t kSortItems = kWindow / kSortThreads;          // 32 items per thread
+constexpr uint32_t kSortCntWords = 32 * (kSortThreads / 2);      // 32 digits x 512 packed counter pairs
+constexpr uint32_t kSortBufWords = kWindow + kWindow / 32;       // +1 pad word per 32 (conflict-free blocked reads)
+constexpr uint32_t kSortSmem = (kSortCntWords + kSortBufWords) * 4 + 256;
+static_assert(kSortItems == 32, "one item per bit of the digit/prefix packing below");
+static_assert(kWindow + 16 <= kSortCntWords * 4, "byte staging must fit in the counter area");
 
-__global__ void __launch_bounds__(kSortThreads) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
-                                                              uint32_t w_first, uint32_t* __restrict__ S,
-                                                              uint16_t* __restrict__ off) {
+__global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
+                                                                 uint32_t w_first, uint2* __restrict__ K,
+                                                                 uint16_t* __restrict__ off) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* sdata = smem;                                             // kSortStage bytes
-    uint32_t* hist32 = reinterpret_cast<uint32_t*>(smem + kSortStage); // 16384 words = 32768 u16
-    uint16_t* cur16 = reinterpret_cast<uint16_t*>(hist32);
-    uint32_t* wtot = hist32 + kWindow / 2;                             // 8 warp totals (+ spare)
-
+    uint32_t* cntw = reinterpret_cast<uint32_t*>(smem);                        // kSortCntWords
+    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem);
+    uint32_t* buf = reinterpret_cast<uint32_t*>(smem) + kSortCntWords;         // kSortBufWords
+    uint32_t* xw = buf + kSortBufWords;                                        // 64 words of scratch
+    const uint32_t t = threadIdx.x;
     const uint32_t w = w_first + blockIdx.x;
     const uint32_t base = w * kWindow;
     const uint32_t cnt = window_count(n, w);
 
-    stage_bytes(sdata, in, (long long)base, kSortStage, n);
-    for (uint32_t i = threadIdx.x; i < kWindow / 2; i += blockDim.x) hist32[i] = 0;
+    // ---- stage the window's bytes (+16) in the counter area and form the items (hash << 15 | pos)
+    stage_bytes(smem, in, (long long)base, kWindow + 16, n);
     __syncthreads();
-
-    // phase 1: bucket sizes (two u16 counters per word; a counter never exceeds 32768)
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        uint32_t h = hash3(sdata[i], sdata[i + 1], sdata[i + 2]);
-        atomicAdd(&hist32[h >> 1], 1u << ((h & 1u) * 16u));
-    }
-    __syncthreads();
-
-    // phase 2: exclusive scan of the 32768 counters; each warp owns 4096 bins (2048 words)
-    const uint32_t nwarps = kSortThreads / 32;   // 8
-    const uint32_t words_per_warp = (kWindow / 2) / nwarps;
     {
-        uint32_t s = 0;
-        for (uint32_t k = lane_id(); k < words_per_warp; k += 32) {
-            uint32_t v = hist32[warp_id() * words_per_warp + k];
-            s += (v & 0xffffu) + (v >> 16);
+        const uint4* s4 = reinterpret_cast<const uint4*>(smem) + t * 2u;
+        uint4 a = s4[0], b = s4[1];
+        uint32_t c = reinterpret_cast<const uint32_t*>(smem)[t * 8u + 8u];
+        uint32_t wv[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c};
+#pragma unroll
+        for (uint32_t i = 0; i < kSortItems; i++) {
+            uint32_t lo = wv[i >> 2], hi = wv[(i >> 2) + 1];
+            uint32_t v = __funnelshift_r(lo, hi, (i & 3u) * 8u);   // bytes i, i+1, i+2 of this thread's run
+            uint32_t pos = t * kSortItems + i;
+            uint32_t h = pos < cnt ? hash3(v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu) : 0x7fffu;
+            buf[t * 33u + i] = (h << 15) | pos;   // positions past the end sort behind every real entry
         }
-        s = warp_incl_scan(s);
-        if (lane_id() == 31) wtot[warp_id()] = s;
-    }
-    __syncthreads();
-    uint32_t running = 0;
-    for (uint32_t k = 0; k < warp_id(); k++) running += wtot[k];
-    __syncthreads();   // wtot lives right after the counters; keep it intact until everyone has read it
-    uint32_t* off32 = reinterpret_cast<uint32_t*>(off + (size_t)w * kWindow);
-    for (uint32_t k = 0; k < words_per_warp; k += 32) {
-        uint32_t idx = warp_id() * words_per_warp + k + lane_id();
-        uint32_t v = hist32[idx];
-        uint32_t c0 = v & 0xffffu, c1 = v >> 16;
-        uint32_t incl = warp_incl_scan(c0 + c1);
-        uint32_t o0 = running + incl - (c0 + c1);
-        uint32_t o1 = o0 + c0;
-        uint32_t packed = o0 | (o1 << 16);
-        hist32[idx] = packed;
-        off32[idx] = packed;
-        running += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncthreads();
 
-    // phase 3: ordered scatter by one warp (order inside a bucket == position order)
-    if (warp_id() == 0) {
-        uint32_t* Sw = S + (size_t)w * kWindow;
-        for (uint32_t r = 0; r < cnt; r += 32) {
-            uint32_t i = r + lane_id();
-            bool act = i < cnt;
-            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-            if (act) { b0 = sdata[i]; b1 = sdata[i + 1]; b2 = sdata[i + 2]; b3 = sdata[i + 3]; }
-            uint32_t h = act ? hash3(b0, b1, b2) : (0x10000u + lane_id());
-            uint32_t peers = __match_any_sync(0xffffffffu, h);
-            uint32_t rank = __popc(peers & ((1u << lane_id()) - 1u));
-            uint32_t npeers = __popc(peers);
-            uint32_t dst = act ? cur16[h] : 0u;
-            __syncwarp();
-            if (act && rank == npeers - 1u) cur16[h] = (uint16_t)(dst + npeers);
-            __syncwarp();
-            if (act) Sw[dst + rank] = pack_entry(i, b0, b1, b3);
+    // Items live in `buf` in blocked order (thread t owns buf[33 t .. 33 t + 31]) between passes.
+    const uint32_t cw = (t & 511u) * 2u + (t >> 9);     // u16 index of this thread's counter inside a digit row
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < 3; pass++) {
+        const uint32_t shift = 15u + 5u * pass;
+        for (uint32_t i = t; i < kSortCntWords; i += kSortThreads) cntw[i] = 0;
+        __syncthreads();
+        // thread-private digit counts; pre = number of earlier items of this thread with the same digit
+        uint32_t pre[kSortItems / 4];                     // 8 bits each
+#pragma unroll
+        for (uint32_t i = 0; i < kSortItems; i++) {
+            uint32_t d = (buf[t * 33u + i] >> shift) & 31u;
+            uint32_t idx = d * 1024u + cw;
+            uint32_t c = cnt16[idx];
+            cnt16[idx] = (uint16_t)(c + 1u);
+            if ((i & 3u) == 0) pre[i >> 2] = c; else pre[i >> 2] |= c << (8u * (i & 3u));
+        }
+        __syncthreads();
+        // exclusive scan of all counters in (digit, thread) order.  Row d lives in words [512 d, 512 d + 512):
+        // low halves are threads 0..511, high halves threads 512..1023.  Warp d scans row d.
+        {
+            const uint32_t d = t >> 5, l = t & 31u;
+            uint32_t* row = cntw + d * 512u + l * 16u;
+            uint32_t sum = 0;                              // packed (hi << 16 | lo); totals <= 32768 each
+#pragma unroll
+            for (uint32_t k = 0; k < 16; k++) sum += row[k];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, incl, dd);
+                if ((int)l >= dd) incl += o;
+            }
+            uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t lo_tot = tot & 0xffffu, hi_tot = tot >> 16;
+            if (l == 0) xw[d] = lo_tot + hi_tot;
+            __syncthreads();
+            uint32_t dbase = 0;
+            {
+                uint32_t x = xw[l];
+                uint32_t xi = x;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    uint32_t o = __shfl_up_sync(0xffffffffu, xi, dd);
+                    if ((int)l >= dd) xi += o;
+                }
+                dbase = __shfl_sync(0xffffffffu, xi - x, d);
+            }
+            uint32_t excl = incl - sum;
+            uint32_t run_lo = dbase + (excl & 0xffffu);
+            uint32_t run_hi = dbase + lo_tot + (excl >> 16);
+#pragma unroll
+            for (uint32_t k = 0; k < 16; k++) {
+                uint32_t vk = row[k];
+                row[k] = run_lo | (run_hi << 16);          // both < 65536 (at most 32768 items)
+                run_lo += vk & 0xffffu;
+                run_hi += vk >> 16;
+            }
+        }
+        // every thread takes its items out of `buf` before anybody scatters into it
+        uint32_t item[kSortItems];
+#pragma unroll
+        for (uint32_t i = 0; i < kSortItems; i++) item[i] = buf[t * 33u + i];
+        __syncthreads();
+#pragma unroll
+        for (uint32_t i = 0; i < kSortItems; i++) {
+            uint32_t d = (item[i] >> shift) & 31u;
+            uint32_t r = cnt16[d * 1024u + cw] + ((pre[i >> 2] >> (8u * (i & 3u))) & 0xffu);
+            buf[r + (r >> 5)] = item[i];
+        }
+        __syncthreads();
+    }
+
+    // ---- output: entries in bucket order
+    stage_bytes(smem, in, (long long)base, kWindow + 16, n);   // counters are dead; bytes again
+    __syncthreads();
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
+    uint2* Kw = K + (size_t)w * kWindow;
+    for (uint32_t r = t; r < kWindow; r += kSortThreads) {
+        uint2 e = make_uint2(0u, 0xfffe0000u);               // filler beyond cnt; never read as a candidate
+        if (r < cnt) {
+            uint32_t it = buf[r + (r >> 5)];
+            uint32_t pos = it & 0x7fffu;
+            uint32_t a = pos >> 2, sh = (pos & 3u) * 8u;
+            uint32_t w0 = sw[a], w1 = sw[a + 1], w2 = sw[a + 2];
+            uint32_t v0 = __funnelshift_r(w0, w1, sh);       // bytes 0..3
+            uint32_t v1 = __funnelshift_r(w1, w2, sh);       // bytes 4..7
+            e.x = (v0 >> 24) | (v1 << 8);                    // bytes 3..6
+            e.y = (v1 >> 24) | (tag9(v0 & 0xffu, (v0 >> 8) & 0xffu) << 8) | (pos << 17);
+        }
+        Kw[r] = e;
+    }
+    __syncthreads();
+    // ---- bucket start offsets: off[h] = number of entries with hash < h
+    uint16_t* st = reinterpret_cast<uint16_t*>(smem);        // 32768 u16, reuses the byte staging area
+    for (uint32_t i = t; i < kWindow / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(st)[i] = 0xffffffffu;
+    __syncthreads();
+    for (uint32_t r = t; r < cnt; r += kSortThreads) {
+        uint32_t h = buf[r + (r >> 5)] >> 15;
+        uint32_t hp = r > 0 ? (buf[(r - 1) + ((r - 1) >> 5)] >> 15) : 0xffffffffu;
+        if (h != hp) st[h] = (uint16_t)r;
+    }
+    __syncthreads();
+    {
+        // backward fill: an empty bucket starts where the next non-empty one starts (or at cnt)
+        uint32_t v[32];
+        const uint4* s4 = reinterpret_cast<const uint4*>(st) + t * 4u;
+        uint32_t first = 0xffffu;                             // first non-empty start in this thread's 32 buckets
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            uint4 q = s4[k];
+            uint32_t ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) { v[k * 8 + j * 2] = ww[j] & 0xffffu; v[k * 8 + j * 2 + 1] = ww[j] >> 16; }
+        }
+#pragma unroll
+        for (int k = 31; k >= 0; k--) if (v[k] != 0xffffu) first = v[k];
+        // suffix "first valid" across threads: starts increase with the bucket index, so it is a suffix minimum
+        uint32_t m = first;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            uint32_t o = __shfl_down_sync(0xffffffffu, m, dd);
+            if ((int)(t & 31u) + dd < 32) m = m < o ? m : o;
+        }
+        if ((t & 31u) == 0) xw[t >> 5] = m;                  // warp minimum
+        __syncthreads();
+        uint32_t carry = 0xffffu;                             // minimum over later warps
+        for (uint32_t k = (t >> 5) + 1; k < 32; k++) { uint32_t o = xw[k]; carry = carry < o ? carry : o; }
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, m, 1);   // suffix minimum of the lanes after this one
+        if ((t & 31u) == 31u) nxt = 0xffffu;
+        uint32_t fill = nxt < carry ? nxt : carry;
+        if (fill == 0xffffu) fill = cnt;
+#pragma unroll
+        for (int k = 31; k >= 0; k--) { if (v[k] == 0xffffu) v[k] = fill; else fill = v[k]; }
+        uint4* o4 = reinterpret_cast<uint4*>(off + (size_t)w * kWindow) + t * 4u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            uint4 q;
+            q.x = v[k * 8 + 0] | (v[k * 8 + 1] << 16); q.y = v[k * 8 + 2] | (v[k * 8 + 3] << 16);
+            q.z = v[k * 8 + 4] | (v[k * 8 + 5] << 16); q.w = v[k * 8 + 6] | (v[k * 8 + 7] << 16);
+            o4[k] = q;
         }
     }
 }
 
 // =====================================================================================
-// k_match: one CTA per window; a thread walks the candidate list of one sorted entry.
+// k_match: one CTA per window; a thread owns one sorted entry (the target) and visits its candidates
+// most recent first: the entries before it in its own bucket, then the tail of the same bucket of
+// the previous window (only positions at distance <= 32768), at most max_hash_checks in total.
+//   A visit is a coalesced 8-byte load and three logic ops (walk_passes); only the few candidates
+//   that can still beat the running best touch the data (walk_consider).  Warps stay converged: the
+//   trip count is the warp maximum and the rare path is entered on a warp vote.
 //   shared: the previous and the current window plus 258 bytes of look-ahead
 // =====================================================================================
 constexpr uint32_t kMatchThreads = 512;
 constexpr uint32_t kMatchStage = 2 * kWindow + 272;   // multiple of 16
 constexpr uint32_t kMatchSmem = kMatchStage + 16;
 
-__device__ __forceinline__ uint32_t smem_common_prefix(const uint32_t* w, uint32_t a, uint32_t b, uint32_t from,
-                                                       uint32_t maxl) {
-    uint32_t l = from;
-    while (l < maxl) {
-        uint32_t x = lds32(w, a + l) ^ lds32(w, b + l);
-        if (x) { l += (__ffs((int)x) - 1) >> 3; break; }
-        l += 4;
+struct SmemBytes {
+    const uint8_t* b;
+    const uint32_t* w;
+    __device__ __forceinline__ uint32_t byte(uint32_t i) const { return b[i]; }
+    __device__ __forceinline__ uint32_t common_prefix(uint32_t a, uint32_t c, uint32_t from, uint32_t maxl) const {
+        uint32_t l = from;
+        while (l < maxl) {
+            uint32_t x = lds32(w, a + l) ^ lds32(w, c + l);
+            if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+            l += 4;
+        }
+        return l < maxl ? l : maxl;
     }
-    return l < maxl ? l : maxl;
-}
+};
 
+template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, 2)
 k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
-        const uint32_t* __restrict__ S, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
+        const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
         uint32_t* __restrict__ Mq) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
+    SmemBytes data;
+    data.b = smem;
+    data.w = reinterpret_cast<const uint32_t*>(smem);
     const uint32_t w = w_first + blockIdx.x;
     const uint32_t base = w * kWindow;
     const uint32_t cnt = window_count(n, w);
@@ -220,73 +341,82 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     stage_bytes(smem, in, (long long)base - (long long)kWindow, kMatchStage, n);
     __syncthreads();
 
-    const uint32_t* Sj = S + (size_t)w * kWindow;
-    const uint16_t* oj = off + (size_t)w * kWindow;
-    const uint32_t* Sp = w > 0 ? S + (size_t)(w - 1) * kWindow : nullptr;
-    const uint16_t* op = w > 0 ? off + (size_t)(w - 1) * kWindow : nullptr;
+    const uint2* Kw = K + (size_t)w * kWindow;
+    const uint16_t* ow = off + (size_t)w * kWindow;
+    const uint2* Kp = w > 0 ? K + (size_t)(w - 1) * kWindow : Kw;
+    const uint16_t* op = w > 0 ? off + (size_t)(w - 1) * kWindow : ow;
     const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
     const uint32_t budget = prm.checks;
     const uint32_t qbudget = prm.checks_quarter;
-    const bool need_q = prm.need_quarter != 0;
 
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const uint32_t e = Sj[i];
-        const uint32_t pl = entry_pos(e);
+    for (uint32_t i0 = (threadIdx.x & ~31u); i0 < cnt; i0 += blockDim.x) {   // warp-uniform loop
+        const uint32_t i = i0 + lane_id();
+        bool act = i < cnt;
+        Entry me;
+        me.lo = 0; me.hi = 0;
+        if (act) { uint2 v = __ldg(Kw + i); me.lo = v.x; me.hi = v.y; }
+        const uint32_t pl = entry_pos(me.hi);
         const uint32_t p = base + pl;
-        if (p < begin) continue;
+        if (p < begin) act = false;
         const uint32_t sp = pl + kWindow;
-        const uint32_t w0 = lds32(sw, sp);
-        const uint32_t h = hash3(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-        const uint32_t my_filter = entry_filter(e);
-        const uint32_t my_tag = entry_tag(e);
-        const uint32_t maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
-        uint32_t best_len = 1, best_dist = 0, q_len = 0, q_dist = 0, k = 0;
-        bool done = false;
-
-#define DFL_CONSIDER(CE, SQ)                                                                      \
-    do {                                                                                          \
-        const uint32_t ce__ = (CE);                                                               \
-        if (entry_tag(ce__) == my_tag && !(best_len >= 3u && maxl > 3u && entry_filter(ce__) != my_filter) && \
-            best_len < maxl) {                                                                    \
-            const uint32_t sq__ = (SQ);                                                           \
-            if (smem[sq__ + best_len] == smem[sp + best_len]) {                                   \
-                uint32_t l__ = smem_common_prefix(sw, sp, sq__, 3u, maxl);                        \
-                if (l__ > best_len) {                                                             \
-                    best_len = l__;                                                               \
-                    best_dist = sp - sq__;                                                        \
-                    if (l__ == maxl) done = true;                                                 \
-                }                                                                                 \
-            }                                                                                     \
-        }                                                                                         \
-    } while (0)
-
-        const uint32_t s0 = oj[h];
-        uint32_t j = i;
-        while (j > s0 && k < budget && !done) {
-            j--;
-            if (need_q && k == qbudget) { q_len = best_len; q_dist = best_dist; }
-            k++;
-            const uint32_t ce = Sj[j];
-            DFL_CONSIDER(ce, entry_pos(ce) + kWindow);
-        }
-        if (w > 0 && !done && k < budget) {
-            const uint32_t ps = op[h];
-            const uint32_t pe = (h + 1u < kWindow) ? op[h + 1u] : cnt_prev;
-            j = pe;
-            while (j > ps && k < budget && !done) {
-                j--;
-                const uint32_t ce = Sp[j];
-                const uint32_t ql = entry_pos(ce);
-                if (ql < pl) break;              // distance would exceed 32768 (matching.rs:102-106,127)
-                if (need_q && k == qbudget) { q_len = best_len; q_dist = best_dist; }
-                k++;
-                DFL_CONSIDER(ce, ql);
+        uint32_t n_own = 0, n_tot = 0, pe = 0;
+        uint32_t maxl = 0;
+        if (act) {
+            const uint32_t w0 = lds32(data.w, sp);
+            const uint32_t h = hash3(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+            maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+            const uint32_t s0 = ow[h];
+            n_own = i - s0 < budget ? i - s0 : budget;
+            n_tot = n_own;
+            if (w > 0 && n_own < budget) {
+                // previous window: entries [ps, pe) of the same bucket whose position is >= pl
+                // (distance <= 32768, matching.rs:102-106,127); they are position sorted.
+                const uint32_t ps = op[h];
+                pe = (h + 1u < kWindow) ? op[h + 1u] : cnt_prev;
+                const uint32_t rem = budget - n_own;
+                uint32_t lo = (pe - ps > rem) ? pe - rem : ps, hi = pe;
+                // first j in [lo, pe) with pos >= pl; the oldest admissible entry is probed first
+                // because usually the whole tail qualifies
+                if (lo < hi) { if (entry_pos(__ldg(&Kp[lo].y)) >= pl) hi = lo; else lo++; }
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (entry_pos(__ldg(&Kp[mid].y)) >= pl) hi = mid; else lo = mid + 1;
+                }
+                n_tot = n_own + (pe - lo);
             }
         }
-#undef DFL_CONSIDER
-        if (need_q && k <= qbudget) { q_len = best_len; q_dist = best_dist; }
-        Mf[p] = finalize_match(best_len, best_dist);
-        if (need_q) Mq[p] = finalize_match(q_len, q_dist);
+        WalkState st = walk_init();
+        uint32_t q_len = 1, q_dist = 0;                     // best after checks_quarter candidates (lz77.rs:351-355)
+        // warp-uniform trip count
+        uint32_t trips = n_tot;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { uint32_t o = __shfl_xor_sync(0xffffffffu, trips, d); trips = trips > o ? trips : o; }
+        const uint2* ptr = Kw + i;                          // candidate k lives at ptr[-1 - k] until the switch
+        for (uint32_t k = 0; k < trips; k++) {
+            if (k == n_own) ptr = Kp + pe + k;              // so that ptr[-1 - k] == Kp[pe - 1 - (k - n_own)]
+            bool valid = k < n_tot;
+            Entry ce;
+            ce.lo = 0; ce.hi = 0;
+            if (valid) { uint2 v = __ldg(ptr - 1 - k); ce.lo = v.x; ce.hi = v.y; }
+            bool pass = valid && walk_passes(st, me, ce);
+            if (__any_sync(0xffffffffu, pass)) {
+                if (pass) {
+                    const uint32_t sq = entry_pos(ce.hi) + (k < n_own ? kWindow : 0u);
+                    walk_consider(st, data, sp, sq, me, ce, maxl);
+                    if (st.done) n_tot = k + 1;             // matching.rs:152-156: stop at max length
+                }
+            }
+            if (NEEDQ) {
+                if (valid && k + 1 == qbudget) { q_len = st.best_len; q_dist = st.best_dist; }
+            }
+        }
+        if (act) {
+            Mf[p] = finalize_match(st.best_len, st.best_dist);
+            if (NEEDQ) {
+                if (n_tot < qbudget) { q_len = st.best_len; q_dist = st.best_dist; }
+                Mq[p] = finalize_match(q_len, q_dist);
+            }
+        }
     }
 }
 
@@ -868,7 +998,9 @@ static cudaError_t ensure_attrs() {
     if (g_attr_done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
     g_attr_done = true;
     return cudaSuccess;
@@ -881,7 +1013,7 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st) 
     uint32_t w_begin = j.begin / kWindow;
     uint32_t w_first = w_begin > 0 ? w_begin - 1 : 0;
     if (n_win <= w_first) return cudaSuccess;
-    k_window_sort<<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.S, b.off);
+    k_window_sort<<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -892,7 +1024,10 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     uint32_t n_win = (j.n + kWindow - 1) / kWindow;
     uint32_t w_first = j.begin / kWindow;
     if (n_win <= w_first) return cudaSuccess;
-    k_match<<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.S, b.off, b.Mf, b.Mq);
+    if (j.prm.need_quarter)
+        k_match<true><<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.K, b.off, b.Mf, b.Mq);
+    else
+        k_match<false><<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.K, b.off, b.Mf, b.Mq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }

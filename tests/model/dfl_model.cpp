@@ -27,11 +27,11 @@ struct Cfg {
     uint32_t rounds; // parallel repair rounds before the sequential fallback
 };
 
-// ---- stage 1: per-window stable counting sort by hash3 (kernel k_window_sort)
-void window_sort(const uint8_t* d, uint32_t n, std::vector<uint32_t>& S, std::vector<uint16_t>& off,
+// ---- stage 1: per-window stable sort by hash3 into 64-bit entries (kernel k_window_sort)
+void window_sort(const uint8_t* d, uint32_t n, std::vector<Entry>& K, std::vector<uint16_t>& off,
                  std::vector<uint32_t>& cnt) {
     uint32_t nseg = (n + kWindow - 1) / kWindow;
-    S.assign((size_t)nseg * kWindow, 0);
+    K.assign((size_t)nseg * kWindow, Entry{0, 0});
     off.assign((size_t)nseg * kWindow, 0);
     cnt.assign(nseg, 0);
     uint32_t hashable = n >= 2 ? n - 2 : 0;   // positions p with p + 2 < n
@@ -47,77 +47,69 @@ void window_sort(const uint8_t* d, uint32_t n, std::vector<uint32_t>& S, std::ve
         for (uint32_t i = 0; i < c; i++) {
             uint32_t p = base + i;
             uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
-            uint32_t b3 = p + 3 < n ? d[p + 3] : 0;
-            S[(size_t)s * kWindow + cur[h]++] = pack_entry(i, d[p], d[p + 1], b3);
+            uint8_t b[8];
+            for (uint32_t k = 0; k < 8; k++) b[k] = p + k < n ? d[p + k] : 0;   // bytes past the end are 0
+            K[(size_t)s * kWindow + cur[h]++] = make_entry(i, b);
         }
     }
 }
 
-uint32_t common_prefix(const uint8_t* d, uint32_t p, uint32_t q, uint32_t maxl) {
-    uint32_t l = 0;
-    while (l < maxl && d[p + l] == d[q + l]) l++;
-    return l;
-}
+struct HostBytes {
+    const uint8_t* d;
+    uint32_t byte(uint32_t i) const { return d[i]; }
+    uint32_t common_prefix(uint32_t a, uint32_t c, uint32_t from, uint32_t maxl) const {
+        uint32_t l = from;
+        while (l < maxl && d[a + l] == d[c + l]) l++;
+        return l;
+    }
+};
 
 // ---- stage 2: candidate walk per sorted entry (kernel k_match)
-void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<uint32_t>& S,
+void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<Entry>& K,
                const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
                std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
     Mf.assign(n, 0);
     if (prm.need_quarter) Mq.assign(n, 0);
     uint32_t nseg = (uint32_t)cnt.size();
+    HostBytes data{d};
     for (uint32_t s = 0; s < nseg; s++) {
-        const uint32_t* Sj = &S[(size_t)s * kWindow];
-        const uint16_t* oj = &off[(size_t)s * kWindow];
+        const Entry* Kw = &K[(size_t)s * kWindow];
+        const uint16_t* ow = &off[(size_t)s * kWindow];
         for (uint32_t i = 0; i < cnt[s]; i++) {
-            uint32_t e = Sj[i];
-            uint32_t pl = entry_pos(e);
+            Entry me = Kw[i];
+            uint32_t pl = entry_pos(me.hi);
             uint32_t p = s * kWindow + pl;
             uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
-            uint32_t my_filter = entry_filter(e);
-            uint32_t my_tag = entry_tag(e);
             uint32_t maxl = std::min(kMaxMatch, n - p);
-            uint32_t best_len = 1, best_dist = 0;   // matching.rs:108: prev_length floor of 1
-            uint32_t q_len = 0, q_dist = 0;         // snapshot after checks_quarter candidates
-            uint32_t budget = prm.checks, k = 0;
-            bool done = false;
-            auto consider = [&](uint32_t ce, uint32_t q) {
-                // necessary conditions first (filters), then the byte compare
-                if (entry_tag(ce) != my_tag) return;             // first three bytes differ
-                if (best_len >= 3 && maxl > 3 && entry_filter(ce) != my_filter) return;  // 4th byte differs
-                if (best_len >= maxl) return;
-                if (d[q + best_len] != d[p + best_len]) return;
-                uint32_t l = common_prefix(d, p, q, maxl);
-                if (l > best_len) {
-                    best_len = l; best_dist = p - q;
-                    if (l == maxl) done = true;                   // matching.rs:152-156
-                }
-            };
-            // own window, most recent first
-            uint32_t s0 = oj[h];
-            for (uint32_t j = i; j > s0 && k < budget && !done; ) {
-                j--;
-                if (prm.need_quarter && k == prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
-                k++;
-                consider(Sj[j], s * kWindow + entry_pos(Sj[j]));
-            }
-            // previous window: only positions at distance <= 32768 (matching.rs:102-106,127)
-            if (s > 0 && !done && k < budget) {
-                const uint32_t* Sp = &S[(size_t)(s - 1) * kWindow];
+            uint32_t budget = prm.checks;
+            // own window, most recent first; then the previous window's bucket, positions at
+            // distance <= 32768 only (matching.rs:102-106,127)
+            uint32_t s0 = ow[h];
+            uint32_t n_own = std::min(budget, i - s0), n_tot = n_own, pe = 0;
+            const Entry* Kp = nullptr;
+            if (s > 0 && n_own < budget) {
+                Kp = &K[(size_t)(s - 1) * kWindow];
                 const uint16_t* op = &off[(size_t)(s - 1) * kWindow];
                 uint32_t ps = op[h];
-                uint32_t pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
-                for (uint32_t j = pe; j > ps && k < budget && !done; ) {
-                    j--;
-                    uint32_t ql = entry_pos(Sp[j]);
-                    if (ql < pl) break;
-                    if (prm.need_quarter && k == prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
-                    k++;
-                    consider(Sp[j], (s - 1) * kWindow + ql);
-                }
+                pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
+                uint32_t rem = budget - n_own;
+                uint32_t lo = (pe - ps > rem) ? pe - rem : ps;
+                while (lo < pe && entry_pos(Kp[lo].hi) < pl) lo++;
+                n_tot = n_own + (pe - lo);
             }
-            if (prm.need_quarter && k <= prm.checks_quarter) { q_len = best_len; q_dist = best_dist; }
-            Mf[p] = finalize_match(best_len, best_dist);
+            WalkState st = walk_init();
+            uint32_t q_len = 1, q_dist = 0;
+            for (uint32_t k = 0; k < n_tot; k++) {
+                Entry ce = k < n_own ? Kw[i - 1 - k] : Kp[pe - 1 - (k - n_own)];
+                if (walk_passes(st, me, ce)) {
+                    uint32_t q = (k < n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
+                    walk_consider(st, data, p, q, me, ce, maxl);
+                    if (st.done) n_tot = k + 1;
+                }
+                if (prm.need_quarter && k + 1 == prm.checks_quarter) { q_len = st.best_len; q_dist = st.best_dist; }
+            }
+            if (prm.need_quarter && n_tot < prm.checks_quarter) { q_len = st.best_len; q_dist = st.best_dist; }
+            Mf[p] = finalize_match(st.best_len, st.best_dist);
             if (prm.need_quarter) Mq[p] = finalize_match(q_len, q_dist);
         }
     }
@@ -316,7 +308,8 @@ int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy,
                   uint32_t warm, uint32_t rounds, uint8_t** out, size_t* out_len, uint32_t* stats /*[4]*/) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<uint32_t> S, cnt, Mf, Mq, tokens;
+    std::vector<Entry> S;
+    std::vector<uint32_t> cnt, Mf, Mq, tokens;
     std::vector<uint16_t> off;
     if (prm.mode != kRle && prm.checks > 0) {
         window_sort(in, n, S, off, cnt);
@@ -337,7 +330,8 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
                 uint32_t warm, uint32_t rounds, uint32_t** toks, size_t* ntoks) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<uint32_t> S, cnt, Mf, Mq, tokens;
+    std::vector<Entry> S;
+    std::vector<uint32_t> cnt, Mf, Mq, tokens;
     std::vector<uint16_t> off;
     if (prm.mode != kRle && prm.checks > 0) {
         window_sort(in, n, S, off, cnt);
