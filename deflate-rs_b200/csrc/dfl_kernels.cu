@@ -325,6 +325,96 @@ struct SmemBytes {
     }
 };
 
+// Per-lane state of one walk, kept in registers (the device-side form of dfl_core.h WalkState: the
+// model in tests/model runs walk_passes/walk_consider, this is the same logic with the frontier-byte
+// test pulled into the visit loop).
+struct Walk {
+    uint32_t best_len;    // 1 = nothing yet
+    uint32_t best_sq;     // shared-memory index of the best candidate
+    uint32_t mlo, mhi;    // entry_mask(best_len)
+    uint32_t myfb;        // target byte at offset best_len
+    uint32_t visited;
+    uint32_t q_len, q_sq; // snapshot after checks_quarter candidates
+};
+
+__device__ __forceinline__ void walk_masks(uint32_t best_len, uint32_t& mlo, uint32_t& mhi) {
+    // bytes 3 .. best_len must agree: best_len - 2 of the five entry bytes (all five from best_len 7 on)
+    uint32_t nb = (best_len < 7u ? best_len : 7u) - 2u;
+    unsigned long long m = (1ull << (8u * nb)) - 1ull;
+    mlo = (uint32_t)m;
+    mhi = kEntryTagHi | (uint32_t)(m >> 32);
+}
+
+__device__ __forceinline__ uint32_t lds_u8_if(uint32_t saddr, bool pred) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0x100;\n\t@p ld.shared.u8 %0, [%1];\n\t}"
+                 : "=r"(v) : "r"(saddr), "r"((uint32_t)pred));
+    return v;
+}
+
+// One candidate.  `foff` = shared-window address of the segment's first byte + best_len, so that
+// (position of the candidate) + foff addresses the candidate byte that would extend the best match.
+template <uint32_t SEG>
+__device__ __forceinline__ void walk_visit(Walk& wk, const SmemBytes& data, uint32_t sbase, uint32_t& foff, uint2 v, bool valid,
+                                           Entry me, uint32_t sp, uint32_t maxl, uint32_t& stop) {
+    bool pass = valid && ((((v.x ^ me.lo) & wk.mlo) | ((v.y ^ me.hi) & wk.mhi)) == 0u);
+    // The reference's quick reject: the byte that would extend the best match (matching.rs:141-143).
+    // Below 8 bytes the entry test above already implies it; from 8 on it does the filtering.
+    const uint32_t fb = lds_u8_if((v.y >> 17) + foff, pass);
+    if (fb == wk.myfb) {                            // implies pass (fb is 0x100 otherwise; myfb is a byte, or 0x200 = stopped)
+        const uint32_t sq = (v.y >> 17) + SEG;
+        uint32_t l;
+        if (wk.best_len >= kEntryBytes) {
+            l = data.common_prefix(sp, sq, kEntryBytes, maxl);
+        } else {
+            l = entry_lcp(v.x ^ me.lo, v.y ^ me.hi);
+            if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
+            l = l < maxl ? l : maxl;
+        }
+        if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
+            foff += l - wk.best_len;
+            wk.best_len = l;
+            wk.best_sq = sq;
+            walk_masks(l, wk.mlo, wk.mhi);
+            if (l == maxl) { stop = 1; wk.myfb = 0x200u; }     // matching.rs:152-156: nothing passes any more
+            else wk.myfb = data.b[sp + l];
+        }
+    }
+}
+
+// One pass over the candidates Kseg[idx], Kseg[idx - 1], ... : lane-private count n_seg, of which the
+// first `tmin` visits are valid in every lane of the warp (no per-visit bounds test) and the rest up
+// to `tmax` are ragged.  SEG is the shared-memory index of the segment's first byte (32768 for the
+// target's own window, 0 for the previous one).
+template <bool NEEDQ, uint32_t SEG>
+__device__ __forceinline__ void walk_segment(Walk& wk, const SmemBytes& data, uint32_t sbase, const uint2* __restrict__ Kseg,
+                                             int idx, uint32_t n_seg, uint32_t tmin, uint32_t tmax, Entry me, uint32_t sp,
+                                             uint32_t maxl, uint32_t qbudget, uint32_t& stop) {
+    const uint2* ptr = Kseg + idx;
+    uint32_t foff = sbase + SEG + wk.best_len;
+    uint32_t k = 0;
+    if (!NEEDQ) {
+#pragma unroll 4
+        for (; k < tmin; k++, ptr--) walk_visit<SEG>(wk, data, sbase, foff, __ldg(ptr), true, me, sp, maxl, stop);
+    }
+    for (; k < tmax; k++, ptr--) {
+        const bool valid = k < n_seg;
+        uint2 v = make_uint2(0u, 0u);
+        if (valid) v = __ldg(ptr);
+        const uint32_t was_stopped = stop;
+        walk_visit<SEG>(wk, data, sbase, foff, v, valid, me, sp, maxl, stop);
+        if (NEEDQ) {
+            if (valid && !was_stopped) {            // candidates after the stop are never visited by the reference
+                wk.visited++;
+                if (wk.visited == qbudget) { wk.q_len = wk.best_len; wk.q_sq = wk.best_sq; }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+
 template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, 2)
 k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
@@ -348,6 +438,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
     const uint32_t budget = prm.checks;
     const uint32_t qbudget = prm.checks_quarter;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 
     for (uint32_t i0 = (threadIdx.x & ~31u); i0 < cnt; i0 += blockDim.x) {   // warp-uniform loop
         const uint32_t i = i0 + lane_id();
@@ -359,7 +450,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
         const uint32_t p = base + pl;
         if (p < begin) act = false;
         const uint32_t sp = pl + kWindow;
-        uint32_t n_own = 0, n_tot = 0, pe = 0;
+        uint32_t n_own = 0, n_prev = 0, pe = 0;
         uint32_t maxl = 0;
         if (act) {
             const uint32_t w0 = lds32(data.w, sp);
@@ -367,7 +458,6 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
             maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
             const uint32_t s0 = ow[h];
             n_own = i - s0 < budget ? i - s0 : budget;
-            n_tot = n_own;
             if (w > 0 && n_own < budget) {
                 // previous window: entries [ps, pe) of the same bucket whose position is >= pl
                 // (distance <= 32768, matching.rs:102-106,127); they are position sorted.
@@ -382,39 +472,24 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                     uint32_t mid = (lo + hi) >> 1;
                     if (entry_pos(__ldg(&Kp[mid].y)) >= pl) hi = mid; else lo = mid + 1;
                 }
-                n_tot = n_own + (pe - lo);
+                n_prev = pe - lo;
             }
         }
-        WalkState st = walk_init();
-        uint32_t q_len = 1, q_dist = 0;                     // best after checks_quarter candidates (lz77.rs:351-355)
-        // warp-uniform trip count
-        uint32_t trips = n_tot;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { uint32_t o = __shfl_xor_sync(0xffffffffu, trips, d); trips = trips > o ? trips : o; }
-        const uint2* ptr = Kw + i;                          // candidate k lives at ptr[-1 - k] until the switch
-        for (uint32_t k = 0; k < trips; k++) {
-            if (k == n_own) ptr = Kp + pe + k;              // so that ptr[-1 - k] == Kp[pe - 1 - (k - n_own)]
-            bool valid = k < n_tot;
-            Entry ce;
-            ce.lo = 0; ce.hi = 0;
-            if (valid) { uint2 v = __ldg(ptr - 1 - k); ce.lo = v.x; ce.hi = v.y; }
-            bool pass = valid && walk_passes(st, me, ce);
-            if (__any_sync(0xffffffffu, pass)) {
-                if (pass) {
-                    const uint32_t sq = entry_pos(ce.hi) + (k < n_own ? kWindow : 0u);
-                    walk_consider(st, data, sp, sq, me, ce, maxl);
-                    if (st.done) n_tot = k + 1;             // matching.rs:152-156: stop at max length
-                }
-            }
-            if (NEEDQ) {
-                if (valid && k + 1 == qbudget) { q_len = st.best_len; q_dist = st.best_dist; }
-            }
-        }
+        Walk wk;
+        wk.best_len = 1; wk.best_sq = 0; wk.mlo = 0; wk.mhi = kEntryTagHi; wk.visited = 0;
+        wk.myfb = data.b[sp + 1u];
+        wk.q_len = 1; wk.q_sq = 0;
+        uint32_t stop = 0;
+        walk_segment<NEEDQ, kWindow>(wk, data, sbase, Kw, (int)i - 1, n_own, warp_min(n_own), warp_max(n_own), me, sp, maxl,
+                                     qbudget, stop);
+        if (stop) n_prev = 0;
+        walk_segment<NEEDQ, 0u>(wk, data, sbase, Kp, (int)pe - 1, n_prev, warp_min(n_prev), warp_max(n_prev), me, sp, maxl,
+                                qbudget, stop);
         if (act) {
-            Mf[p] = finalize_match(st.best_len, st.best_dist);
+            Mf[p] = finalize_match(wk.best_len, sp - wk.best_sq);
             if (NEEDQ) {
-                if (n_tot < qbudget) { q_len = st.best_len; q_dist = st.best_dist; }
-                Mq[p] = finalize_match(q_len, q_dist);
+                if (wk.visited < qbudget) { wk.q_len = wk.best_len; wk.q_sq = wk.best_sq; }
+                Mq[p] = finalize_match(wk.q_len, sp - wk.q_sq);
             }
         }
     }
