@@ -89,7 +89,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.off); dev_free(b.M); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -98,6 +98,7 @@ struct Context {
         b.tok = nullptr;
         b.cap_n = 0;
         b.cap_quarter = false;
+        b.cap_chains = false;
     }
     ~Context() {
         if (!ok) return;
@@ -109,14 +110,16 @@ struct Context {
     }
 
     // Scratch for inputs of up to n bytes (history + payload).
-    int ensure(size_t n, bool quarter) {
+    int ensure(size_t n, bool quarter, bool chains) {
         Buffers& b = buf;
-        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter)) return DFL_OK;
+        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter) && (b.cap_chains || !chains)) return DFL_OK;
         size_t cap = n + n / 8 + 65536;
+        if (cap < b.cap_n) cap = b.cap_n;      // growing one kind of scratch never shrinks another
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
         if (cap < n) return DFL_E_ARG;
         cudaStreamSynchronize(stream);
         quarter = quarter || b.cap_quarter;
+        chains = chains || b.cap_chains;
         free_buffers();
         size_t n_win = (cap + kWindow - 1) / kWindow + 1;
         size_t n_seg = (cap + kParseSeg - 1) / kParseSeg + 1;
@@ -125,6 +128,7 @@ struct Context {
         int rc = 0;
         if ((rc = dev_alloc(b.K, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
+        if (chains && (rc = dev_alloc(b.M, n_win * kSpanSlots))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
         if ((rc = dev_alloc(b.segtok, n_seg * kParseTokCap))) return rc;
@@ -149,6 +153,7 @@ struct Context {
         b.tok = reinterpret_cast<uint32_t*>(b.K);   // the candidate lists are dead once k_match has run; the token stream reuses them
         b.cap_n = cap;
         b.cap_quarter = quarter;
+        b.cap_chains = chains;
         return DFL_OK;
     }
     int ensure_stage(uint8_t*& p, size_t& cap, size_t need) {
@@ -228,7 +233,8 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     j.stop_after_tokens = stop_after_tokens;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
 
-    int rc = c.ensure(n, j.prm.need_quarter != 0);
+    const bool need_match_stage = (d_tokens_override == nullptr) && j.prm.mode != kRle && j.prm.checks > 0;
+    int rc = c.ensure(n, j.prm.need_quarter != 0, need_match_stage && use_chains(j.prm));
     if (rc) return rc;
     Buffers& b = c.buf;
     g_launch_count = 0;
@@ -386,7 +392,7 @@ extern "C" int dfl_adler32_device(const void* d_in, size_t n, uint32_t* adler, v
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
-    if ((rc = c.ensure(n ? n : 1, false))) return rc;
+    if ((rc = c.ensure(n ? n : 1, false, false))) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     CK(launch_adler32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -470,7 +476,7 @@ int encoder_fold_checksum(dfl_encoder* e, size_t to) {
     if (rc) return rc;
     size_t len = to - from;
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, e->data.size() + 64))) return rc;
-    if ((rc = c.ensure(len, false))) return rc;
+    if ((rc = c.ensure(len, false, false))) return rc;
     CK(cudaMemcpyAsync(c.d_in, e->data.data() + from, len, cudaMemcpyHostToDevice, c.stream));
     CK(launch_adler32(c.d_in, len, c.buf, c.stream));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, c.stream));

@@ -137,6 +137,50 @@ DFL_HD void walk_consider(WalkState& s, const D& data, uint32_t sp, uint32_t sq,
     }
 }
 
+// ---------------------------------------------------------------- span entries (multi-level chains)
+// The fast match path (kernel k_match_chains, max_hash_checks <= kChainMaxChecks) works on *spans*:
+// kSpanWin target windows plus the window before them, merged into one list sorted by
+// (hash3, position).  In that list the candidates of a position are simply the entries in front of
+// it: the previous `max_hash_checks` of its own bucket, cut where the distance exceeds 32768
+// (matching.rs:102-106,127-134).  A span entry is 64 bits:
+//   lo = bytes p+3 .. p+6 (little endian)
+//   hi = tag9 | first-of-bucket << 9 | position-in-span << 15   (position counted from the start of
+//        the window in front of the first target window, so targets have position >= 32768)
+// Entries prove common prefixes of 3..7 bytes; longer ones are resolved on the data.
+constexpr uint32_t kSpanWin = 1;                       // target windows per span
+constexpr uint32_t kSpanSlots = (kSpanWin + 1) * kWindow;   // entries reserved per span
+constexpr uint32_t kChainMaxChecks = 128;              // ring capacity of the chain kernel
+constexpr uint32_t kChainLevels = 5;                   // prefix lengths 3, 4, 5, 6, 7
+constexpr uint32_t kSpanTagMask = 0x1ffu;
+constexpr uint32_t kSpanFirstBit = 0x200u;
+constexpr uint32_t kSpanEntryBytes = 7;                // prefix length a span entry can prove
+DFL_HD Entry make_span_entry(uint32_t pos_in_span, const uint8_t b[7], bool first_of_bucket) {
+    Entry e;
+    e.lo = b[3] | (b[4] << 8) | (b[5] << 16) | ((uint32_t)b[6] << 24);
+    e.hi = tag9(b[0], b[1]) | (first_of_bucket ? kSpanFirstBit : 0u) | (pos_in_span << 15);
+    return e;
+}
+DFL_HD uint32_t span_entry_pos(uint32_t hi) { return hi >> 15; }
+// bytes 3 .. L-1 of the entry, L = 3 + level
+DFL_HD uint32_t span_level_mask(uint32_t level) { return level == 0u ? 0u : (0xffffffffu >> (8u * (4u - level))); }
+// 8-bit chain slot of an entry at a level: a hash of exactly the bits that define the level's key
+DFL_HD uint32_t span_sig(uint32_t lo, uint32_t hi, uint32_t level) {
+    return (((lo & span_level_mask(level)) * 0x9E3779B1u) + ((hi & kSpanTagMask) * 0x7FEB352Du) + level * 0x3C6EF372u) >> 24;
+}
+// do two entries of one bucket share their first 3 + level bytes?
+DFL_HD bool span_key_equal(Entry a, Entry b, uint32_t level) {
+    return ((((a.lo ^ b.lo) & span_level_mask(level)) | ((a.hi ^ b.hi) & kSpanTagMask)) == 0u);
+}
+// common prefix (3..7) of two entries of one bucket with equal tags
+DFL_HD uint32_t span_entry_lcp(uint32_t xlo) {
+    if (xlo == 0u) return 7u;
+#if defined(__CUDA_ARCH__)
+    return 3u + ((uint32_t)(__ffs((int)xlo) - 1) >> 3);
+#else
+    return 3u + ((uint32_t)__builtin_ctz(xlo) >> 3);
+#endif
+}
+
 // ---------------------------------------------------------------- per-position match record
 // len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23.  0 == "no usable match".
 DFL_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 9); }

@@ -55,6 +55,7 @@ struct BlockTables {
 struct Buffers {   // device scratch of one context, grown on demand
     uint2* K = nullptr;             // candidate entries in bucket order (dfl_core.h Entry), n_windows * 32768
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
+    uint2* M = nullptr;             // span entries (chain path only), n_windows * kSpanSlots
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
     uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * kParseTokCap
@@ -80,7 +81,12 @@ struct Buffers {   // device scratch of one context, grown on demand
     DevMeta* meta = nullptr;
     size_t cap_n = 0;               // input size the buffers were sized for
     bool cap_quarter = false;
+    bool cap_chains = false;
 };
+
+// The span/chain match path (k_span_scatter + k_match_chains) covers every option set whose chain
+// budget fits its ring; anything else takes the generic candidate walk (k_match).
+inline bool use_chains(const Params& p) { return p.checks >= 1 && p.checks <= kChainMaxChecks && !p.need_quarter; }
 
 struct EncodeJob {
     const uint8_t* d_in;     // device input (history + payload)

@@ -121,6 +121,7 @@ constexpr uint32_t kSortSmem = (kSortCntWords + kSortBufWords) * 4 + 256;
 static_assert(kSortItems == 32, "one item per bit of the digit/prefix packing below");
 static_assert(kWindow + 16 <= kSortCntWords * 4, "byte staging must fit in the counter area");
 
+template <bool ITEMS>   // ITEMS: emit the sorted (hash << 15 | position) words for k_span_scatter instead of entries
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
                                                                  uint16_t* __restrict__ off) {
@@ -226,6 +227,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
     }
 
     // ---- output: entries in bucket order
+    if (ITEMS) {
+        uint32_t* Iw = reinterpret_cast<uint32_t*>(K) + (size_t)w * kWindow;
+        for (uint32_t r = t; r < kWindow; r += kSortThreads) Iw[r] = buf[r + (r >> 5)];
+    } else {
     stage_bytes(smem, in, (long long)base, kWindow + 16, n);   // counters are dead; bytes again
     __syncthreads();
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
             e.y = (v1 >> 24) | (tag9(v0 & 0xffu, (v0 >> 8) & 0xffu) << 8) | (pos << 17);
         }
         Kw[r] = e;
+    }
     }
     __syncthreads();
     // ---- bucket start offsets: off[h] = number of entries with hash < h
@@ -491,6 +497,196 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                 if (wk.visited < qbudget) { wk.q_len = wk.best_len; wk.q_sq = wk.best_sq; }
                 Mq[p] = finalize_match(wk.q_len, sp - wk.q_sq);
             }
+        }
+    }
+}
+
+// =====================================================================================
+// k_span_scatter: one CTA per window.  Turns the window's sorted (hash, position) words into span
+// entries (dfl_core.h) and writes each into the one or two spans the window belongs to: as a target
+// window into span v, and as the history window into span v + 1.  Within a span the two windows'
+// lists are merged bucket by bucket (history first), so the slot of an entry is its rank in its own
+// window plus the number of entries of the other window that sort in front of it -- one lookup in
+// the other window's bucket offsets.
+// =====================================================================================
+constexpr uint32_t kScatterThreads = 512;
+
+__device__ __forceinline__ uint32_t off_at(const uint16_t* __restrict__ off, uint32_t n, uint32_t u, uint32_t h) {
+    return h < kWindow ? (uint32_t)__ldg(off + (size_t)u * kWindow + h) : window_count(n, u);
+}
+
+__global__ void __launch_bounds__(kScatterThreads) k_span_scatter(const uint8_t* __restrict__ in, uint32_t n, uint32_t w_first,
+                                                                  uint32_t w_begin, const uint32_t* __restrict__ items,
+                                                                  const uint16_t* __restrict__ off, uint2* __restrict__ M) {
+    __shared__ __align__(16) uint8_t sb[kWindow + 16];
+    const uint32_t v = w_first + blockIdx.x;
+    const uint32_t base = v * kWindow;
+    const uint32_t cnt = window_count(n, v);
+    const uint32_t n_win = (n + kWindow - 1) / kWindow;
+    stage_bytes(sb, in, (long long)base, kWindow + 16, n);
+    __syncthreads();
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb);
+    const uint32_t* Iv = items + (size_t)v * kWindow;
+    const bool as_target = v >= w_begin;             // span v exists (v is a window that gets encoded)
+    const bool as_history = v + 1 < n_win;           // span v + 1 exists
+    for (uint32_t r = threadIdx.x; r < cnt; r += kScatterThreads) {
+        const uint32_t it = __ldg(Iv + r);
+        const uint32_t h = it >> 15, pl = it & kWindowMask;
+        const bool first_own = (r == 0) || ((__ldg(Iv + r - 1) >> 15) != h);
+        const uint32_t a = pl >> 2, sh = (pl & 3u) * 8u;
+        const uint32_t w0 = sw[a], w1 = sw[a + 1], w2 = sw[a + 2];
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh);       // bytes 0..3
+        const uint32_t v1 = __funnelshift_r(w1, w2, sh);       // bytes 4..7
+        const uint32_t lo = (v0 >> 24) | (v1 << 8);            // bytes 3..6
+        const uint32_t tg = tag9(v0 & 0xffu, (v0 >> 8) & 0xffu);
+        if (as_target) {
+            uint32_t idx = r;
+            bool first = first_own;
+            if (v > 0) {
+                const uint32_t e1 = off_at(off, n, v - 1, h + 1), e0 = off_at(off, n, v - 1, h);
+                idx += e1;
+                first = first && (e1 == e0);
+            }
+            M[(size_t)v * kSpanSlots + idx] = make_uint2(lo, tg | (first ? kSpanFirstBit : 0u) | ((pl + kWindow) << 15));
+        }
+        if (as_history) {
+            const uint32_t idx = r + off_at(off, n, v + 1, h);
+            M[(size_t)(v + 1) * kSpanSlots + idx] = make_uint2(lo, tg | (first_own ? kSpanFirstBit : 0u) | (pl << 15));
+        }
+    }
+}
+
+// =====================================================================================
+// k_match_chains: one CTA per span (the window being encoded plus the window in front of it).
+//   The span's merged entry list is cut into chunks; a warp runs through a chunk 32 entries at a
+//   time and keeps, per prefix length L = 3..7, a hash-chain over the last 256 entries: head[L][slot]
+//   = latest entry whose first L bytes hash to the slot, prevd[L][entry] = distance to the previous
+//   one.  The 32 entries of a step are linked among themselves with match.any.  A target then finds
+//   "the nearest candidate sharing at least L bytes" by following chain L until an entry with an equal
+//   key turns up or the candidate range ends -- the range being the previous max_hash_checks entries of
+//   its bucket (matching.rs:127: the chain budget counts every position with the same hash).
+//   The reference's walk keeps the first candidate that beats the running best; that is reproduced by
+//   asking for L = 3, then for (length found) + 1, and so on.  Prefixes of 7 and more bytes are resolved
+//   on the data staged in shared memory, with the reference's own quick reject (matching.rs:141-143).
+//   shared: 64 KiB + 272 B of data, and per warp 256 ring entries, 5 x 256 chain links, 5 x 128 heads
+// =====================================================================================
+constexpr uint32_t kChainWarps = 16;
+constexpr uint32_t kChainThreads = kChainWarps * 32;
+constexpr uint32_t kChainChunk = 2048;                  // entries per chunk (a warp takes every kChainWarps-th chunk)
+constexpr uint32_t kChainCtx = kChainMaxChecks;         // entries re-inserted in front of a chunk
+constexpr uint32_t kChainSlots = 128;                   // head slots per level
+constexpr uint32_t kChainRing = 256;
+constexpr uint32_t kChainData = 2 * kWindow + 272;
+constexpr uint32_t kChainWarpBytes = kChainRing * 8 + kChainLevels * kChainRing + kChainLevels * kChainSlots * 2;
+constexpr uint32_t kChainSmem = kChainData + kChainWarps * kChainWarpBytes + 16;
+static_assert(kChainCtx % 32 == 0 && kChainCtx + 32 + 32 <= kChainRing, "ring must hold the candidate range of a whole step");
+static_assert(kChainChunk + kChainCtx + kChainRing < 65536, "local indices are 16 bit");
+
+__global__ void __launch_bounds__(kChainThreads, 1)
+k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, uint32_t checks,
+               const uint2* __restrict__ M, uint32_t* __restrict__ Mf) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t w = w_first + blockIdx.x;
+    const uint32_t base = w * kWindow;                   // first byte of the target window
+    const uint32_t cnt_t = window_count(n, w);
+    const uint32_t ne = cnt_t + (w > 0 ? window_count(n, w - 1) : 0u);
+    if (cnt_t == 0) return;
+    // shared data index of absolute position a is a - base + 32768 == position-in-span
+    stage_bytes(smem, in, (long long)base - (long long)kWindow, kChainData, n);
+    __syncthreads();
+    const uint8_t* data = smem;
+    const uint32_t* dataw = reinterpret_cast<const uint32_t*>(smem);
+    uint8_t* wbase = smem + kChainData + warp_id() * kChainWarpBytes;
+    uint2* ring = reinterpret_cast<uint2*>(wbase);                                   // kChainRing entries
+    uint8_t* prevd = wbase + kChainRing * 8;                                         // [level][ring slot]
+    uint16_t* head = reinterpret_cast<uint16_t*>(prevd + kChainLevels * kChainRing); // [level][slot]
+    const uint2* E = M + (size_t)w * kSpanSlots;
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t a = warp_id() * kChainChunk; a < ne; a += kChainWarps * kChainChunk) {
+        const uint32_t ctx = a >= kChainCtx ? a - kChainCtx : 0u;
+        const uint32_t b = a + kChainChunk < ne ? a + kChainChunk : ne;
+        for (uint32_t i = lane; i < kChainLevels * kChainSlots / 2; i += 32) reinterpret_cast<uint32_t*>(head)[i] = 0u;
+        for (uint32_t i = lane; i < kChainLevels * kChainRing / 4; i += 32) reinterpret_cast<uint32_t*>(prevd)[i] = 0u;
+        __syncwarp();
+        uint32_t bs_carry = kChainRing;                  // local index of the first entry of the current bucket
+        uint2 nxt = make_uint2(0u, 0u);
+        if (ctx + lane < b) nxt = __ldg(E + ctx + lane);
+        for (uint32_t m0 = ctx; m0 < b; m0 += 32) {
+            const uint32_t m = m0 + lane;
+            const bool valid = m < b;
+            const uint2 e = nxt;
+            if (m + 32 < b) nxt = __ldg(E + m + 32);
+            const uint32_t li0 = m0 - ctx + kChainRing;  // local index of lane 0; never 0, so a zero head means "none"
+            const uint32_t li = li0 + lane;
+            if (valid) ring[li & (kChainRing - 1)] = e;
+            const uint32_t fmask = __ballot_sync(0xffffffffu, valid && (e.y & kSpanFirstBit));
+            const uint32_t fle = fmask & (lt_mask | (1u << lane));
+            const uint32_t bs = fle ? li0 + (31u - (uint32_t)__clz((int)fle)) : bs_carry;
+            if (fmask) bs_carry = li0 + (31u - (uint32_t)__clz((int)fmask));
+            // ---- link the 32 entries into the chains of every level
+#pragma unroll
+            for (uint32_t lv = 0; lv < kChainLevels; lv++) {
+                const uint32_t sg = span_sig(e.x, e.y, lv) >> 1;               // 7 bits
+                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? sg : (0x100u | lane));
+                const uint32_t below = grp & lt_mask;
+                uint32_t pi = below ? li0 + (31u - (uint32_t)__clz((int)below)) : (uint32_t)head[lv * kChainSlots + sg];
+                const uint32_t dl = li - pi;
+                if (valid) {
+                    prevd[lv * kChainRing + (li & (kChainRing - 1))] = (uint8_t)(dl < kChainRing ? dl : 0u);
+                    if ((grp >> lane) == 1u) head[lv * kChainSlots + sg] = (uint16_t)li;
+                }
+            }
+            __syncwarp();
+            // ---- targets of this step: entries of the window being encoded, at or after `begin`
+            const uint32_t pos = span_entry_pos(e.y);
+            const uint32_t p = base + pos - kWindow;
+            if (valid && m >= a && pos >= kWindow && p >= begin) {
+                const uint32_t maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                const uint32_t lb = bs > li - checks ? bs : li - checks;
+                uint32_t best_len = 1, best_pos = pos;
+                uint32_t lvl = 0, mask = 0;
+                bool deep = false;
+                uint32_t j = li;
+                for (;;) {
+                    const uint32_t dl = prevd[lvl * kChainRing + (j & (kChainRing - 1))];
+                    j -= dl;
+                    if (dl == 0 || j < lb) break;
+                    const uint2 ce = ring[j & (kChainRing - 1)];
+                    const uint32_t xlo = ce.x ^ e.x;
+                    if (((xlo & mask) | ((ce.y ^ e.y) & kSpanTagMask)) != 0u) continue;     // slot collision
+                    const uint32_t cpos = span_entry_pos(ce.y);
+                    if (pos - cpos > kWindow) break;                                          // matching.rs:102-106
+                    if (!deep) {
+                        const uint32_t l = span_entry_lcp(xlo);
+                        if (l >= maxl) { best_len = maxl; best_pos = cpos; break; }
+                        if (l < kSpanEntryBytes) {
+                            // nearest candidate with >= lvl + 3 bytes has exactly l: now look for l + 1
+                            best_len = l; best_pos = cpos;
+                            lvl = l - 2u; mask = span_level_mask(lvl);
+                            j = li;
+                            continue;
+                        }
+                        deep = true; lvl = kChainLevels - 1; mask = 0xffffffffu;
+                    }
+                    // a candidate sharing 7+ bytes: reference's quick reject, then the real length
+                    if (best_len >= kSpanEntryBytes && data[cpos + best_len] != data[pos + best_len]) continue;
+                    uint32_t l = kSpanEntryBytes;
+                    while (l < maxl) {
+                        const uint32_t x = lds32(dataw, pos + l) ^ lds32(dataw, cpos + l);
+                        if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        l += 4;
+                    }
+                    l = l < maxl ? l : maxl;
+                    if (l > best_len) {
+                        best_len = l; best_pos = cpos;
+                        if (l == maxl) break;                                                 // matching.rs:152-156
+                    }
+                }
+                Mf[p] = finalize_match(best_len, pos - best_pos);
+            }
+            __syncwarp();
         }
     }
 }
@@ -1071,7 +1267,11 @@ static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
 static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
     if (g_attr_done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_window_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_window_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
@@ -1088,7 +1288,15 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st) 
     uint32_t w_begin = j.begin / kWindow;
     uint32_t w_first = w_begin > 0 ? w_begin - 1 : 0;
     if (n_win <= w_first) return cudaSuccess;
-    k_window_sort<<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
+    if (use_chains(j.prm)) {
+        k_window_sort<true><<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
+        DFL_LAUNCH_CHECK();
+        k_span_scatter<<<n_win - w_first, kScatterThreads, 0, st>>>(j.d_in, j.n, w_first, w_begin,
+                                                                     reinterpret_cast<const uint32_t*>(b.K), b.off, b.M);
+        DFL_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
+    k_window_sort<false><<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1099,6 +1307,11 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     uint32_t n_win = (j.n + kWindow - 1) / kWindow;
     uint32_t w_first = j.begin / kWindow;
     if (n_win <= w_first) return cudaSuccess;
+    if (use_chains(j.prm)) {
+        k_match_chains<<<n_win - w_first, kChainThreads, kChainSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm.checks, b.M, b.Mf);
+        DFL_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     if (j.prm.need_quarter)
         k_match<true><<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.K, b.off, b.Mf, b.Mq);
     else

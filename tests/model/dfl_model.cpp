@@ -115,6 +115,172 @@ void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vecto
     }
 }
 
+// ---- stage 1b/2b: the span path (kernels k_window_sort<items>, k_span_scatter, k_match_chains)
+// Sorted positions per window -> per-span merged entry lists -> multi-level chains walked per target.
+uint64_t g_chain_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // targets, level queries, chain steps, deep compares
+
+void window_sort_items(const uint8_t* d, uint32_t n, std::vector<uint32_t>& items, std::vector<uint16_t>& off,
+                       std::vector<uint32_t>& cnt) {
+    uint32_t nwin = (n + kWindow - 1) / kWindow;
+    items.assign((size_t)nwin * kWindow, 0);
+    off.assign((size_t)nwin * kWindow, 0);
+    cnt.assign(nwin, 0);
+    uint32_t hashable = n >= 2 ? n - 2 : 0;
+    for (uint32_t v = 0; v < nwin; v++) {
+        uint32_t base = v * kWindow;
+        uint32_t c = hashable > base ? std::min(kWindow, hashable - base) : 0;
+        cnt[v] = c;
+        std::vector<uint32_t> hist(kWindow + 1, 0);
+        for (uint32_t i = 0; i < c; i++) hist[hash3(d[base + i], d[base + i + 1], d[base + i + 2]) + 1]++;
+        for (uint32_t h = 0; h < kWindow; h++) hist[h + 1] += hist[h];
+        for (uint32_t h = 0; h < kWindow; h++) off[(size_t)v * kWindow + h] = (uint16_t)hist[h];
+        std::vector<uint32_t> cur(hist.begin(), hist.end() - 1);
+        for (uint32_t i = 0; i < c; i++) {
+            uint32_t h = hash3(d[base + i], d[base + i + 1], d[base + i + 2]);
+            items[(size_t)v * kWindow + cur[h]++] = (h << 15) | i;
+        }
+    }
+}
+
+void span_scatter(const uint8_t* d, uint32_t n, const std::vector<uint32_t>& items, const std::vector<uint16_t>& off,
+                  const std::vector<uint32_t>& cnt, std::vector<Entry>& M, std::vector<uint32_t>& span_cnt) {
+    uint32_t nwin = (uint32_t)cnt.size();
+    uint32_t nspan = (nwin + kSpanWin - 1) / kSpanWin;
+    M.assign((size_t)nspan * kSpanSlots, Entry{0, 0});
+    span_cnt.assign(nspan, 0);
+    auto offx = [&](uint32_t u, uint32_t h) { return h < kWindow ? (uint32_t)off[(size_t)u * kWindow + h] : cnt[u]; };
+    for (uint32_t s = 0; s < nspan; s++) {
+        uint32_t w_lo = s * kSpanWin > 0 ? s * kSpanWin - 1 : 0, w_hi = std::min(nwin, s * kSpanWin + kSpanWin);
+        for (uint32_t v = w_lo; v < w_hi; v++) {
+            span_cnt[s] += cnt[v];
+            for (uint32_t r = 0; r < cnt[v]; r++) {
+                uint32_t it = items[(size_t)v * kWindow + r];
+                uint32_t h = it >> 15, pl = it & kWindowMask, p = v * kWindow + pl;
+                uint32_t idx = r;
+                bool first = (r == offx(v, h));
+                for (uint32_t u = w_lo; u < w_hi; u++) {
+                    if (u < v) { idx += offx(u, h + 1); if (offx(u, h + 1) != offx(u, h)) first = false; }
+                    else if (u > v) idx += offx(u, h);
+                }
+                uint8_t b[7];
+                for (uint32_t k = 0; k < 7; k++) b[k] = p + k < n ? d[p + k] : 0;
+                uint32_t pos_in_span = p - s * kSpanWin * kWindow + kWindow;
+                M[(size_t)s * kSpanSlots + idx] = make_span_entry(pos_in_span, b, first);
+            }
+        }
+    }
+}
+
+constexpr uint32_t kModelChainChunk = 2048;   // entries per warp chunk
+constexpr uint32_t kModelChainCtx = 128;      // entries re-inserted in front of a chunk
+
+void match_all_chains(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<Entry>& M,
+                      const std::vector<uint32_t>& span_cnt, std::vector<uint32_t>& Mf) {
+    Mf.assign(n, 0);
+    HostBytes data{d};
+    const uint32_t c = prm.checks;
+    for (uint32_t s = 0; s < span_cnt.size(); s++) {
+        const Entry* E = &M[(size_t)s * kSpanSlots];
+        const uint32_t ne = span_cnt[s];
+        const uint32_t span_base = s * kSpanWin * kWindow;
+        for (uint32_t a = 0; a < ne; a += kModelChainChunk) {
+            const uint32_t ctx = a >= kModelChainCtx ? a - kModelChainCtx : 0;
+            const uint32_t b = std::min(ne, a + kModelChainChunk);
+            uint16_t head[kChainLevels][128];
+            uint8_t prevd[kChainLevels][256];
+            Entry ring[256];
+            memset(head, 0, sizeof(head));
+            memset(prevd, 0, sizeof(prevd));
+            uint32_t bstart = 256;                       // local index of the current bucket's first entry
+            for (uint32_t m = ctx; m < b; m++) {
+                const uint32_t i = m - ctx + 256;       // local index: never 0, so a zero head means "none"
+                const Entry me = E[m];
+                ring[i & 255] = me;
+                if (me.hi & kSpanFirstBit) bstart = i;
+                for (uint32_t lv = 0; lv < kChainLevels; lv++) {
+                    uint32_t sg = span_sig(me.lo, me.hi, lv) >> 1;   // 7-bit slot, as in the kernel
+                    uint32_t dl = i - head[lv][sg];
+                    prevd[lv][i & 255] = (uint8_t)(dl < 256 ? dl : 0);
+                    head[lv][sg] = (uint16_t)i;
+                }
+                const uint32_t pos = span_entry_pos(me.hi);
+                if (m < a || pos < kWindow) continue;   // context or history entry: not a target here
+                const uint32_t p = span_base + pos - kWindow;
+                const uint32_t maxl = std::min(kMaxMatch, n - p);
+                const uint32_t lb = std::max(bstart, i > c ? i - c : 0u);
+                uint32_t best_len = 1, best_q = 0, level = 0;
+                bool deep = false, done = false;
+                g_chain_stats[0]++;
+                while (level < kChainLevels && !done && !deep) {
+                    g_chain_stats[1]++;
+                    uint32_t j = i;
+                    bool found = false;
+                    Entry ce{0, 0};
+                    for (;;) {
+                        uint32_t dl = prevd[level][j & 255];
+                        if (dl == 0) break;
+                        j -= dl;
+                        if (j < lb) break;
+                        g_chain_stats[2]++;
+                        ce = ring[j & 255];
+                        if (span_key_equal(me, ce, level)) { found = true; break; }
+                        g_chain_stats[4]++;
+                    }
+                    if (!found) break;
+                    if (pos - span_entry_pos(ce.hi) > kWindow) break;      // matching.rs:102-106: beyond the window
+                    uint32_t l = span_entry_lcp(ce.lo ^ me.lo);
+                    uint32_t q = span_base + span_entry_pos(ce.hi) - kWindow;
+                    if (l >= maxl) { best_len = maxl; best_q = q; done = true; break; }
+                    if (l == kSpanEntryBytes) { deep = true; break; }
+                    best_len = l; best_q = q; level = l - 2;
+                }
+                if (deep) {
+                    // every candidate sharing 7+ bytes, nearest first: the reference's quick reject on the byte
+                    // that would extend the best match (matching.rs:141-143), then the real length
+                    g_chain_stats[7]++;
+                    uint32_t j = i;
+                    const uint32_t lv = kChainLevels - 1;
+                    for (;;) {
+                        uint32_t dl = prevd[lv][j & 255];
+                        if (dl == 0) break;
+                        j -= dl;
+                        if (j < lb) break;
+                        g_chain_stats[5]++;
+                        Entry ce = ring[j & 255];
+                        if (!span_key_equal(me, ce, lv)) { g_chain_stats[6]++; continue; }
+                        if (pos - span_entry_pos(ce.hi) > kWindow) break;
+                        uint32_t q = span_base + span_entry_pos(ce.hi) - kWindow;
+                        if (best_len >= kSpanEntryBytes && d[q + best_len] != d[p + best_len]) continue;
+                        g_chain_stats[3]++;
+                        uint32_t l = data.common_prefix(p, q, kSpanEntryBytes, maxl);
+                        if (l > best_len) { best_len = l; best_q = q; if (l == maxl) break; }
+                    }
+                }
+                Mf[p] = finalize_match(best_len, p - best_q);
+            }
+        }
+    }
+}
+
+int g_match_impl = 1;   // 0 = candidate walk (k_match), 1 = span chains (k_match_chains) when the options allow it
+bool use_chains(const Params& prm) { return g_match_impl == 1 && prm.checks <= kChainMaxChecks && !prm.need_quarter; }
+
+void find_matches(const uint8_t* in, uint32_t n, const Params& prm, std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
+    std::vector<uint32_t> cnt;
+    std::vector<uint16_t> off;
+    if (use_chains(prm)) {
+        std::vector<uint32_t> items, span_cnt;
+        std::vector<Entry> M;
+        window_sort_items(in, n, items, off, cnt);
+        span_scatter(in, n, items, off, cnt, M, span_cnt);
+        match_all_chains(in, n, prm, M, span_cnt, Mf);
+    } else {
+        std::vector<Entry> S;
+        window_sort(in, n, S, off, cnt);
+        match_all(in, n, prm, S, off, cnt, Mf, Mq);
+    }
+}
+
 // ---- stage 3: speculative segment parse + hand-off verification + repair (k_parse*, k_verify)
 struct SegRec {
     uint32_t e_pos, e_key, e_tok;   // first iteration at or after the segment start
@@ -308,13 +474,8 @@ int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy,
                   uint32_t warm, uint32_t rounds, uint8_t** out, size_t* out_len, uint32_t* stats /*[4]*/) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<Entry> S;
-    std::vector<uint32_t> cnt, Mf, Mq, tokens;
-    std::vector<uint16_t> off;
-    if (prm.mode != kRle && prm.checks > 0) {
-        window_sort(in, n, S, off, cnt);
-        match_all(in, n, prm, S, off, cnt, Mf, Mq);
-    }
+    std::vector<uint32_t> Mf, Mq, tokens;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
     parse_all(prm, cfg, in, n, Mf, Mq, tokens);
     std::vector<uint8_t> o;
     emit_blocks(in, n, tokens, o, 1);
@@ -330,13 +491,8 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
                 uint32_t warm, uint32_t rounds, uint32_t** toks, size_t* ntoks) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<Entry> S;
-    std::vector<uint32_t> cnt, Mf, Mq, tokens;
-    std::vector<uint16_t> off;
-    if (prm.mode != kRle && prm.checks > 0) {
-        window_sort(in, n, S, off, cnt);
-        match_all(in, n, prm, S, off, cnt, Mf, Mq);
-    }
+    std::vector<uint32_t> Mf, Mq, tokens;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
     parse_all(prm, cfg, in, n, Mf, Mq, tokens);
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
@@ -350,4 +506,8 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 }
 
 void dflm_free(void* p) { free(p); }
+void dflm_set_match_impl(int impl) { g_match_impl = impl; }
+void dflm_chain_stats(uint64_t* o /*[8]*/, int reset) {
+    for (int i = 0; i < 8; i++) { o[i] = g_chain_stats[i]; if (reset) g_chain_stats[i] = 0; }
+}
 }
