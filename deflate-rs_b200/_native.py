@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeflate_b200.so")
+# DFL_LIB_PATH: tuning hook (tools/tune_variants.sh builds several libraries with different kernel constants)
+LIB_PATH = os.environ.get("DFL_LIB_PATH") or os.path.join(_HERE, "libdeflate_b200.so")
 
 RAW, ZLIB, GZIP = 0, 1, 2
 FLUSH_SYNC, FLUSH_FINISH = 1, 2

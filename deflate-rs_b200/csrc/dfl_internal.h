@@ -86,7 +86,10 @@ struct Buffers {   // device scratch of one context, grown on demand
 
 // The span/chain match path (k_span_scatter + k_match_chains) covers every option set whose chain
 // budget fits its ring; anything else takes the generic candidate walk (k_match).
-inline bool use_chains(const Params& p) { return p.checks >= 1 && p.checks <= kChainMaxChecks && !p.need_quarter; }
+extern int g_match_path;   // 0 = candidate walk everywhere, 1 = chains where they apply (dfl_kernels.cu; DFL_MATCH_PATH)
+inline bool use_chains(const Params& p) {
+    return g_match_path == 1 && p.checks >= 1 && p.checks <= kChainMaxChecks && !p.need_quarter;
+}
 
 struct EncodeJob {
     const uint8_t* d_in;     // device input (history + payload)

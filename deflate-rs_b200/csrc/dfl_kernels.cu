@@ -16,12 +16,19 @@
 //                   bitstream.rs:76-86, stored_block.rs:13-40)
 //   k_adler32*      Adler-32 of the input (checksum.rs:33-57), k_finalize container bytes
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "dfl_internal.h"
 
 namespace dfl {
 
 int g_launch_count = 0;
+// Which match path serves option sets both can handle.  Results are identical; the switch exists so
+// that the two can be timed against each other (bench.py --match-path, tools/).
+int g_match_path = [] {
+    const char* e = getenv("DFL_MATCH_PATH");
+    return (e && e[0] == 'c') ? 1 : 0;   // "chains" | "walk" (default)
+}();
 
 #define DFL_LAUNCH_CHECK()                         \
     do {                                           \
@@ -559,28 +566,53 @@ __global__ void __launch_bounds__(kScatterThreads) k_span_scatter(const uint8_t*
 // =====================================================================================
 // k_match_chains: one CTA per span (the window being encoded plus the window in front of it).
 //   The span's merged entry list is cut into chunks; a warp runs through a chunk 32 entries at a
-//   time and keeps, per prefix length L = 3..7, a hash-chain over the last 256 entries: head[L][slot]
-//   = latest entry whose first L bytes hash to the slot, prevd[L][entry] = distance to the previous
-//   one.  The 32 entries of a step are linked among themselves with match.any.  A target then finds
-//   "the nearest candidate sharing at least L bytes" by following chain L until an entry with an equal
-//   key turns up or the candidate range ends -- the range being the previous max_hash_checks entries of
-//   its bucket (matching.rs:127: the chain budget counts every position with the same hash).
-//   The reference's walk keeps the first candidate that beats the running best; that is reproduced by
-//   asking for L = 3, then for (length found) + 1, and so on.  Prefixes of 7 and more bytes are resolved
-//   on the data staged in shared memory, with the reference's own quick reject (matching.rs:141-143).
-//   shared: 64 KiB + 272 B of data, and per warp 256 ring entries, 5 x 256 chain links, 5 x 128 heads
+//   time and keeps, per prefix length L = 3..7, a hash chain over the most recent entries:
+//   head[L][slot] = latest entry whose first L bytes hash to the slot, prevd[L][entry] = distance to
+//   the previous one.  The 32 entries of a step are linked among themselves with match.any.
+//   A target finds "the nearest candidate sharing at least L bytes" by following chain L until an
+//   entry with an equal key turns up or its candidate range ends -- the range being the previous
+//   max_hash_checks entries of its bucket (matching.rs:127: the chain budget counts every position
+//   with the same hash).  The reference keeps the first candidate that beats the running best;
+//   that is reproduced by asking for L = 3, then for (length found) + 1, and so on ("level walk").
+//   Once a candidate shares 7 bytes the remaining work is the reference's own loop restricted to
+//   chain 7: quick reject on the byte that would extend the best match (matching.rs:141-143), full
+//   comparison on the data staged in shared memory otherwise ("deep walk").
+//   Both walks are run as work loops: targets are queued, every lane of the warp owns one target at
+//   a time, makes one chain step per iteration and takes the next target when it is done, so lanes
+//   stay busy however uneven the chains are.  Full comparisons are batched: a lane whose candidate
+//   passed the quick reject parks until enough lanes wait.
+//   shared: 64 KiB + 272 B of data; per warp 256 entries, 4 x 256 + 512 chain links, 512 positions,
+//   5 x 128 heads and the two queues
 // =====================================================================================
-constexpr uint32_t kChainWarps = 16;
+#ifndef DFL_CHAIN_WARPS
+#define DFL_CHAIN_WARPS 24
+#endif
+#ifndef DFL_CHAIN_DEEP_STEPS
+#define DFL_CHAIN_DEEP_STEPS 4
+#endif
+#ifndef DFL_CHAIN_PARK_MIN
+#define DFL_CHAIN_PARK_MIN 8
+#endif
+#ifndef DFL_CHAIN_CHUNK
+#define DFL_CHAIN_CHUNK 1024
+#endif
+constexpr uint32_t kChainWarps = DFL_CHAIN_WARPS;
 constexpr uint32_t kChainThreads = kChainWarps * 32;
-constexpr uint32_t kChainChunk = 2048;                  // entries per chunk (a warp takes every kChainWarps-th chunk)
 constexpr uint32_t kChainCtx = kChainMaxChecks;         // entries re-inserted in front of a chunk
 constexpr uint32_t kChainSlots = 128;                   // head slots per level
-constexpr uint32_t kChainRing = 256;
+constexpr uint32_t kChainRingS = 256;                   // entries + links of levels 3..6: alive during the level walk
+constexpr uint32_t kChainRingD = 512;                   // level-7 links + positions: alive during the deep walk
+constexpr uint32_t kChainLQ = 64, kChainDQ = 64;        // queue capacities (a step adds at most 32 to each)
+constexpr int kChainDeepSteps = DFL_CHAIN_DEEP_STEPS;                      // chain steps per iteration of the deep work loop
+constexpr uint32_t kChainParkMin = DFL_CHAIN_PARK_MIN;                   // parked lanes that trigger a comparison round
 constexpr uint32_t kChainData = 2 * kWindow + 272;
-constexpr uint32_t kChainWarpBytes = kChainRing * 8 + kChainLevels * kChainRing + kChainLevels * kChainSlots * 2;
+constexpr uint32_t kChainWarpBytes = kChainRingS * 8 + (kChainLevels - 1) * kChainRingS + kChainRingD + kChainRingD * 2 +
+                                     kChainLevels * kChainSlots * 2 + kChainLQ * 4 + kChainDQ * 8;
 constexpr uint32_t kChainSmem = kChainData + kChainWarps * kChainWarpBytes + 16;
-static_assert(kChainCtx % 32 == 0 && kChainCtx + 32 + 32 <= kChainRing, "ring must hold the candidate range of a whole step");
-static_assert(kChainChunk + kChainCtx + kChainRing < 65536, "local indices are 16 bit");
+static_assert(kChainCtx % 32 == 0 && kChainCtx + 96 <= kChainRingS, "the small ring must hold a step, its range and some slack");
+constexpr uint32_t kChainChunk = DFL_CHAIN_CHUNK;                  // entries per unit of work
+static_assert(kChainChunk + 32 + kChainCtx + kChainRingD < 65536, "local indices are 16 bit");
+static_assert(kChainSmem <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(kChainThreads, 1)
 k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, uint32_t checks,
@@ -593,24 +625,180 @@ k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint3
     if (cnt_t == 0) return;
     // shared data index of absolute position a is a - base + 32768 == position-in-span
     stage_bytes(smem, in, (long long)base - (long long)kWindow, kChainData, n);
+    uint32_t* next_chunk = reinterpret_cast<uint32_t*>(smem + kChainData + kChainWarps * kChainWarpBytes);
+    if (threadIdx.x == 0) *next_chunk = 0u;
     __syncthreads();
     const uint8_t* data = smem;
     const uint32_t* dataw = reinterpret_cast<const uint32_t*>(smem);
     uint8_t* wbase = smem + kChainData + warp_id() * kChainWarpBytes;
-    uint2* ring = reinterpret_cast<uint2*>(wbase);                                   // kChainRing entries
-    uint8_t* prevd = wbase + kChainRing * 8;                                         // [level][ring slot]
-    uint16_t* head = reinterpret_cast<uint16_t*>(prevd + kChainLevels * kChainRing); // [level][slot]
+    uint2* ring = reinterpret_cast<uint2*>(wbase);                                        // [kChainRingS]
+    uint8_t* prevs = wbase + kChainRingS * 8;                                             // [level 0..3][kChainRingS]
+    uint8_t* prev7 = prevs + (kChainLevels - 1) * kChainRingS;                            // [kChainRingD]
+    uint16_t* cpos16 = reinterpret_cast<uint16_t*>(prev7 + kChainRingD);                  // [kChainRingD]
+    uint16_t* head = cpos16 + kChainRingD;                                                // [level][slot]
+    uint32_t* lq = reinterpret_cast<uint32_t*>(head + kChainLevels * kChainSlots);        // li | lb << 16
+    uint2* dq = reinterpret_cast<uint2*>(lq + kChainLQ);                                  // + best_len | best_pos << 9
     const uint2* E = M + (size_t)w * kSpanSlots;
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr uint32_t MS = kChainRingS - 1, MD = kChainRingD - 1;
+    constexpr uint32_t kTop = kChainLevels - 1;
 
-    for (uint32_t a = warp_id() * kChainChunk; a < ne; a += kChainWarps * kChainChunk) {
+    // ---- level walk state (one target per lane)
+    bool l_busy = false;
+    uint32_t l_elo = 0, l_ehi = 0, l_li = 0, l_lb = 0, l_j = 0, l_lvl = 0, l_mask = 0, l_best_len = 1, l_best_pos = 0, l_maxl = 0;
+    uint32_t lq_head = 0, lq_tail = 0;                   // warp-uniform
+    // ---- deep walk state
+    uint32_t d_state = 0;                                // 0 idle, 1 walking, 2 parked on a candidate that passed the quick reject
+    uint32_t d_link = 0, d_pos = 0, d_lb = 0, d_j = 0, d_best_len = 0, d_best_pos = 0, d_maxl = 0, d_myfb = 0, d_cpos = 0;
+    uint32_t dq_head = 0, dq_tail = 0;
+
+    auto level_iterate = [&]() {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !l_busy);
+        const uint32_t avail = lq_tail - lq_head;
+        if (idle != 0u && avail != 0u) {
+            const uint32_t r = __popc(idle & lt_mask);
+            if (!l_busy && r < avail) {
+                const uint32_t t = lq[(lq_head + r) & (kChainLQ - 1)];
+                l_li = t & 0xffffu; l_lb = t >> 16;
+                const uint2 e = ring[l_li & MS];
+                l_elo = e.x; l_ehi = e.y;
+                const uint32_t p = base + span_entry_pos(e.y) - kWindow;
+                l_maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                l_j = l_li; l_lvl = 0; l_mask = 0; l_best_len = 1; l_best_pos = span_entry_pos(e.y);
+                l_busy = true;
+            }
+            const uint32_t taken = __popc(idle);
+            lq_head += taken < avail ? taken : avail;
+        }
+        bool to_deep = false;
+        if (l_busy) {
+            const uint32_t pos = span_entry_pos(l_ehi);
+            const uint32_t dl = (l_lvl == kTop) ? prev7[l_j & MD] : prevs[l_lvl * kChainRingS + (l_j & MS)];
+            l_j -= dl;                                    // a link of 255 means "none": it always leaves the range
+            bool fin = l_j < l_lb;
+            if (!fin) {
+                const uint2 ce = ring[l_j & MS];
+                const uint32_t xlo = ce.x ^ l_elo;
+                if (((xlo & l_mask) | ((ce.y ^ l_ehi) & kSpanTagMask)) == 0u) {             // else: slot collision, walk on
+                    const uint32_t cpos = span_entry_pos(ce.y);
+                    const uint32_t l = span_entry_lcp(xlo);
+                    if (pos - cpos > kWindow) fin = true;                                     // matching.rs:102-106
+                    else if (l >= l_maxl) { l_best_len = l_maxl; l_best_pos = cpos; fin = true; }
+                    else if (l < kSpanEntryBytes) {
+                        // the nearest candidate with >= lvl + 3 bytes has exactly l: now look for l + 1
+                        l_best_len = l; l_best_pos = cpos;
+                        l_lvl = l - 2u; l_mask = span_level_mask(l_lvl);
+                        l_j = l_li;
+                    } else to_deep = true;
+                }
+            }
+            if (fin) {
+                Mf[base + pos - kWindow] = finalize_match(l_best_len, pos - l_best_pos);
+                l_busy = false;
+            }
+        }
+        const uint32_t dmask = __ballot_sync(0xffffffffu, to_deep);
+        if (dmask) {
+            if (to_deep) {
+                dq[(dq_tail + __popc(dmask & lt_mask)) & (kChainDQ - 1)] =
+                    make_uint2(l_li | (l_lb << 16), l_best_len | (l_best_pos << 9));
+                l_busy = false;
+            }
+            dq_tail += __popc(dmask);
+        }
+    };
+
+    // unaligned 64-bit little-endian read from the staged data
+    auto lds64 = [&](uint32_t byte_idx, uint32_t& lo, uint32_t& hi) {
+        const uint32_t a = byte_idx >> 2, sh = (byte_idx & 3u) * 8u;
+        const uint32_t w0 = dataw[a], w1 = dataw[a + 1], w2 = dataw[a + 2];
+        lo = __funnelshift_r(w0, w1, sh);
+        hi = __funnelshift_r(w1, w2, sh);
+    };
+    auto deep_iterate = [&]() {
+        const uint32_t idle = __ballot_sync(0xffffffffu, d_state == 0u);
+        const uint32_t avail = dq_tail - dq_head;
+        if (idle != 0u && avail != 0u) {
+            const uint32_t r = __popc(idle & lt_mask);
+            if (d_state == 0u && r < avail) {
+                const uint2 t = dq[(dq_head + r) & (kChainDQ - 1)];
+                d_j = t.x & 0xffffu; d_lb = t.x >> 16;
+                d_best_len = t.y & 0x1ffu; d_best_pos = t.y >> 9;
+                d_pos = cpos16[d_j & MD];
+                d_link = prev7[d_j & MD];
+                const uint32_t p = base + d_pos - kWindow;
+                d_maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                d_myfb = data[d_pos + d_best_len];
+                d_state = 1u;
+            }
+            const uint32_t taken = __popc(idle);
+            dq_head += taken < avail ? taken : avail;
+        }
+#pragma unroll
+        for (int u = 0; u < kChainDeepSteps; u++) {       // chain steps of the walking lanes
+            if (d_state == 1u) {
+                d_j -= d_link;
+                const uint32_t a = d_j & MD;
+                d_link = prev7[a];
+                const uint32_t cpos = cpos16[a];
+                if (d_j < d_lb || d_pos - cpos > kWindow) d_state = 3u;                      // range end / matching.rs:102-106
+                else if (data[cpos + d_best_len] == d_myfb) { d_state = 2u; d_cpos = cpos; } // matching.rs:141-143
+            }
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, d_state == 2u);
+        if (pmask != 0u && ((uint32_t)__popc(pmask) >= kChainParkMin || !__any_sync(0xffffffffu, d_state == 1u))) {
+            // comparison round: real length of every parked candidate (any bucket member is a legal
+            // candidate, so the comparison starts at byte 0 and needs no key check)
+            if (d_state == 2u) {
+                uint32_t l = 0;
+                while (l < d_maxl) {
+                    uint32_t a0, a1, b0, b1;
+                    lds64(d_pos + l, a0, a1);
+                    lds64(d_cpos + l, b0, b1);
+                    const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1;
+                    if (x0 | x1) { l += x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3); break; }
+                    l += 8;
+                }
+                l = l < d_maxl ? l : d_maxl;
+                d_state = 1u;
+                if (l > d_best_len) {                     // strictly longer: the nearest candidate wins ties
+                    d_best_len = l; d_best_pos = d_cpos;
+                    if (l == d_maxl) d_state = 3u;        // matching.rs:152-156
+                    else d_myfb = data[d_pos + l];
+                }
+            }
+        }
+        if (d_state == 3u) {
+            Mf[base + d_pos - kWindow] = finalize_match(d_best_len, d_pos - d_best_pos);
+            d_state = 0u;
+        }
+    };
+
+    // oldest local index a queued or running target can still look at
+    auto oldest_level = [&]() {
+        uint32_t mine = l_busy ? l_lb : 0xffffffffu;
+        if (lane == 0 && lq_tail != lq_head) { const uint32_t t = lq[lq_head & (kChainLQ - 1)] >> 16; mine = mine < t ? mine : t; }
+        return __reduce_min_sync(0xffffffffu, mine);
+    };
+    auto oldest_deep = [&]() {
+        uint32_t mine = d_state != 0u ? d_lb : 0xffffffffu;
+        if (lane == 0 && dq_tail != dq_head) { const uint32_t t = dq[dq_head & (kChainDQ - 1)].x >> 16; mine = mine < t ? mine : t; }
+        return __reduce_min_sync(0xffffffffu, mine);
+    };
+
+    // warps take chunks of the span's entries as they become free (chains are very uneven across buckets)
+    for (;;) {
+        uint32_t a = 0;
+        if (lane == 0) a = atomicAdd(next_chunk, kChainChunk);
+        a = __shfl_sync(0xffffffffu, a, 0);
+        if (a >= ne) break;
+        const uint32_t chunk = kChainChunk;
         const uint32_t ctx = a >= kChainCtx ? a - kChainCtx : 0u;
-        const uint32_t b = a + kChainChunk < ne ? a + kChainChunk : ne;
+        const uint32_t b = a + chunk < ne ? a + chunk : ne;
         for (uint32_t i = lane; i < kChainLevels * kChainSlots / 2; i += 32) reinterpret_cast<uint32_t*>(head)[i] = 0u;
-        for (uint32_t i = lane; i < kChainLevels * kChainRing / 4; i += 32) reinterpret_cast<uint32_t*>(prevd)[i] = 0u;
         __syncwarp();
-        uint32_t bs_carry = kChainRing;                  // local index of the first entry of the current bucket
+        uint32_t bs_carry = kChainRingD;                 // local index of the first entry of the current bucket
         uint2 nxt = make_uint2(0u, 0u);
         if (ctx + lane < b) nxt = __ldg(E + ctx + lane);
         for (uint32_t m0 = ctx; m0 < b; m0 += 32) {
@@ -618,9 +806,14 @@ k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint3
             const bool valid = m < b;
             const uint2 e = nxt;
             if (m + 32 < b) nxt = __ldg(E + m + 32);
-            const uint32_t li0 = m0 - ctx + kChainRing;  // local index of lane 0; never 0, so a zero head means "none"
+            const uint32_t li0 = m0 - ctx + kChainRingD; // local index of lane 0; never 0, so a zero head means "none"
             const uint32_t li = li0 + lane;
-            if (valid) ring[li & (kChainRing - 1)] = e;
+            // the slots about to be overwritten must be dead
+            while (oldest_level() < li0 + 32u - kChainRingS) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
+            while (oldest_deep() < li0 + 32u - kChainRingD) deep_iterate();
+            __syncwarp();
+            const uint32_t pos = span_entry_pos(e.y);
+            if (valid) { ring[li & MS] = e; cpos16[li & MD] = (uint16_t)pos; }
             const uint32_t fmask = __ballot_sync(0xffffffffu, valid && (e.y & kSpanFirstBit));
             const uint32_t fle = fmask & (lt_mask | (1u << lane));
             const uint32_t bs = fle ? li0 + (31u - (uint32_t)__clz((int)fle)) : bs_carry;
@@ -628,66 +821,32 @@ k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint3
             // ---- link the 32 entries into the chains of every level
 #pragma unroll
             for (uint32_t lv = 0; lv < kChainLevels; lv++) {
-                const uint32_t sg = span_sig(e.x, e.y, lv) >> 1;               // 7 bits
+                const uint32_t sg = span_sig(e.x, e.y, lv) >> 1;                 // 7 bits
                 const uint32_t grp = __match_any_sync(0xffffffffu, valid ? sg : (0x100u | lane));
                 const uint32_t below = grp & lt_mask;
-                uint32_t pi = below ? li0 + (31u - (uint32_t)__clz((int)below)) : (uint32_t)head[lv * kChainSlots + sg];
-                const uint32_t dl = li - pi;
+                const uint32_t pi = below ? li0 + (31u - (uint32_t)__clz((int)below)) : (uint32_t)head[lv * kChainSlots + sg];
+                const uint32_t dl = li - pi < 255u ? li - pi : 255u;
                 if (valid) {
-                    prevd[lv * kChainRing + (li & (kChainRing - 1))] = (uint8_t)(dl < kChainRing ? dl : 0u);
+                    if (lv == kTop) prev7[li & MD] = (uint8_t)dl; else prevs[lv * kChainRingS + (li & MS)] = (uint8_t)dl;
                     if ((grp >> lane) == 1u) head[lv * kChainSlots + sg] = (uint16_t)li;
                 }
             }
-            __syncwarp();
-            // ---- targets of this step: entries of the window being encoded, at or after `begin`
-            const uint32_t pos = span_entry_pos(e.y);
-            const uint32_t p = base + pos - kWindow;
-            if (valid && m >= a && pos >= kWindow && p >= begin) {
-                const uint32_t maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+            // ---- queue the targets of this step: entries of the window being encoded, at or after `begin`
+            const bool is_target = valid && m >= a && pos >= kWindow && base + pos - kWindow >= begin;
+            const uint32_t tmask = __ballot_sync(0xffffffffu, is_target);
+            if (is_target) {
                 const uint32_t lb = bs > li - checks ? bs : li - checks;
-                uint32_t best_len = 1, best_pos = pos;
-                uint32_t lvl = 0, mask = 0;
-                bool deep = false;
-                uint32_t j = li;
-                for (;;) {
-                    const uint32_t dl = prevd[lvl * kChainRing + (j & (kChainRing - 1))];
-                    j -= dl;
-                    if (dl == 0 || j < lb) break;
-                    const uint2 ce = ring[j & (kChainRing - 1)];
-                    const uint32_t xlo = ce.x ^ e.x;
-                    if (((xlo & mask) | ((ce.y ^ e.y) & kSpanTagMask)) != 0u) continue;     // slot collision
-                    const uint32_t cpos = span_entry_pos(ce.y);
-                    if (pos - cpos > kWindow) break;                                          // matching.rs:102-106
-                    if (!deep) {
-                        const uint32_t l = span_entry_lcp(xlo);
-                        if (l >= maxl) { best_len = maxl; best_pos = cpos; break; }
-                        if (l < kSpanEntryBytes) {
-                            // nearest candidate with >= lvl + 3 bytes has exactly l: now look for l + 1
-                            best_len = l; best_pos = cpos;
-                            lvl = l - 2u; mask = span_level_mask(lvl);
-                            j = li;
-                            continue;
-                        }
-                        deep = true; lvl = kChainLevels - 1; mask = 0xffffffffu;
-                    }
-                    // a candidate sharing 7+ bytes: reference's quick reject, then the real length
-                    if (best_len >= kSpanEntryBytes && data[cpos + best_len] != data[pos + best_len]) continue;
-                    uint32_t l = kSpanEntryBytes;
-                    while (l < maxl) {
-                        const uint32_t x = lds32(dataw, pos + l) ^ lds32(dataw, cpos + l);
-                        if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                        l += 4;
-                    }
-                    l = l < maxl ? l : maxl;
-                    if (l > best_len) {
-                        best_len = l; best_pos = cpos;
-                        if (l == maxl) break;                                                 // matching.rs:152-156
-                    }
-                }
-                Mf[p] = finalize_match(best_len, pos - best_pos);
+                lq[(lq_tail + __popc(tmask & lt_mask)) & (kChainLQ - 1)] = li | (lb << 16);
             }
+            lq_tail += __popc(tmask);
             __syncwarp();
+            // lanes still walking keep their state across steps
+            while (lq_tail != lq_head) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
+            while (dq_tail != dq_head) deep_iterate();
         }
+        // the next chunk restarts the local indices: finish everything
+        while (__any_sync(0xffffffffu, l_busy)) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
+        while (dq_tail != dq_head || __any_sync(0xffffffffu, d_state != 0u)) deep_iterate();
     }
 }
 
