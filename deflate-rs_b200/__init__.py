@@ -4,9 +4,11 @@ Names, argument meaning and error behaviour follow the reference crate (image-rs
 
     deflate_bytes / deflate_bytes_conf            src/lib.rs:163 / :137
     deflate_bytes_zlib / deflate_bytes_zlib_conf  src/lib.rs:216 / :182
+    deflate_bytes_gzip / deflate_bytes_gzip_conf  src/lib.rs:284 / :242 (GzBuilder: gzip-header 1.0)
     Compression, CompressionOptions, MatchingType, SpecialOptions
                                                   src/compression_options.rs:31-196, src/lz77.rs:26-37
-    write.DeflateEncoder / write.ZlibEncoder      src/writer.rs:89-152 / :183-290
+    write.DeflateEncoder / write.ZlibEncoder / write.GzEncoder
+                                                  src/writer.rs:89-152 / :183-290 / :331-467
 
 Everything below this module is the C ABI of include/deflate_b200.h; all compression arithmetic runs
 in sm_100a CUDA kernels (deflate-rs_b200/csrc).  There is no CPU path: importing works anywhere, but
@@ -21,7 +23,8 @@ from ._native import DeflateB200Error, RAW, ZLIB, GZIP  # noqa: F401
 
 __all__ = [
     "Compression", "CompressionOptions", "MatchingType", "SpecialOptions", "deflate_bytes", "deflate_bytes_conf",
-    "deflate_bytes_zlib", "deflate_bytes_zlib_conf", "write", "compress_device", "DeflateB200Error",
+    "deflate_bytes_zlib", "deflate_bytes_zlib_conf", "deflate_bytes_gzip", "deflate_bytes_gzip_conf", "GzBuilder",
+    "write", "compress_device", "DeflateB200Error",
 ]
 
 
@@ -90,14 +93,61 @@ class CompressionOptions:
         return _native.dfl_options(self.max_hash_checks, self.lazy_if_less_than, int(self.matching_type), int(self.special))
 
 
-def _oneshot(data, options, wrap):
+class GzBuilder:
+    """Host-side stand-in for `gzip_header::GzBuilder` (crate gzip-header 1.0, the type the reference's
+    gzip entry points take: src/lib.rs:242, src/writer.rs:346): builds the RFC 1952 member header.
+    Only the header *bytes* cross the C ABI.  Defaults: no optional fields, MTIME 0, XFL 0, OS 255."""
+
+    def __init__(self):
+        self._extra = None
+        self._filename = None
+        self._comment = None
+        self._mtime = 0
+        self._os = 255
+
+    def mtime(self, mtime):
+        self._mtime = int(mtime) & 0xFFFFFFFF
+        return self
+
+    def os(self, os_code):
+        self._os = int(os_code) & 0xFF
+        return self
+
+    def extra(self, extra):
+        self._extra = bytes(extra)
+        return self
+
+    def filename(self, filename):
+        self._filename = bytes(filename)
+        return self
+
+    def comment(self, comment):
+        self._comment = bytes(comment)
+        return self
+
+    def into_header(self) -> bytes:
+        flg = (4 if self._extra is not None else 0) | (8 if self._filename is not None else 0) | \
+              (16 if self._comment is not None else 0)
+        h = bytearray([0x1F, 0x8B, 8, flg]) + self._mtime.to_bytes(4, "little") + bytes([0, self._os])
+        if self._extra is not None:
+            h += len(self._extra).to_bytes(2, "little") + self._extra
+        if self._filename is not None:
+            h += self._filename + b"\0"
+        if self._comment is not None:
+            h += self._comment + b"\0"
+        return bytes(h)
+
+
+def _oneshot(data, options, wrap, gz_hdr=None):
     data = bytes(data)
     opts = CompressionOptions.from_(options)._c()
     L = _native.lib()
-    cap = L.dfl_bound(len(data), wrap)
+    hdr = bytes(gz_hdr) if gz_hdr else None
+    cap = L.dfl_bound(len(data), wrap) + (len(hdr) if hdr else 0)
     out = ctypes.create_string_buffer(cap)
     n = ctypes.c_size_t()
-    _native.check(L.dfl_compress(data, len(data), ctypes.byref(opts), wrap, None, 0, out, cap, ctypes.byref(n)), "dfl_compress")
+    _native.check(L.dfl_compress(data, len(data), ctypes.byref(opts), wrap, hdr, len(hdr) if hdr else 0, out, cap,
+                                 ctypes.byref(n)), "dfl_compress")
     return out.raw[: n.value]
 
 
@@ -119,6 +169,22 @@ def deflate_bytes_zlib_conf(input, options):
 def deflate_bytes_zlib(input):
     """src/lib.rs:216"""
     return _oneshot(input, Compression.Default, ZLIB)
+
+
+def deflate_bytes_gzip_conf(input, options, gzip_header=None):
+    """src/lib.rs:242 -- gzip member: header from `gzip_header` (a GzBuilder), stream, CRC-32 and ISIZE."""
+    hdr = (gzip_header or GzBuilder()).into_header()
+    return _oneshot(input, options, GZIP, hdr)
+
+
+def deflate_bytes_gzip(input):
+    """src/lib.rs:284"""
+    return deflate_bytes_gzip_conf(input, Compression.Default, GzBuilder())
+
+
+def set_match_path(path):
+    """Tuning hook (dfl_set_match_path): "walk" or "chains".  Both produce identical bytes."""
+    return _native.lib().dfl_set_match_path({"walk": 0, "chains": 1}[path])
 
 
 def compress_device(src, options=Compression.Default, wrap=RAW, out=None, stream=None):
@@ -147,10 +213,10 @@ class _Encoder:
     """Shared body of write.DeflateEncoder / write.ZlibEncoder (src/writer.rs)."""
     _wrap = RAW
 
-    def __init__(self, writer, options):
+    def __init__(self, writer, options, _gz_hdr=None):
         self._opts = CompressionOptions.from_(options)
         c = self._opts._c()
-        self._h = _native.lib().dfl_encoder_new(ctypes.byref(c), self._wrap, None, 0)
+        self._h = _native.lib().dfl_encoder_new(ctypes.byref(c), self._wrap, _gz_hdr, len(_gz_hdr) if _gz_hdr else 0)
         if not self._h:
             raise DeflateB200Error(-1, "dfl_encoder_new")
         self._inner = writer
@@ -186,10 +252,10 @@ class _Encoder:
         self._close()
         return w
 
-    def reset(self, writer):
+    def reset(self, writer, _gz_hdr=None):
         """reset(&mut self, W) -> io::Result<W> (src/writer.rs:112-115, 218-223)."""
         self._require_open()
-        _native.check(_native.lib().dfl_encoder_reset(self._h, None, 0), "dfl_encoder_reset")
+        _native.check(_native.lib().dfl_encoder_reset(self._h, _gz_hdr, len(_gz_hdr) if _gz_hdr else 0), "dfl_encoder_reset")
         self._drain()
         old, self._inner = self._inner, writer
         return old
@@ -251,10 +317,33 @@ class ZlibEncoder(_Encoder):
         return int(_native.lib().dfl_encoder_checksum(self._h))
 
 
+class GzEncoder(_Encoder):
+    """write::GzEncoder<W> (src/writer.rs:331-467, feature `gzip`)."""
+    _wrap = GZIP
+
+    def __init__(self, writer, options, _gz_hdr=None):
+        super().__init__(writer, options, _gz_hdr)
+
+    @classmethod
+    def from_builder(cls, builder, writer, options):
+        """src/writer.rs:346-357"""
+        return cls(writer, options, builder.into_header())
+
+    def reset_with_builder(self, writer, builder):
+        """src/writer.rs:403-406"""
+        return self.reset(writer, builder.into_header())
+
+    def checksum(self) -> int:
+        """CRC-32 of the data consumed so far (src/writer.rs:429)."""
+        self._require_open()
+        return int(_native.lib().dfl_encoder_checksum(self._h))
+
+
 class _WriteNamespace:
     """`deflate::write` (src/lib.rs:104-108)."""
     DeflateEncoder = DeflateEncoder
     ZlibEncoder = ZlibEncoder
+    GzEncoder = GzEncoder
 
 
 write = _WriteNamespace

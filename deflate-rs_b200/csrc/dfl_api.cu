@@ -213,9 +213,14 @@ uint32_t wrap_header_bytes(int wrap, size_t gz_hdr_len) {
 // Runs the kernel pipeline for one piece of a stream.  d_in holds `n` bytes of which the first
 // `begin` are dictionary only.  On success *out_bytes is the number of bytes produced in d_out
 // (container header included when hdr_bytes > 0, trailer included when final && wrap == zlib).
+// RFC 1952 member header the reference gets from gzip-header 1.0 `GzBuilder::new().into_header()`
+// (lib.rs:251, writer.rs:341-357): no flags, MTIME 0, XFL 0, OS 255 (unknown).
+const uint8_t kGzipDefaultHeader[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
+
 int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, size_t begin, const dfl_options* opt, int wrap,
                  uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out, size_t out_cap, size_t* out_bytes,
-                 const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0) {
+                 const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0,
+                 const uint8_t* gz_hdr = nullptr) {
     if (n >= 0xfffffff0ull) return DFL_E_UNSUPPORTED;   // 32-bit positions; see DESIGN.md "limits"
     if (opt->special != 0) return DFL_E_UNSUPPORTED;    // compression_options.rs:52-59: placeholders
     EncodeJob j;
@@ -228,6 +233,7 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     j.d_out = d_out;
     j.out_cap = out_cap & ~(size_t)15;
     j.hdr_bytes = hdr_bytes;
+    j.isize = (uint32_t)((n - begin) & 0xffffffffull);
     j.d_tokens_override = d_tokens_override;
     j.n_tokens_override = n_tokens_override;
     j.stop_after_tokens = stop_after_tokens;
@@ -245,6 +251,10 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     if (wrap == DFL_ZLIB && final_block && !stop_after_tokens) {
         CK(launch_adler32(d_in + begin, n - begin, b, st));
         tm.mark("adler32");
+    }
+    if (wrap == DFL_GZIP && final_block && !stop_after_tokens) {
+        CK(launch_crc32(d_in + begin, n - begin, b, st));
+        tm.mark("crc32");
     }
     if (need_match) {
         CK(launch_window_sort(j, b, st));
@@ -268,6 +278,8 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
         CK(launch_pack(j, b, st));
         tm.mark("pack");
         CK(launch_finalize(j, b, wrap, st));
+        if (wrap == DFL_GZIP && hdr_bytes > 0 && hdr_bytes + 16 <= j.out_cap)   // the header bytes are the caller's (or the default)
+            CK(cudaMemcpyAsync(d_out, gz_hdr ? gz_hdr : kGzipDefaultHeader, hdr_bytes, cudaMemcpyHostToDevice, st));
         tm.mark("finalize");
     }
     CK(cudaMemcpyAsync(c.h_meta, b.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -333,6 +345,11 @@ extern "C" size_t dfl_bound(size_t n, int wrap) {
     return n + 5 * (n / 32767 + 1) + 6 * (n / 31744 + 2) + 64 + (wrap == DFL_GZIP ? 320 : 0);
 }
 
+extern "C" int dfl_set_match_path(int path) {
+    int old = g_match_path;
+    g_match_path = path ? 1 : 0;
+    return old;
+}
 extern "C" int dfl_set_profiling(int enabled) {
     int old = t_profiling;
     t_profiling = enabled;
@@ -355,35 +372,50 @@ extern "C" int dfl_last_counters(uint64_t* out, int cap) {
 extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
                                    size_t gz_hdr_len, void* d_out, size_t out_cap, size_t* out_len, void* stream) {
     if (!opt || !d_out || !out_len || (!d_in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
-    if (wrap == DFL_GZIP) return DFL_E_UNSUPPORTED;   // CRC-32 kernel: SURVEY 8(f) rank 2
-    (void)gz_hdr; (void)gz_hdr_len;
+    if (wrap != DFL_GZIP || !gz_hdr || gz_hdr_len == 0) { gz_hdr = nullptr; gz_hdr_len = 0; }
+    if (gz_hdr_len > 0xffffu) return DFL_E_ARG;
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     return run_pipeline(c, st, reinterpret_cast<const uint8_t*>(d_in), n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1,
-                        0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+                        0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len, nullptr, 0, 0, gz_hdr);
 }
 
 extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
                             size_t gz_hdr_len, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!opt || !out || !out_len || (!in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
-    if (wrap == DFL_GZIP) return DFL_E_UNSUPPORTED;
+    if (wrap != DFL_GZIP || !gz_hdr || gz_hdr_len == 0) { gz_hdr = nullptr; gz_hdr_len = 0; }
+    if (gz_hdr_len > 0xffffu) return DFL_E_ARG;
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
-    size_t bound = dfl_bound(n, wrap);
+    size_t bound = dfl_bound(n, wrap) + gz_hdr_len;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound + 64))) return rc;
     if (n) CK(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, c.stream));
     size_t produced = 0;
     rc = run_pipeline(c, c.stream, c.d_in, n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1, 0, c.d_out, c.d_out_cap,
-                      &produced);
+                      &produced, nullptr, 0, 0, gz_hdr);
     if (rc) return rc;
     *out_len = produced;
     if (produced > out_cap) return DFL_E_OVERFLOW;
     CK(cudaMemcpyAsync(out, c.d_out, produced, cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
+    return DFL_OK;
+}
+
+extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void* stream) {
+    if (!crc || (!d_in && n)) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.ensure(n ? n : 1, false, false))) return rc;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
+    CK(launch_crc32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
+    CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *crc = c.h_meta->crc;
     return DFL_OK;
 }
 
@@ -460,15 +492,17 @@ struct dfl_encoder {
     bool header_written = false;
     bool finished = false;
     uint32_t adler = 1;          // Adler-32 of everything encoded so far (device-computed per piece)
-    size_t adler_upto = 0;       // data[pending_from..adler_upto) is already folded into `adler`
+    uint32_t crc = 0;            // CRC-32 likewise (gzip)
+    size_t adler_upto = 0;       // data[pending_from..adler_upto) is already folded into the checksum
     uint64_t total_in = 0;
+    std::vector<uint8_t> gz_hdr; // gzip member header to emit (GzBuilder::into_header(), writer.rs:341-357)
 };
 
 namespace {
 
-// Adler-32 of data[from..to) on the device, folded into e->adler.
+// Adler-32 / CRC-32 of data[from..to) on the device, folded into e->adler / e->crc.
 int encoder_fold_checksum(dfl_encoder* e, size_t to) {
-    if (e->wrap != DFL_ZLIB) return DFL_OK;
+    if (e->wrap == DFL_RAW) return DFL_OK;
     size_t from = e->adler_upto < e->pending_from ? e->pending_from : e->adler_upto;
     if (to <= from) return DFL_OK;
     Context& c = e->ctx;
@@ -478,10 +512,13 @@ int encoder_fold_checksum(dfl_encoder* e, size_t to) {
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, e->data.size() + 64))) return rc;
     if ((rc = c.ensure(len, false, false))) return rc;
     CK(cudaMemcpyAsync(c.d_in, e->data.data() + from, len, cudaMemcpyHostToDevice, c.stream));
-    CK(launch_adler32(c.d_in, len, c.buf, c.stream));
+    if (e->wrap == DFL_ZLIB) CK(launch_adler32(c.d_in, len, c.buf, c.stream));
+    else CK(launch_crc32(c.d_in, len, c.buf, c.stream));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
-    e->adler = adler32_combine(e->adler, c.h_meta->adler, len);   // arithmetic on two device results
+    // arithmetic on two device results
+    if (e->wrap == DFL_ZLIB) e->adler = adler32_combine(e->adler, c.h_meta->adler, len);
+    else e->crc = crc32_combine(e->crc, c.h_meta->crc, len);
     e->adler_upto = to;
     return DFL_OK;
 }
@@ -494,16 +531,17 @@ int encoder_emit(dfl_encoder* e, int mode) {
     const size_t begin = e->pending_from;
     if ((rc = encoder_fold_checksum(e, n))) return rc;
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
-    size_t bound = dfl_bound(n - begin, e->wrap) + 64;
+    size_t bound = dfl_bound(n - begin, e->wrap) + e->gz_hdr.size() + 64;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
     if (n) CK(cudaMemcpyAsync(c.d_in, e->data.data(), n, cudaMemcpyHostToDevice, c.stream));
     uint32_t hdr = 0;
-    if (!e->header_written) hdr = wrap_header_bytes(e->wrap, 0);
+    if (!e->header_written) hdr = wrap_header_bytes(e->wrap, e->gz_hdr.size());
     size_t produced = 0;
     // The trailer is appended here from the running checksum, so the kernels see wrap == RAW
     // unless the header still has to be written.
     rc = run_pipeline(c, c.stream, c.d_in, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr, mode == DFL_FLUSH_FINISH ? 1 : 0,
-                      mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, &produced);
+                      mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, &produced, nullptr, 0, 0,
+                      e->gz_hdr.empty() ? nullptr : e->gz_hdr.data());
     if (rc) return rc;
     size_t stream_part = (size_t)c.h_meta->stream_bytes + hdr;
     size_t old = e->out.size();
@@ -516,6 +554,10 @@ int encoder_emit(dfl_encoder* e, int mode) {
             uint32_t a = e->adler;
             uint8_t t[4] = {(uint8_t)(a >> 24), (uint8_t)(a >> 16), (uint8_t)(a >> 8), (uint8_t)a};
             e->out.insert(e->out.end(), t, t + 4);
+        } else if (e->wrap == DFL_GZIP) {   // writer.rs:408-426: CRC-32 and the input size, little endian
+            uint32_t v[2] = {e->crc, (uint32_t)(e->total_in & 0xffffffffull)};
+            for (uint32_t x : v)
+                for (int k = 0; k < 4; k++) e->out.push_back((uint8_t)(x >> (8 * k)));
         }
         e->finished = true;
     }
@@ -531,12 +573,12 @@ int encoder_emit(dfl_encoder* e, int mode) {
 }  // namespace
 
 extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const uint8_t* gz_hdr, size_t gz_hdr_len) {
-    (void)gz_hdr; (void)gz_hdr_len;
-    if (!opt || !valid_wrap(wrap) || wrap == DFL_GZIP) return nullptr;
+    if (!opt || !valid_wrap(wrap) || gz_hdr_len > 0xffffu) return nullptr;
     dfl_encoder* e = new (std::nothrow) dfl_encoder();
     if (!e) return nullptr;
     e->opt = *opt;
     e->wrap = wrap;
+    if (wrap == DFL_GZIP && gz_hdr && gz_hdr_len) e->gz_hdr.assign(gz_hdr, gz_hdr + gz_hdr_len);
     return e;
 }
 
@@ -577,14 +619,13 @@ extern "C" void dfl_encoder_advance_output(dfl_encoder* e, size_t n) {
 }
 
 extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
-    if (!e || e->wrap != DFL_ZLIB) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
+    if (!e || e->wrap == DFL_RAW) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
     if (encoder_fold_checksum(e, e->data.size()) != DFL_OK) return 0;
-    return e->adler;
+    return e->wrap == DFL_ZLIB ? e->adler : e->crc;
 }
 
 extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t gz_hdr_len) {
-    (void)gz_hdr; (void)gz_hdr_len;
-    if (!e) return DFL_E_ARG;
+    if (!e || gz_hdr_len > 0xffffu) return DFL_E_ARG;
     if (!e->finished) {
         int rc = encoder_emit(e, DFL_FLUSH_FINISH);   // output_all() (writer.rs:112-115,218-223)
         if (rc) return rc;
@@ -594,8 +635,12 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
     e->header_written = false;
     e->finished = false;
     e->adler = 1;
+    e->crc = 0;
     e->adler_upto = 0;
     e->total_in = 0;
+    // reset() installs the default header, reset_with_builder() the caller's (writer.rs:394-406)
+    e->gz_hdr.clear();
+    if (e->wrap == DFL_GZIP && gz_hdr && gz_hdr_len) e->gz_hdr.assign(gz_hdr, gz_hdr + gz_hdr_len);
     return DFL_OK;
 }
 

@@ -581,4 +581,40 @@ DFL_HD uint32_t adler32_combine(uint32_t ad1, uint32_t ad2, uint64_t len2) {
     return (uint32_t)((b % kAdlerMod) << 16) | a;
 }
 
+// ---------------------------------------------------------------- CRC-32 (RFC 1952 section 8)
+// The reference takes CRC-32 from the `gzip-header` crate (lib.rs:257-258, writer.rs:411-412); it is
+// the standard reflected CRC with polynomial 0xEDB88320.  Pieces are checksummed independently and
+// combined: crc(A || B) = crc(A) * x^(8 len(B)) mod P  xor  crc(B) (carry-less arithmetic).
+constexpr uint32_t kCrcPoly = 0xedb88320u;
+DFL_HD uint32_t crc32_multmodp(uint32_t a, uint32_t b) {
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1u)) == 0u) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ kCrcPoly : b >> 1;
+    }
+    return p;
+}
+// x^(2^k) mod P for k = 0..31 (the exponent sequence repeats with period 32 beyond that)
+DFL_HD uint32_t crc32_x2n(uint32_t k) {
+    const uint32_t t[32] = {0x40000000u, 0x20000000u, 0x08000000u, 0x00800000u, 0x00008000u, 0xedb88320u, 0xb1e6b092u,
+                            0xa06a2517u, 0xed627daeu, 0x88d14467u, 0xd7bbfe6au, 0xec447f11u, 0x8e7ea170u, 0x6427800eu,
+                            0x4d47bae0u, 0x09fe548fu, 0x83852d0fu, 0x30362f1au, 0x7b5a9cc3u, 0x31fec169u, 0x9fec022au,
+                            0x6c8dedc4u, 0x15d6874du, 0x5fde7a4eu, 0xbad90e37u, 0x2e4e5eefu, 0x4eaba214u, 0xa8a472c0u,
+                            0x429a969eu, 0x148d302au, 0xc40ba6d0u, 0xc4e22c3cu};
+    return t[k & 31u];
+}
+// combine(crc of A, crc of B, len(B)) -> crc of A || B
+DFL_HD uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+    if (len2 == 0) return crc1;
+    uint32_t p = 1u << 31;          // x^0
+    uint32_t k = 3;                 // bytes -> bits
+    for (uint64_t nn = len2; nn; nn >>= 1, k++)
+        if (nn & 1u) p = crc32_multmodp(crc32_x2n(k), p);
+    return crc32_multmodp(p, crc1) ^ crc2;
+}
+
 }  // namespace dfl

@@ -22,6 +22,7 @@ struct DevMeta {
     unsigned long long out_bytes;     // container size: header + stream + trailer
     uint32_t n_blocks;
     uint32_t adler;
+    uint32_t crc;                     // CRC-32 of the payload (gzip)
     uint32_t n_bad;                   // segments whose hand-off check failed in the latest verify
     uint32_t n_repaired_par;
     uint32_t n_repaired_seq;
@@ -101,6 +102,7 @@ struct EncodeJob {
     uint8_t* d_out;          // device output, zero-filled by the pipeline
     size_t out_cap;
     uint32_t hdr_bytes;      // container header already accounted for at the start of d_out
+    uint32_t isize;          // gzip ISIZE: total input length modulo 2^32
     const uint32_t* d_tokens_override;   // test hook: skip the LZ77 stage, use these tokens
     unsigned long long n_tokens_override;
     int stop_after_tokens;   // test hook: run only the LZ77 stage
@@ -118,6 +120,7 @@ cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_block_scan(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_pack(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_adler32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st);
+cudaError_t launch_crc32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st);
 cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st);
 uint32_t max_blocks_for(uint32_t n_payload);
 extern int g_launch_count;   // kernels launched since the last reset (host-side counter)

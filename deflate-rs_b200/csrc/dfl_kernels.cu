@@ -428,8 +428,11 @@ __device__ __forceinline__ void walk_segment(Walk& wk, const SmemBytes& data, ui
 __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 
+#ifndef DFL_MATCH_CTAS
+#define DFL_MATCH_CTAS 3
+#endif
 template <bool NEEDQ>
-__global__ void __launch_bounds__(kMatchThreads, 2)
+__global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
 k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
         const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
         uint32_t* __restrict__ Mq) {
@@ -1388,12 +1391,94 @@ __global__ void __launch_bounds__(1024) k_adler32_combine(const unsigned long lo
 }
 
 // =====================================================================================
+// CRC-32 (gzip trailer; lib.rs:257-265, writer.rs:408-426): per 64 KiB chunk every thread checksums
+// 256 bytes with a byte table, the 256 results are combined in a tree (the right operand of a full
+// subtree has a power-of-two length, so its shift operator is one table entry), then one CTA
+// combines the chunks in order.
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_crc32_chunks(const uint8_t* __restrict__ in, unsigned long long n,
+                                                      unsigned long long* __restrict__ part) {
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t sc[256];
+    __shared__ uint32_t sl[256];
+    {
+        uint32_t c = threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        tab[threadIdx.x] = c;
+    }
+    __syncthreads();
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * kAdlerChunk;
+    const uint32_t L = (uint32_t)((n - c0) < kAdlerChunk ? (n - c0) : kAdlerChunk);
+    const uint32_t lo = threadIdx.x * 256u < L ? threadIdx.x * 256u : L;
+    const uint32_t hi = lo + 256u < L ? lo + 256u : L;
+    const uint8_t* p = in + c0;
+    uint32_t c = 0xffffffffu;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && hi - lo == 256u;
+    if (aligned) {
+#pragma unroll 4
+        for (uint32_t i = lo; i < hi; i += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) c = tab[(c ^ (wv[k] >> (8 * q))) & 0xffu] ^ (c >> 8);
+            }
+        }
+    } else {
+        for (uint32_t i = lo; i < hi; i++) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+    }
+    sc[threadIdx.x] = c ^ 0xffffffffu;
+    sl[threadIdx.x] = hi - lo;
+    __syncthreads();
+    for (uint32_t s = 1; s < 256; s <<= 1) {
+        const uint32_t i = threadIdx.x;
+        if ((i & (2 * s - 1)) == 0) {
+            sc[i] = crc32_combine(sc[i], sc[i + s], sl[i + s]);
+            sl[i] += sl[i + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        part[2ull * blockIdx.x] = sc[0];
+        part[2ull * blockIdx.x + 1] = L;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_crc32_combine(const unsigned long long* __restrict__ part, uint32_t n_chunks,
+                                                        DevMeta* meta) {
+    __shared__ uint32_t cr[1024];
+    __shared__ unsigned long long ln[1024];
+    uint32_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
+    uint32_t lo = threadIdx.x * per, hi = lo + per < n_chunks ? lo + per : n_chunks;
+    uint32_t c = 0;
+    unsigned long long len = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        c = crc32_combine(c, (uint32_t)part[2ull * i], part[2ull * i + 1]);
+        len += part[2ull * i + 1];
+    }
+    cr[threadIdx.x] = c; ln[threadIdx.x] = len;
+    __syncthreads();
+    for (uint32_t s = 1; s < blockDim.x; s <<= 1) {
+        uint32_t i = threadIdx.x;
+        if ((i & (2 * s - 1)) == 0 && i + s < blockDim.x) {
+            cr[i] = crc32_combine(cr[i], cr[i + s], ln[i + s]);
+            ln[i] += ln[i + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) meta->crc = cr[0];
+}
+
+// =====================================================================================
 // k_finalize: sync marker bytes, container header and trailer (zlib.rs:59-62, lib.rs:192-196)
 // =====================================================================================
 __global__ void k_finalize(DevMeta* meta, uint8_t* out, unsigned long long out_cap, uint32_t hdr_bytes, int wrap,
-                           int sync_marker, int write_trailer) {
+                           int sync_marker, int write_trailer, uint32_t isize) {
     unsigned long long end = hdr_bytes + meta->stream_bytes;
-    if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = end + (wrap == 1 && write_trailer ? 4ull : 0ull); return; }
+    const unsigned long long trailer = write_trailer ? (wrap == 1 ? 4ull : (wrap == 2 ? 8ull : 0ull)) : 0ull;
+    if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = end + trailer; return; }
     if (sync_marker && end >= 4 && end <= out_cap) {
         out[end - 2] = 0xff;
         out[end - 1] = 0xff;
@@ -1405,6 +1490,14 @@ __global__ void k_finalize(DevMeta* meta, uint8_t* out, unsigned long long out_c
             out[end] = (uint8_t)(a >> 24); out[end + 1] = (uint8_t)(a >> 16); out[end + 2] = (uint8_t)(a >> 8); out[end + 3] = (uint8_t)a;
         }
         if (write_trailer) end += 4;
+    }
+    if (wrap == 2 && write_trailer) {   // gzip: CRC-32 then ISIZE, little endian (lib.rs:260-265, writer.rs:408-426)
+        if (end + 8 <= out_cap) {
+            const uint32_t c = meta->crc;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { out[end + k] = (uint8_t)(c >> (8 * k)); out[end + 4 + k] = (uint8_t)(isize >> (8 * k)); }
+        }
+        end += 8;
     }
     meta->out_bytes = end;
 }
@@ -1561,9 +1654,20 @@ cudaError_t launch_adler32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream
     return cudaSuccess;
 }
 
+cudaError_t launch_crc32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st) {
+    uint32_t n_chunks = (uint32_t)((n + kAdlerChunk - 1) / kAdlerChunk);
+    if (n_chunks > 0) {
+        k_crc32_chunks<<<n_chunks, 256, 0, st>>>(d_in, (unsigned long long)n, b.adler_part);   // zlib and gzip never coincide
+        DFL_LAUNCH_CHECK();
+    }
+    k_crc32_combine<<<1, 1024, 0, st>>>(b.adler_part, n_chunks, b.meta);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st) {
     k_finalize<<<1, 1, 0, st>>>(b.meta, j.d_out, (unsigned long long)j.out_cap, j.hdr_bytes, wrap, j.sync_marker,
-                                j.final_block);
+                                j.final_block, j.isize);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }

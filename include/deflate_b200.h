@@ -136,6 +136,9 @@ void dfl_encoder_free(dfl_encoder *e);
 /* ---- building blocks exposed for tests and for callers that keep data on the device --------
  * Adler-32 (checksum.rs:33-57) of a device buffer, computed on the device. */
 int dfl_adler32_device(const void *d_in, size_t n, uint32_t *adler, void *stream);
+/* CRC-32 (gzip-header 1.0 `Crc`, the reference's gzip trailer: lib.rs:257-265, writer.rs:408-426)
+ * of a device buffer, computed on the device. */
+int dfl_crc32_device(const void *d_in, size_t n, uint32_t *crc, void *stream);
 /* Runs only the entropy stage (block cut at 31744 tokens, code construction, block-type choice,
  * bit packing: huffman_lengths.rs:167-369, encoder_state.rs:58-105, compress.rs:187-247) on a
  * caller-supplied token stream (host memory; token = literal byte, or len | dist << 9), so the
@@ -146,6 +149,13 @@ int dfl_encode_tokens(const uint8_t *in, size_t n, const uint32_t *tokens, size_
 /* Runs only the LZ77 stage and returns the token stream (host memory, same encoding). */
 int dfl_lz77_tokens(const uint8_t *in, size_t n, const dfl_options *opt, uint32_t *tokens,
                     size_t tokens_cap, size_t *n_tokens);
+
+/* Tuning hook, process wide: which match kernels serve option sets that both paths can handle
+ * (max_hash_checks 1..128 without quarter-budget searches).  0 = candidate walk (k_match, the
+ * default), 1 = span entries + multi-level chains (k_span_scatter + k_match_chains).  The two
+ * produce identical bytes; the switch exists to time them against each other.  Returns the
+ * previous value.  Environment override at load time: DFL_MATCH_PATH=walk|chains. */
+int dfl_set_match_path(int path);
 
 #ifdef __cplusplus
 }

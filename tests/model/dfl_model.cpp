@@ -506,6 +506,8 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 }
 
 void dflm_free(void* p) { free(p); }
+uint32_t dflm_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return crc32_combine(c1, c2, len2); }
+uint32_t dflm_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
 void dflm_set_match_impl(int impl) { g_match_impl = impl; }
 void dflm_chain_stats(uint64_t* o /*[8]*/, int reset) {
     for (int i = 0; i < 8; i++) { o[i] = g_chain_stats[i]; if (reset) g_chain_stats[i] = 0; }

@@ -25,6 +25,10 @@ def lib():
                                   ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(ctypes.c_size_t)]
         L.dflm_symbols.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
         L.dflm_free.argtypes = [ctypes.c_void_p]
+        L.dflm_crc32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+        L.dflm_crc32_combine.restype = ctypes.c_uint32
+        L.dflm_adler32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+        L.dflm_adler32_combine.restype = ctypes.c_uint32
         L.dflm_set_match_impl.argtypes = [ctypes.c_int]
         L.dflm_chain_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
         _lib = L

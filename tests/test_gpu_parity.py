@@ -235,3 +235,117 @@ def test_writer_small_sink_and_checksum(dfl, pg11):
     assert enc.checksum() == zlib.adler32(pg11[:9000])
     enc.finish()
     assert zlib.decompress(bytes(w.data)) == pg11[:9000]
+
+
+# ---------------------------------------------------------------- gzip (lib.rs:241-286, writer.rs:331-467)
+def test_crc32_on_device(dfl, pg11):
+    import torch
+    L = dfl._native.lib()
+    rng = np.random.default_rng(7)
+    cases = [b"", b"a", pg11, bytes([255]) * 300000, rng.integers(0, 256, (1 << 20) + 12345, dtype=np.uint8).tobytes(),
+             rng.integers(0, 256, 65536, dtype=np.uint8).tobytes(), rng.integers(0, 256, 65537, dtype=np.uint8).tobytes()]
+    for data in cases:
+        t = torch.frombuffer(bytearray(data) if data else bytearray(1), dtype=torch.uint8).cuda()
+        c = ctypes.c_uint32()
+        assert L.dfl_crc32_device(ctypes.c_void_p(t.data_ptr()), len(data), ctypes.byref(c), None) == 0
+        assert c.value == zlib.crc32(data), len(data)
+        assert c.value == o.lib().dfo_crc32(0, data, len(data))
+    # unaligned device pointer
+    data = cases[4]
+    t = torch.frombuffer(bytearray(b"xyz" + data), dtype=torch.uint8).cuda()
+    c = ctypes.c_uint32()
+    assert L.dfl_crc32_device(ctypes.c_void_p(t.data_ptr() + 3), len(data), ctypes.byref(c), None) == 0
+    assert c.value == zlib.crc32(data)
+
+
+def test_gzip_oneshot_equals_oracle(dfl, pg11):
+    """lib.rs:393-406: gzip one-shot; default GzBuilder header, CRC-32 and ISIZE trailer."""
+    for name, data in _inputs(pg11).items():
+        for preset in ("default", "fast"):
+            opts = o.PRESETS[preset]()
+            got = dfl.deflate_bytes_gzip_conf(data, _copts(dfl, opts))
+            assert zlib.decompress(got, 31) == data, (name, preset)
+            assert got == o.compress(data, opts, o.GZIP), (name, preset)
+    assert dfl.deflate_bytes_gzip(pg11) == o.compress(pg11, o.opts_default(), o.GZIP)
+
+
+def test_gzip_builder_header_fields(dfl, pg11):
+    """writer.rs:473-491 / lib.rs:393-406 assert the comment field survives; here the whole header does."""
+    b = dfl.GzBuilder().comment(b"Test").filename(b"pg11.txt").extra(b"ab").mtime(1234567)
+    got = dfl.deflate_bytes_gzip_conf(pg11, dfl.Compression.Default, b)
+    hdr = b.into_header()
+    assert got[:len(hdr)] == hdr and hdr[3] == 4 | 8 | 16 and b"Test\0" in hdr
+    d = zlib.decompressobj(31)
+    assert d.decompress(got) == pg11 and d.eof
+    # the deflate stream and the trailer do not depend on the header
+    ref = o.compress(pg11, o.opts_default(), o.GZIP)
+    assert got[len(hdr):] == ref[10:]
+
+
+def test_gz_encoder_writer(dfl, pg11):
+    """writer.rs:331-467: chunked writes == one-shot; checksum(); reset_with_builder; sync flush."""
+    want = dfl.deflate_bytes_gzip(pg11)
+    for chunk in (50, 32768, 70001):
+        sink = bytearray()
+        enc = dfl.write.GzEncoder(sink, dfl.Compression.Default)
+        for i in range(0, len(pg11), chunk):
+            enc.write_all(pg11[i:i + chunk])
+        assert enc.checksum() == zlib.crc32(pg11)
+        enc.finish()
+        assert bytes(sink) == want, chunk
+    s = o.Stream(o.opts_default(), o.GZIP)
+    s.write(pg11[:1000]); s.flush(); s.write(pg11[1000:])
+    sink = bytearray()
+    enc = dfl.write.GzEncoder(sink, dfl.CompressionOptions.default())
+    enc.write_all(pg11[:1000]); enc.flush(); enc.write_all(pg11[1000:])
+    enc.finish()
+    assert bytes(sink) == s.finish()
+    enc = dfl.write.GzEncoder.from_builder(dfl.GzBuilder().comment(b"one"), bytearray(), dfl.Compression.Fast)
+    enc.write_all(pg11[:5000])
+    first = enc.reset_with_builder(bytearray(), dfl.GzBuilder().comment(b"two"))
+    enc.write_all(pg11[5000:12000])
+    second = enc.finish()
+    assert zlib.decompress(bytes(first), 31) == pg11[:5000] and b"one\0" in bytes(first[:20])
+    assert zlib.decompress(bytes(second), 31) == pg11[5000:12000] and b"two\0" in bytes(second[:20])
+
+
+# ---------------------------------------------------------------- the two match paths
+@pytest.fixture(params=["walk", "chains"])
+def match_path(request, dfl):
+    old = dfl.set_match_path(request.param)
+    yield request.param
+    dfl._native.lib().dfl_set_match_path(old)
+
+
+def test_both_match_paths_bit_exact(dfl, pg11, match_path):
+    """k_match (candidate walk) and k_span_scatter + k_match_chains (multi-level chains) are two
+    implementations of matching.rs:87-166 over the same sorted windows; both must equal the oracle."""
+    import datagen
+    inputs = _inputs(pg11)
+    inputs["mix2m"] = datagen.silesia_mix(2 << 20)
+    inputs["enwik1m"] = datagen.enwik_like(1 << 20)
+    inputs["png1m"] = datagen.png_idat_like(1 << 20)
+    inputs["bin1m"] = datagen.binary_like(1 << 20)
+    for name in sorted(os.listdir(os.path.join(FIXTURES, "afl")))[:12]:
+        inputs["afl/" + name] = fixture_bytes("afl/" + name)
+    for preset in ("default", "fast"):
+        opts = o.PRESETS[preset]()
+        for name, data in inputs.items():
+            got = dfl.deflate_bytes_conf(data, _copts(dfl, opts))
+            assert got == o.compress(data, opts, o.RAW), (match_path, name, preset)
+    for checks, lazy, mt in ((4, 8, 1), (16, 258, 1), (64, 4, 1), (7, 0, 0), (128, 33, 1), (129, 32, 1), (100, 20, 0)):
+        opts = o.Options(checks, lazy, mt, 0)
+        data = inputs["mix2m"][:600000]
+        assert dfl.deflate_bytes_conf(data, _copts(dfl, opts)) == o.compress(data, opts, o.RAW), (match_path, checks, lazy, mt)
+
+
+def test_both_match_paths_streaming_dictionary(dfl, pg11, match_path):
+    """Pieces encoded with the previous 32 KiB as dictionary (begin > 0) through either path."""
+    s = o.Stream(o.opts_default(), o.ZLIB)
+    sink = bytearray()
+    enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Default)
+    for lo, hi in ((0, 40000), (40000, 40010), (40010, 120000), (120000, len(pg11))):
+        s.write(pg11[lo:hi]); s.flush()
+        enc.write_all(pg11[lo:hi]); enc.flush()
+    enc.finish()
+    assert bytes(sink) == s.finish()

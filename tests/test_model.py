@@ -79,3 +79,21 @@ def test_model_custom_options(pg11, match_impl):
         opts = o.Options(checks, lazy, mt, 0)
         got, _ = m.compress(data, opts, 4096, 256, 3)
         assert got == o.compress(data, opts, o.RAW), (checks, lazy, mt)
+
+
+def test_checksum_combine_arithmetic():
+    """dfl_core.h crc32_combine / adler32_combine (used by the kernels' tree reductions and by the
+    streaming handle) against CPython zlib on random splits, incl. empty and > 4 GiB-style lengths."""
+    L = m.lib()
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        a = rng.integers(0, 256, int(rng.integers(0, 5000)), dtype=np.uint8).tobytes()
+        b = rng.integers(0, 256, int(rng.integers(0, 70000)), dtype=np.uint8).tobytes()
+        assert L.dflm_crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(a + b)
+        assert L.dflm_adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(a + b)
+    z = bytes(1 << 20)
+    c = zlib.crc32(b"x")
+    want = zlib.crc32(b"x")
+    for _ in range(8):
+        want = zlib.crc32(z, want)
+    assert L.dflm_crc32_combine(c, zlib.crc32(z * 8), 8 << 20) == want
