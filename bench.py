@@ -144,6 +144,7 @@ def run_ours(args):
 
     import datagen
     import deflate_rs_b200 as dfl
+    from deflate_rs_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +156,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = dfl._native.lib()
+    if args.match_path:
+        dfl.set_match_path(args.match_path)
 
     size = args.size_mib << 20
     data = datagen.silesia_mix(size, SEED + rank)
@@ -167,7 +170,6 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     gather_buf = None
-    sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def step():
         rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), size, ctypes.byref(opts), dfl.RAW, None, 0,
@@ -176,23 +178,10 @@ def run_ours(args):
             raise dfl.DeflateB200Error(rc, "dfl_compress_device")
         if world > 1:
             # the one real exchange step: compressed shards -> rank 0 (sizes all-gather, then send/recv)
-            mine = torch.tensor([sz.value], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(sizes_t, mine)
-            sizes = sizes_t.tolist()
+            nonlocal gather_buf
+            buf, _ = sharding.gather_streams(out, sz.value, dst=0, recv_buf=gather_buf)
             if rank == 0:
-                offs = [0]
-                for s in sizes:
-                    offs.append(offs[-1] + s)
-                nonlocal gather_buf
-                if gather_buf is None or gather_buf.numel() < offs[-1]:
-                    gather_buf = torch.empty(int(offs[-1] * 1.1) + 4096, dtype=torch.uint8, device=dev)
-                ops = [dist.P2POp(dist.irecv, gather_buf[offs[r]:offs[r + 1]], r) for r in range(1, world)]
-                gather_buf[: sizes[0]].copy_(out[: sizes[0]])
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            else:
-                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, out[: sz.value], 0)]):
-                    w.wait()
+                gather_buf = buf
         return sz.value
 
     def barrier():
@@ -309,6 +298,8 @@ def main():
     ap.add_argument("--size-mib", type=int, default=1024, help="input size per GPU (default: the 1 GiB config)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
     ap.add_argument("--verify", default="prefix", choices=["none", "prefix", "full"])
+    ap.add_argument("--match-path", default=None, choices=["walk", "chains"],
+                    help="match kernels for the default options (identical output; default: the library's choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -405,6 +405,22 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     return DFL_OK;
 }
 
+extern "C" int dfl_compress_device_piece(const void* d_in, size_t n_total, size_t dict_len, const dfl_options* opt, int flush_mode,
+                                         void* d_out, size_t out_cap, size_t* out_len, void* stream) {
+    if (!opt || !d_out || !out_len || (!d_in && n_total) || dict_len > n_total) return DFL_E_ARG;
+    if (flush_mode != DFL_FLUSH_SYNC && flush_mode != DFL_FLUSH_FINISH) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
+    // only the last 32 KiB in front of the piece can be referenced (matching.rs:102-106)
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(d_in);
+    size_t skip = dict_len > kWindow ? dict_len - kWindow : 0;
+    skip &= ~(size_t)15;   // keep the 16-byte alignment of the staging loads
+    return run_pipeline(c, st, p + skip, n_total - skip, dict_len - skip, opt, DFL_RAW, 0, flush_mode == DFL_FLUSH_FINISH ? 1 : 0,
+                        flush_mode == DFL_FLUSH_SYNC ? 1 : 0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+}
+
 extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void* stream) {
     if (!crc || (!d_in && n)) return DFL_E_ARG;
     Context& c = tls_context();

@@ -99,6 +99,18 @@ int dfl_compress_device(const void *d_in, size_t n, const dfl_options *opt, int 
                         const uint8_t *gz_hdr, size_t gz_hdr_len, void *d_out, size_t out_cap,
                         size_t *out_len, void *stream);
 
+/* ---- one piece of a longer stream, device buffers ------------------------------------------
+ * compress_data_dynamic_n(piece, &mut state, Flush::{Sync,Finish}) (compress.rs:80-84) for a state
+ * whose window already holds the plaintext in front of the piece: d_in points at `dict_len` bytes
+ * of that plaintext (the last 32768 are what matters, matching.rs:102-106) followed by the piece,
+ * n_total bytes in all.  Produces the piece's raw DEFLATE blocks only (no container bytes):
+ * DFL_FLUSH_SYNC ends them with the empty stored block 00 00 FF FF (compress.rs:258-261), so the
+ * next piece starts byte aligned and pieces encoded independently -- e.g. one per GPU -- concatenate
+ * into the stream the reference's writer produces with flush() called at the same offsets;
+ * DFL_FLUSH_FINISH sets BFINAL on the last block. */
+int dfl_compress_device_piece(const void *d_in, size_t n_total, size_t dict_len, const dfl_options *opt,
+                              int flush_mode, void *d_out, size_t out_cap, size_t *out_len, void *stream);
+
 /* Per-stage device timings of the most recent dfl_compress_device call on this thread, in
  * milliseconds (CUDA events on the launching stream): names[i] points to a static string.
  * Returns the number of stages (0 if timing was not enabled with dfl_set_profiling(1)). */

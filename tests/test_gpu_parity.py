@@ -349,3 +349,27 @@ def test_both_match_paths_streaming_dictionary(dfl, pg11, match_path):
         enc.write_all(pg11[lo:hi]); enc.flush()
     enc.finish()
     assert bytes(sink) == s.finish()
+
+
+# ---------------------------------------------------------------- pieces of one stream
+def test_pieces_concatenate_to_the_flushed_reference_stream(dfl, pg11, match_path):
+    """dfl_compress_device_piece: pieces encoded independently (as the ranks of a multi-GPU job do),
+    each with the 32 KiB in front of it as dictionary, concatenate into the stream the reference's
+    writer produces with flush() at the piece boundaries."""
+    import datagen
+    import torch
+    from deflate_rs_b200 import sharding
+    for data, world, align in ((pg11, 3, 4096), (datagen.silesia_mix(3 << 20), 4, 1 << 16), (pg11[:50000], 8, 4096)):
+        src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        bounds = [b for b in sharding.piece_bounds(len(data), world, align) if b[1] > b[0]]
+        s = o.Stream(o.opts_default(), o.RAW)
+        got = b""
+        for g, (lo, hi) in enumerate(bounds):
+            last = g + 1 == len(bounds)
+            out, n = sharding.encode_piece_device(src, lo, hi, dfl.Compression.Default, last)
+            got += bytes(out[:n].cpu().numpy())
+            s.write(data[lo:hi])
+            if not last:
+                s.flush()
+        assert got == s.finish(), (len(data), world)
+        assert zlib.decompress(got, -15) == data
