@@ -324,15 +324,15 @@ ParseState state_from(uint32_t pos, uint32_t key) {
 uint32_t g_last_repairs = 0, g_last_seq_repairs = 0;
 
 void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, const std::vector<uint32_t>& Mf,
-               const std::vector<uint32_t>& Mq, std::vector<uint32_t>& tokens) {
+               const std::vector<uint32_t>& Mq, std::vector<uint32_t>& tokens, uint32_t begin = 0) {
     tokens.clear();
     g_last_repairs = g_last_seq_repairs = 0;
-    if (n == 0) return;
-    uint32_t nseg = (n + cfg.pseg - 1) / cfg.pseg;
+    if (n <= begin) return;
+    uint32_t nseg = (n - begin + cfg.pseg - 1) / cfg.pseg;
     std::vector<SegRec> seg(nseg);
     for (uint32_t s = 0; s < nseg; s++) {
-        uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
-        uint32_t start = a > cfg.warm ? a - cfg.warm : 0;
+        uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+        uint32_t start = a - begin > cfg.warm ? a - cfg.warm : begin;
         parse_segment(prm, d, n, Mf, Mq, parse_state_init(start), a, b, seg[s]);
     }
     auto bad = [&](uint32_t s) {
@@ -346,14 +346,14 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
         std::vector<SegRec> fixed(list.size());
         for (size_t i = 0; i < list.size(); i++) {
             uint32_t s = list[i];
-            uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+            uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
             parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, fixed[i]);
         }
         for (size_t i = 0; i < list.size(); i++) { seg[list[i]] = fixed[i]; g_last_repairs++; }
     }
     for (uint32_t s = 1; s < nseg; s++) {   // sequential fallback
         if (bad(s)) {
-            uint32_t a = s * cfg.pseg, b = std::min(n, a + cfg.pseg);
+            uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
             SegRec r;
             parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, r);
             seg[s] = r; g_last_seq_repairs++;
@@ -494,6 +494,20 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
     std::vector<uint32_t> Mf, Mq, tokens;
     if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
     parse_all(prm, cfg, in, n, Mf, Mq, tokens);
+    *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
+    memcpy(*toks, tokens.data(), tokens.size() * 4);
+    *ntoks = tokens.size();
+    return 0;
+}
+
+// tokens of in[begin..n) with in[0..begin) as dictionary (the GPU pipeline's `begin` semantics)
+int dflm_tokens_from(const uint8_t* in, uint32_t n, uint32_t begin, uint16_t checks, uint16_t lazy, uint8_t mtype,
+                     uint32_t** toks, size_t* ntoks) {
+    Params prm = make_params(checks, lazy, mtype);
+    Cfg cfg{8192, 1024, 3};
+    std::vector<uint32_t> Mf, Mq, tokens;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
+    parse_all(prm, cfg, in, n, Mf, Mq, tokens, begin);
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
     *ntoks = tokens.size();
