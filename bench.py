@@ -31,6 +31,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# BASELINE.json configs.  The default (c2) is the one the metric is quoted on; the others are
+# measured with the same machinery (`--config`) and reported in DESIGN.md.
+CONFIGS = {
+    "c2": dict(gen="silesia_mix", seed=0x51DE51A, size_mib=1024, preset="default", wrap="raw",
+               desc="synthetic Silesia-mix text", opts="Compression::Default (128 checks, lazy<32), raw deflate"),
+    "c3": dict(gen="enwik_like", seed=0xE2010C, size_mib=1024, preset="fast", wrap="zlib",
+               desc="synthetic enwik-like text", opts="Compression::Fast (1 check, greedy), zlib (Adler-32 on device)"),
+    "c5": dict(gen="binary_like", seed=0xB1A2, size_mib=256, preset="high", wrap="raw",
+               desc="synthetic binary", opts="CompressionOptions::high() (1768 checks, lazy<128), raw deflate"),
+}
+
 METRIC = "encode MiB/s (uncompressed in)"
 UNIT = "MiB/s"
 SEED = 0x51DE51A
@@ -91,12 +102,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_rate(data: bytes, sample_bytes: int):
+def oracle_rate(data: bytes, sample_bytes: int, preset: str = "default", wrap: str = "raw"):
     """MiB/s of the oracle (reference algorithm, single thread) on the first sample_bytes of data."""
     import oracle_lib
     sample = data[:sample_bytes]
     t = time.perf_counter()
-    out = oracle_lib.compress(sample, oracle_lib.opts_default(), oracle_lib.RAW)
+    out = oracle_lib.compress(sample, oracle_lib.PRESETS[preset](), {"raw": oracle_lib.RAW, "zlib": oracle_lib.ZLIB}[wrap])
     dt = time.perf_counter() - t
     return len(sample) / dt / 2 ** 20, len(out), dt
 
@@ -109,26 +120,27 @@ def run_reference(args):
     if rank != 0:
         return
     import datagen
+    cfg = CONFIGS[args.config]
     size = min(args.size_mib, 256) << 20
-    data = datagen.silesia_mix(size, SEED)
+    data = getattr(datagen, cfg["gen"])(size, cfg["seed"])
     # size the per-step sample so that the whole run stays within ~2 minutes
-    probe_rate, _, _ = oracle_rate(data, 4 << 20)
+    probe_rate, _, _ = oracle_rate(data, 4 << 20, cfg["preset"], cfg["wrap"])
     steps_total = args.steps + args.warmup
     sample = int(min(size, max(4 << 20, probe_rate * 2 ** 20 * 110.0 / steps_total)))
     sample &= ~0xFFFF
     for _ in range(args.warmup):
-        oracle_rate(data, sample)
+        oracle_rate(data, sample, cfg["preset"], cfg["wrap"])
     t0 = time.perf_counter()
     csize = 0
     for _ in range(args.steps):
-        _, csize, _ = oracle_rate(data, sample)
+        _, csize, _ = oracle_rate(data, sample, cfg["preset"], cfg["wrap"])
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt / 2 ** 20
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.size_mib} MiB synthetic Silesia-mix text, Compression::Default, raw deflate",
+        "config": {"workload": f"{args.size_mib} MiB {cfg['desc']}, {cfg['opts']}",
                    "sample": f"first {sample >> 20} MiB per step", "ratio": csize / sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"first {sample >> 20} MiB of the workload per step, oracle/ (C port of the reference "
@@ -159,20 +171,24 @@ def run_ours(args):
     if args.match_path:
         dfl.set_match_path(args.match_path)
 
+    cfg = CONFIGS[args.config]
+    wrap = {"raw": dfl.RAW, "zlib": dfl.ZLIB}[cfg["wrap"]]
+    wbits = {"raw": -15, "zlib": 15}[cfg["wrap"]]
     size = args.size_mib << 20
-    data = datagen.silesia_mix(size, SEED + rank)
+    data = getattr(datagen, cfg["gen"])(size, cfg["seed"] + rank)
     host_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
     src = host_in.to(dev, non_blocking=False)
-    cap = L.dfl_bound(size, dfl.RAW) + 64
+    cap = L.dfl_bound(size, wrap) + 64
     out = torch.empty(cap, dtype=torch.uint8, device=dev)
-    opts = dfl.CompressionOptions.default()._c()
+    opts = {"default": dfl.CompressionOptions.default, "fast": dfl.CompressionOptions.fast,
+            "high": dfl.CompressionOptions.high}[cfg["preset"]]()._c()
     sz = ctypes.c_size_t()
     stream = torch.cuda.current_stream(dev)
 
     gather_buf = None
 
     def step():
-        rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), size, ctypes.byref(opts), dfl.RAW, None, 0,
+        rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), size, ctypes.byref(opts), wrap, None, 0,
                                    ctypes.c_void_p(out.data_ptr()), cap, ctypes.byref(sz), ctypes.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise dfl.DeflateB200Error(rc, "dfl_compress_device")
@@ -197,7 +213,7 @@ def run_ours(args):
     verify_n = min(size, 64 << 20) if args.verify == "prefix" else size
     if args.verify != "none" and rank == 0:
         comp = bytes(out[:csize].cpu().numpy())
-        d = zlib.decompressobj(-15)
+        d = zlib.decompressobj(wbits)
         got = d.decompress(comp, verify_n)
         assert got == data[:verify_n], "GPU stream does not inflate to the input"
 
@@ -238,7 +254,7 @@ def run_ours(args):
     n_out = ctypes.c_size_t()
 
     def e2e_step():
-        rc = L.dfl_compress(ctypes.c_void_p(host_in.data_ptr()), size, ctypes.byref(opts), dfl.RAW, None, 0,
+        rc = L.dfl_compress(ctypes.c_void_p(host_in.data_ptr()), size, ctypes.byref(opts), wrap, None, 0,
                             ctypes.c_void_p(host_out.data_ptr()), cap, ctypes.byref(n_out))
         if rc != 0:
             raise dfl.DeflateB200Error(rc, "dfl_compress")
@@ -261,13 +277,13 @@ def run_ours(args):
         alg_bytes = size + csize
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms else None
         cpu_sample = min(size, args.cpu_sample_mib << 20)
-        cpu_rate, cpu_csize, cpu_dt = oracle_rate(data, cpu_sample)
+        cpu_rate, cpu_csize, cpu_dt = oracle_rate(data, cpu_sample, cfg["preset"], cfg["wrap"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{args.size_mib} MiB synthetic Silesia-mix text per GPU (seed 0x51DE51A+rank), "
-                                   "Compression::Default (128 checks, lazy<32), raw deflate",
+            "config": {"workload": f"{args.size_mib} MiB {cfg['desc']} per GPU (seed {cfg['seed']:#x}+rank), {cfg['opts']}",
+                       "name": args.config,
                        "l2": "input (>= 1 GiB) larger than L2, no flush needed", "compressed_bytes": csize,
                        "ratio": csize / size, "verified": args.verify,
                        "parallelism": f"independent shards x{world}, NCCL gather to rank 0" if world > 1 else "single GPU"},
@@ -295,12 +311,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size-mib", type=int, default=1024, help="input size per GPU (default: the 1 GiB config)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (default: c2, the headline)")
+    ap.add_argument("--size-mib", type=int, default=None, help="input size per GPU (default: the config's own size)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
     ap.add_argument("--verify", default="prefix", choices=["none", "prefix", "full"])
     ap.add_argument("--match-path", default=None, choices=["walk", "chains"],
                     help="match kernels for the default options (identical output; default: the library's choice)")
     args = ap.parse_args()
+    if args.size_mib is None:
+        args.size_mib = CONFIGS[args.config]["size_mib"]
     if args.impl == "reference":
         run_reference(args)
     else:

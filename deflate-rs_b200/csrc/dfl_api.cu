@@ -62,8 +62,28 @@ void dev_free(T*& p) {
     p = nullptr;
 }
 
+// Input that is still on its way to the device: slice k (kCopySlice bytes) is complete once
+// ev[k] has fired (recorded on the copy stream by dfl_compress).
+constexpr size_t kCopySlice = 128u << 20;
+struct InputArrival {
+    std::vector<cudaEvent_t>* ev;
+    size_t n_slices;
+    const uint8_t* h_src;      // host source; slice k is copied by feed(k) right before it is waited for, so
+    uint8_t* d_dst;            // that with pageable memory (a blocking, staged copy) the kernels of slice k
+    size_t n;                  // run while slice k + 1 is being staged
+    cudaStream_t copy_stream;
+    cudaError_t feed(size_t k) const {
+        const size_t lo = k * kCopySlice, len = (n - lo) < kCopySlice ? (n - lo) : kCopySlice;
+        cudaError_t e = cudaMemcpyAsync(d_dst + lo, h_src + lo, len, cudaMemcpyHostToDevice, copy_stream);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord((*ev)[k], copy_stream);
+    }
+};
+
 struct Context {
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_ev;
     Buffers buf;
     uint8_t* d_in = nullptr;    // staging for host-buffer calls
     size_t d_in_cap = 0;
@@ -81,6 +101,7 @@ struct Context {
             return DFL_E_NODEVICE;
         }
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         CK(cudaMallocHost(reinterpret_cast<void**>(&h_meta), sizeof(DevMeta)));
         int rc = dev_alloc(buf.meta, 1);
         if (rc) return rc;
@@ -106,6 +127,8 @@ struct Context {
         dev_free(buf.meta);
         dev_free(d_in); dev_free(d_out); dev_free(d_tok_in);
         if (h_meta) cudaFreeHost(h_meta);
+        for (auto e : copy_ev) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -220,7 +243,7 @@ const uint8_t kGzipDefaultHeader[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
 int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, size_t begin, const dfl_options* opt, int wrap,
                  uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out, size_t out_cap, size_t* out_bytes,
                  const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0,
-                 const uint8_t* gz_hdr = nullptr) {
+                 const uint8_t* gz_hdr = nullptr, const InputArrival* arrival = nullptr) {
     if (n >= 0xfffffff0ull) return DFL_E_UNSUPPORTED;   // 32-bit positions; see DESIGN.md "limits"
     if (opt->special != 0) return DFL_E_UNSUPPORTED;    // compression_options.rs:52-59: placeholders
     EncodeJob j;
@@ -248,6 +271,35 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
     const bool need_lz = (d_tokens_override == nullptr);
     const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
+    if (need_match) {
+        const uint32_t w_end = n_windows(j), w_sort0 = first_sort_window(j), w_match0 = first_match_window(j);
+        if (arrival && !use_chains(j.prm)) {
+            // the input is still being copied: sort and match every window as soon as its bytes
+            // (and the 272 bytes of look-ahead behind it) are on the device
+            uint32_t w_sorted = w_sort0, w_matched = w_match0;
+            for (size_t k = 0; k < arrival->n_slices; k++) {
+                CK(arrival->feed(k));
+                CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0));
+                const size_t have = (k + 1 == arrival->n_slices) ? n : (k + 1) * kCopySlice;
+                uint32_t w_ok = (have >= n) ? w_end : (uint32_t)((have - 272) / kWindow);
+                if (w_ok > w_end) w_ok = w_end;
+                CK(launch_window_sort(j, b, st, w_sorted, w_ok));
+                if (w_ok > w_sorted) w_sorted = w_ok;
+                CK(launch_match(j, b, st, w_matched, w_sorted));
+                if (w_sorted > w_matched) w_matched = w_sorted;
+            }
+            tm.mark("window_sort+match");
+        } else {
+            if (arrival)
+                for (size_t k = 0; k < arrival->n_slices; k++) { CK(arrival->feed(k)); CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
+            CK(launch_window_sort(j, b, st, w_sort0, w_end));
+            tm.mark("window_sort");
+            CK(launch_match(j, b, st, w_match0, w_end));
+            tm.mark("match");
+        }
+    } else if (arrival) {
+        for (size_t k = 0; k < arrival->n_slices; k++) { CK(arrival->feed(k)); CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
+    }
     if (wrap == DFL_ZLIB && final_block && !stop_after_tokens) {
         CK(launch_adler32(d_in + begin, n - begin, b, st));
         tm.mark("adler32");
@@ -255,12 +307,6 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     if (wrap == DFL_GZIP && final_block && !stop_after_tokens) {
         CK(launch_crc32(d_in + begin, n - begin, b, st));
         tm.mark("crc32");
-    }
-    if (need_match) {
-        CK(launch_window_sort(j, b, st));
-        tm.mark("window_sort");
-        CK(launch_match(j, b, st));
-        tm.mark("match");
     }
     if (need_lz) {
         CK(launch_parse(j, b, st));
@@ -393,10 +439,17 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
     size_t bound = dfl_bound(n, wrap) + gz_hdr_len;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound + 64))) return rc;
-    if (n) CK(cudaMemcpyAsync(c.d_in, in, n, cudaMemcpyHostToDevice, c.stream));
+    // host -> device in slices on a second stream; the pipeline's first two stages start on a
+    // slice as soon as it has landed (writer.rs callers pay PCIe: SURVEY 8(f) rank 1)
+    InputArrival arrival{&c.copy_ev, (n + kCopySlice - 1) / kCopySlice, in, c.d_in, n, c.copy_stream};
+    while (c.copy_ev.size() < arrival.n_slices) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c.copy_ev.push_back(e);
+    }
     size_t produced = 0;
     rc = run_pipeline(c, c.stream, c.d_in, n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1, 0, c.d_out, c.d_out_cap,
-                      &produced, nullptr, 0, 0, gz_hdr);
+                      &produced, nullptr, 0, 0, gz_hdr, arrival.n_slices ? &arrival : nullptr);
     if (rc) return rc;
     *out_len = produced;
     if (produced > out_cap) return DFL_E_OVERFLOW;

@@ -9,8 +9,14 @@
 namespace dfl {
 
 // Tunables of the parse stage (see DESIGN.md "parse").
-constexpr uint32_t kParseSeg = 8192;     // positions owned by one parse thread
-constexpr uint32_t kParseWarm = 1024;    // speculative warm-up before the segment start
+#ifndef DFL_PARSE_SEG
+#define DFL_PARSE_SEG 8192
+#endif
+#ifndef DFL_PARSE_WARM
+#define DFL_PARSE_WARM 1024
+#endif
+constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread
+constexpr uint32_t kParseWarm = DFL_PARSE_WARM;   // speculative warm-up before the segment start
 constexpr uint32_t kParseTokCap = kParseSeg + kParseWarm + 264;   // tokens one thread can emit
 constexpr uint32_t kRepairRounds = 3;    // parallel repair rounds before the sequential fallback
 
@@ -111,8 +117,11 @@ struct EncodeJob {
 constexpr uint32_t kAdlerChunk = 1u << 16;
 
 // Stage launchers (dfl_kernels.cu).  All asynchronous on `st`.
-cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st);
-cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st);
+uint32_t n_windows(const EncodeJob& j);
+uint32_t first_match_window(const EncodeJob& j);
+uint32_t first_sort_window(const EncodeJob& j);
+cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
 cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st);

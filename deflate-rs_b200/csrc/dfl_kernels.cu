@@ -1533,41 +1533,46 @@ static cudaError_t ensure_attrs() {
     return cudaSuccess;
 }
 
-cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+// Window ranges: the sort needs windows [first_sort_window(j), n_windows(j)), the match stage
+// [first_match_window(j), n_windows(j)).  Both can be issued in pieces [w_lo, w_hi) as the input
+// arrives (dfl_compress overlaps the host-to-device copy with them); matching window w needs the
+// sorted lists of w - 1 and w (the chain path also the bucket offsets of w + 1, so it is issued whole).
+uint32_t n_windows(const EncodeJob& j) { return (j.n + kWindow - 1) / kWindow; }
+uint32_t first_match_window(const EncodeJob& j) { return j.begin / kWindow; }
+uint32_t first_sort_window(const EncodeJob& j) { uint32_t w = j.begin / kWindow; return w > 0 ? w - 1 : 0; }
+
+cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
-    uint32_t n_win = (j.n + kWindow - 1) / kWindow;
-    uint32_t w_begin = j.begin / kWindow;
-    uint32_t w_first = w_begin > 0 ? w_begin - 1 : 0;
-    if (n_win <= w_first) return cudaSuccess;
+    if (w_hi <= w_lo) return cudaSuccess;
     if (use_chains(j.prm)) {
-        k_window_sort<true><<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
-        DFL_LAUNCH_CHECK();
-        k_span_scatter<<<n_win - w_first, kScatterThreads, 0, st>>>(j.d_in, j.n, w_first, w_begin,
-                                                                     reinterpret_cast<const uint32_t*>(b.K), b.off, b.M);
+        k_window_sort<true><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
         DFL_LAUNCH_CHECK();
         return cudaSuccess;
     }
-    k_window_sort<false><<<n_win - w_first, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_first, b.K, b.off);
+    k_window_sort<false><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
-    uint32_t n_win = (j.n + kWindow - 1) / kWindow;
-    uint32_t w_first = j.begin / kWindow;
-    if (n_win <= w_first) return cudaSuccess;
+    if (w_hi <= w_lo) return cudaSuccess;
     if (use_chains(j.prm)) {
-        k_match_chains<<<n_win - w_first, kChainThreads, kChainSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm.checks, b.M, b.Mf);
+        // issued once, over every window: [w_lo, w_hi) must be the whole range here
+        const uint32_t w_sort = first_sort_window(j);
+        k_span_scatter<<<n_windows(j) - w_sort, kScatterThreads, 0, st>>>(j.d_in, j.n, w_sort, first_match_window(j),
+                                                                          reinterpret_cast<const uint32_t*>(b.K), b.off, b.M);
+        DFL_LAUNCH_CHECK();
+        k_match_chains<<<w_hi - w_lo, kChainThreads, kChainSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm.checks, b.M, b.Mf);
         DFL_LAUNCH_CHECK();
         return cudaSuccess;
     }
     if (j.prm.need_quarter)
-        k_match<true><<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<true><<<w_hi - w_lo, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     else
-        k_match<false><<<n_win - w_first, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_first, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<false><<<w_hi - w_lo, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
