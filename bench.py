@@ -38,6 +38,9 @@ CONFIGS = {
                desc="synthetic Silesia-mix text", opts="Compression::Default (128 checks, lazy<32), raw deflate"),
     "c3": dict(gen="enwik_like", seed=0xE2010C, size_mib=1024, preset="fast", wrap="zlib",
                desc="synthetic enwik-like text", opts="Compression::Fast (1 check, greedy), zlib (Adler-32 on device)"),
+    "c4": dict(gen="png_idat_like", seed=0x1DA7, size_mib=1024, preset="default", wrap="zlib", chunks=256,
+               desc="synthetic PNG-IDAT-like data as 256 independent 4 MiB chunks",
+               opts="Compression::Default, one zlib stream per chunk, chunks dealt round-robin to the GPUs"),
     "c5": dict(gen="binary_like", seed=0xB1A2, size_mib=256, preset="high", wrap="raw",
                desc="synthetic binary", opts="CompressionOptions::high() (1768 checks, lazy<128), raw deflate"),
 }
@@ -148,6 +151,119 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def run_chunks(args):
+    """BASELINE config 4: independent chunks, one zlib stream each, dealt round-robin to the ranks (strong
+    scaling: the job is the same 256 chunks at every N); the compressed chunks are gathered on rank 0."""
+    import zlib
+
+    import torch
+    import torch.distributed as dist
+
+    import datagen
+    import deflate_rs_b200 as dfl
+    from deflate_rs_b200 import sharding
+
+    cfg = CONFIGS["c4"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = dfl._native.lib()
+    n_chunks = cfg["chunks"]
+    chunk = (args.size_mib << 20) // n_chunks
+    mine = sharding.assign_units(n_chunks, world, rank)
+    datas = [datagen.png_idat_like(chunk, cfg["seed"] + i) for i in mine]
+    host = [torch.frombuffer(bytearray(d), dtype=torch.uint8).pin_memory() for d in datas]
+    srcs = [h.to(dev) for h in host]
+    cap = L.dfl_bound(chunk, dfl.ZLIB) + 64
+    outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in mine]
+    packed = torch.empty(len(mine) * cap, dtype=torch.uint8, device=dev)
+    gather_buf = None
+    sizes = []
+
+    def step():
+        nonlocal gather_buf, sizes
+        _, sizes = dfl.compress_device_batch(srcs, dfl.Compression.Default, dfl.ZLIB, outs)
+        off = 0
+        for o, s in zip(outs, sizes):
+            packed[off:off + s].copy_(o[:s])
+            off += s
+        if world > 1:
+            buf, _ = sharding.gather_streams(packed, off, dst=0, recv_buf=gather_buf)
+            if rank == 0:
+                gather_buf = buf
+        return off
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if args.verify != "none":
+        for o, s, d in list(zip(outs, sizes, datas))[:8]:
+            assert zlib.decompress(bytes(o[:s].cpu().numpy())) == d, "chunk does not inflate to its input"
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    csize = 0
+    for _ in range(args.steps):
+        csize = step()
+    ev1.record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(csize)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms_per_step = float(t.item()) / args.steps
+    total_in = chunk * n_chunks
+    value = total_in / (ms_per_step / 1e3) / 2 ** 20
+    # e2e: host chunks in, host streams out, through the one-shot host API
+    e2e_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    opts = dfl.CompressionOptions.default()._c()
+    n_out = ctypes.c_size_t()
+    barrier()
+    t0 = time.perf_counter()
+    for h in host:
+        rc = L.dfl_compress(ctypes.c_void_p(h.data_ptr()), chunk, ctypes.byref(opts), dfl.ZLIB, None, 0,
+                            ctypes.c_void_p(e2e_out.data_ptr()), cap, ctypes.byref(n_out))
+        assert rc == 0
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        cpu_rate, cpu_csize, cpu_dt = oracle_rate(datas[0], min(chunk, args.cpu_sample_mib << 20), "default", "zlib")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{args.size_mib} MiB {cfg['desc']} (seed {cfg['seed']:#x}+i), {cfg['opts']}", "name": "c4",
+                       "l2": "1 GiB of input per step, larger than L2", "compressed_bytes": int(tot.item()),
+                       "ratio": float(tot.item()) / total_in, "verified": args.verify,
+                       "parallelism": f"{n_chunks} chunks over {world} GPU(s), NCCL gather to rank 0" if world > 1 else "single GPU"},
+            "e2e": {"value": total_in / float(te.item()) / 2 ** 20, "unit": UNIT, "h2d_bytes_per_step": chunk * len(mine),
+                    "d2h_bytes_per_step": int(csize)},
+            "gpu_launches": None, "clocks": clk,
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"one chunk ({chunk >> 20} MiB), oracle/, {cpu_dt:.1f} s", "ratio": cpu_csize / min(chunk, args.cpu_sample_mib << 20)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -322,6 +438,8 @@ def main():
         args.size_mib = CONFIGS[args.config]["size_mib"]
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_chunks(args)
     else:
         run_ours(args)
 

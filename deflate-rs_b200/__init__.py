@@ -24,7 +24,7 @@ from ._native import DeflateB200Error, RAW, ZLIB, GZIP  # noqa: F401
 __all__ = [
     "Compression", "CompressionOptions", "MatchingType", "SpecialOptions", "deflate_bytes", "deflate_bytes_conf",
     "deflate_bytes_zlib", "deflate_bytes_zlib_conf", "deflate_bytes_gzip", "deflate_bytes_gzip_conf", "GzBuilder",
-    "write", "compress_device", "DeflateB200Error",
+    "write", "compress_device", "compress_device_batch", "DeflateB200Error",
 ]
 
 
@@ -207,6 +207,29 @@ def compress_device(src, options=Compression.Default, wrap=RAW, out=None, stream
                                    ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.byref(sz), st)
     _native.check(rc, "dfl_compress_device")
     return out, sz.value
+
+
+def compress_device_batch(srcs, options=Compression.Default, wrap=ZLIB, outs=None):
+    """dfl_compress_device_batch: independent streams (a list of CUDA uint8 tensors) encoded concurrently.
+    Returns (outs, sizes)."""
+    import torch
+
+    L = _native.lib()
+    k = len(srcs)
+    if outs is None:
+        outs = [torch.empty(L.dfl_bound(s.numel(), wrap) + 64, dtype=torch.uint8, device=s.device) for s in srcs]
+    opts = CompressionOptions.from_(options)._c()
+    d_in = (ctypes.c_void_p * k)(*[s.data_ptr() for s in srcs])
+    d_out = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
+    n = (ctypes.c_size_t * k)(*[s.numel() for s in srcs])
+    cap = (ctypes.c_size_t * k)(*[o.numel() for o in outs])
+    out_len = (ctypes.c_size_t * k)()
+    status = (ctypes.c_int * k)()
+    torch.cuda.current_stream(srcs[0].device).synchronize() if k else None
+    with torch.cuda.device(srcs[0].device if k else 0):
+        rc = L.dfl_compress_device_batch(k, d_in, n, ctypes.byref(opts), wrap, d_out, cap, out_len, status)
+    _native.check(rc, "dfl_compress_device_batch")
+    return outs, [int(x) for x in out_len]
 
 
 class _Encoder:

@@ -240,10 +240,13 @@ uint32_t wrap_header_bytes(int wrap, size_t gz_hdr_len) {
 // (lib.rs:251, writer.rs:341-357): no flags, MTIME 0, XFL 0, OS 255 (unknown).
 const uint8_t kGzipDefaultHeader[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
 
-int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, size_t begin, const dfl_options* opt, int wrap,
-                 uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out, size_t out_cap, size_t* out_bytes,
-                 const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0,
-                 const uint8_t* gz_hdr = nullptr, const InputArrival* arrival = nullptr) {
+// issue_pipeline queues every stage and the read-back of the bookkeeping on `st` without waiting;
+// finish_pipeline waits for it and turns the bookkeeping into the call's result.  dfl_compress_device_batch
+// keeps several of these in flight on different streams; everything else runs them back to back.
+int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d_in, size_t n, size_t begin,
+                   const dfl_options* opt, int wrap, uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out,
+                   size_t out_cap, const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0,
+                   int stop_after_tokens = 0, const uint8_t* gz_hdr = nullptr, const InputArrival* arrival = nullptr) {
     if (n >= 0xfffffff0ull) return DFL_E_UNSUPPORTED;   // 32-bit positions; see DESIGN.md "limits"
     if (opt->special != 0) return DFL_E_UNSUPPORTED;    // compression_options.rs:52-59: placeholders
     EncodeJob j;
@@ -266,8 +269,6 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
     int rc = c.ensure(n, j.prm.need_quarter != 0, need_match_stage && use_chains(j.prm));
     if (rc) return rc;
     Buffers& b = c.buf;
-    g_launch_count = 0;
-    StageTimer tm(st, t_profiling != 0);
     CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
     const bool need_lz = (d_tokens_override == nullptr);
     const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
@@ -329,8 +330,11 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
         tm.mark("finalize");
     }
     CK(cudaMemcpyAsync(c.h_meta, b.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
+    return DFL_OK;
+}
+
+int finish_pipeline(Context& c, cudaStream_t st, size_t n, size_t begin, size_t* out_bytes) {
     CK(cudaStreamSynchronize(st));
-    tm.finish();
     const DevMeta& m = *c.h_meta;
     t_counters[0] = m.n_tokens;
     t_counters[1] = m.n_blocks;
@@ -347,6 +351,20 @@ int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, siz
         return DFL_E_INTERNAL;
     }
     return DFL_OK;
+}
+
+int run_pipeline(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, size_t begin, const dfl_options* opt, int wrap,
+                 uint32_t hdr_bytes, int final_block, int sync_marker, uint8_t* d_out, size_t out_cap, size_t* out_bytes,
+                 const uint32_t* d_tokens_override = nullptr, uint64_t n_tokens_override = 0, int stop_after_tokens = 0,
+                 const uint8_t* gz_hdr = nullptr, const InputArrival* arrival = nullptr) {
+    g_launch_count = 0;
+    StageTimer tm(st, t_profiling != 0);
+    int rc = issue_pipeline(c, st, tm, d_in, n, begin, opt, wrap, hdr_bytes, final_block, sync_marker, d_out, out_cap,
+                            d_tokens_override, n_tokens_override, stop_after_tokens, gz_hdr, arrival);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    rc = finish_pipeline(c, st, n, begin, out_bytes);
+    tm.finish();
+    return rc;
 }
 
 bool valid_wrap(int wrap) { return wrap == DFL_RAW || wrap == DFL_ZLIB || wrap == DFL_GZIP; }
@@ -472,6 +490,45 @@ extern "C" int dfl_compress_device_piece(const void* d_in, size_t n_total, size_
     skip &= ~(size_t)15;   // keep the 16-byte alignment of the staging loads
     return run_pipeline(c, st, p + skip, n_total - skip, dict_len - skip, opt, DFL_RAW, 0, flush_mode == DFL_FLUSH_FINISH ? 1 : 0,
                         flush_mode == DFL_FLUSH_SYNC ? 1 : 0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+}
+
+// ---- many independent streams (PNG IDAT-like chunks): a pool of contexts, each with
+// its own stream and scratch, keeps kBatchLanes pipelines in flight so that small inputs fill the GPU.
+extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, const size_t* n, const dfl_options* opt,
+                                         int wrap, void* const* d_out, const size_t* out_cap, size_t* out_len,
+                                         int* status) {
+    if (!opt || !valid_wrap(wrap) || (count && (!d_in || !n || !d_out || !out_cap || !out_len))) return DFL_E_ARG;
+    constexpr size_t kBatchLanes = 16;
+    thread_local std::vector<std::unique_ptr<Context>> pool;
+    const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
+    while (pool.size() < lanes) pool.emplace_back(new Context());
+    int first_err = DFL_OK;
+    const int saved_prof = t_profiling;
+    t_profiling = 0;
+    g_launch_count = 0;
+    for (size_t base = 0; base < count; base += lanes) {
+        const size_t m = (count - base) < lanes ? (count - base) : lanes;
+        std::vector<int> rc(m, DFL_OK);
+        for (size_t k = 0; k < m; k++) {
+            const size_t i = base + k;
+            Context& c = *pool[k];
+            rc[k] = (!d_out[i] || (!d_in[i] && n[i])) ? DFL_E_ARG : c.init();
+            if (rc[k]) continue;
+            StageTimer tm(c.stream, false);
+            rc[k] = issue_pipeline(c, c.stream, tm, reinterpret_cast<const uint8_t*>(d_in[i]), n[i], 0, opt, wrap,
+                                   wrap_header_bytes(wrap, 0), 1, 0, reinterpret_cast<uint8_t*>(d_out[i]), out_cap[i]);
+        }
+        for (size_t k = 0; k < m; k++) {
+            const size_t i = base + k;
+            Context& c = *pool[k];
+            if (rc[k] == DFL_OK) rc[k] = finish_pipeline(c, c.stream, n[i], 0, &out_len[i]);
+            else if (c.ok) cudaStreamSynchronize(c.stream);
+            if (status) status[i] = rc[k];
+            if (rc[k] != DFL_OK && first_err == DFL_OK) first_err = rc[k];
+        }
+    }
+    t_profiling = saved_prof;
+    return first_err;
 }
 
 extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void* stream) {

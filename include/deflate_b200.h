@@ -111,6 +111,15 @@ int dfl_compress_device(const void *d_in, size_t n, const dfl_options *opt, int 
 int dfl_compress_device_piece(const void *d_in, size_t n_total, size_t dict_len, const dfl_options *opt,
                               int flush_mode, void *d_out, size_t out_cap, size_t *out_len, void *stream);
 
+/* ---- many independent streams, device buffers ----------------------------------------------
+ * `count` separate calls of deflate_bytes*_conf (lib.rs:137,182,242) with the same options, e.g. the
+ * IDAT chunks of a batch of PNGs: stream i is d_in[i][0..n[i]) -> d_out[i], size in out_len[i].
+ * Several pipelines are kept in flight on different CUDA streams so that small inputs still fill the
+ * GPU.  Blocking.  status (may be NULL) receives one code per stream; the return value is the first
+ * non-zero one.  gzip streams get the default header. */
+int dfl_compress_device_batch(size_t count, const void *const *d_in, const size_t *n, const dfl_options *opt,
+                              int wrap, void *const *d_out, const size_t *out_cap, size_t *out_len, int *status);
+
 /* Per-stage device timings of the most recent dfl_compress_device call on this thread, in
  * milliseconds (CUDA events on the launching stream): names[i] points to a static string.
  * Returns the number of stages (0 if timing was not enabled with dfl_set_profiling(1)). */

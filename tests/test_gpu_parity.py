@@ -404,3 +404,17 @@ def test_sync_flush_inside_first_window_is_valid_but_not_the_reference_quirk(dfl
         s.write(part); s.flush()
     enc.finish()
     assert bytes(sink) == s.finish()
+
+
+def test_batch_of_independent_streams(dfl, pg11):
+    """dfl_compress_device_batch (BASELINE config 4 shape): every stream equals the one-shot result."""
+    import datagen
+    import torch
+    datas = [datagen.png_idat_like(200000 + 1000 * i, 0x1DA7 + i) for i in range(20)] + [b"", b"x", pg11]
+    srcs = [torch.frombuffer(bytearray(d) if d else bytearray(1), dtype=torch.uint8).cuda()[:len(d)] for d in datas]
+    for wrap, owrap, wbits in ((dfl.ZLIB, o.ZLIB, 15), (dfl.RAW, o.RAW, -15), (dfl.GZIP, o.GZIP, 31)):
+        outs, sizes = dfl.compress_device_batch(srcs, dfl.Compression.Default, wrap)
+        for d, out, s in zip(datas, outs, sizes):
+            got = bytes(out[:s].cpu().numpy())
+            assert zlib.decompress(got, wbits) == d
+            assert got == o.compress(d, o.opts_default(), owrap), len(d)
