@@ -418,3 +418,74 @@ def test_batch_of_independent_streams(dfl, pg11):
             got = bytes(out[:s].cpu().numpy())
             assert zlib.decompress(got, wbits) == d
             assert got == o.compress(d, o.opts_default(), owrap), len(d)
+
+
+# ---------------------------------------------------------------- BASELINE.json's full sizes
+def _inflate_equals(comp: bytes, data: bytes, wbits: int) -> bool:
+    d = zlib.decompressobj(wbits)
+    pos, step = 0, 64 << 20
+    view = memoryview(comp)
+    off = 0
+    while off < len(view):
+        out = d.decompress(view[off:off + (8 << 20)])
+        off += 8 << 20
+        if out != data[pos:pos + len(out)]:
+            return False
+        pos += len(out)
+    out = d.flush()
+    return out == data[pos:pos + len(out)] and pos + len(out) == len(data) and d.eof
+
+
+def test_full_size_default_raw_roundtrip(dfl):
+    """Config 2 at its real size (1 GiB, Compression::Default, raw deflate): the stream inflates to the
+    input, its first blocks are the oracle's, and the result does not depend on the match path."""
+    import datagen
+    import torch
+    data = datagen.silesia_mix(1 << 30)
+    src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    out, n = dfl.compress_device(src, dfl.Compression.Default, dfl.RAW)
+    comp = bytes(out[:n].cpu().numpy())
+    assert _inflate_equals(comp, data, -15)
+    # every deflate block of the one-shot stream is a function of its own tokens only, so the stream of a
+    # 2 MiB prefix (minus its final block) is a prefix of the 1 GiB stream up to the last complete block
+    ref = o.compress(data[:2 << 20], o.opts_default(), o.RAW)
+    assert comp[:len(ref) * 9 // 10] == ref[:len(ref) * 9 // 10]
+    old = dfl.set_match_path("chains")
+    try:
+        out2, n2 = dfl.compress_device(src[:256 << 20], dfl.Compression.Default, dfl.RAW)
+        dfl.set_match_path("walk")
+        out3, n3 = dfl.compress_device(src[:256 << 20], dfl.Compression.Default, dfl.RAW)
+        assert n2 == n3 and torch.equal(out2[:n2], out3[:n3])
+    finally:
+        dfl._native.lib().dfl_set_match_path(old)
+
+
+def test_full_size_fast_zlib_roundtrip(dfl):
+    """Config 3 at its real size (1 GiB enwik-like, Compression::Fast, ZlibEncoder framing): zlib verifies the
+    Adler-32 computed on the device; the device checksums equal CPython's on the whole GiB."""
+    import datagen
+    import torch
+    data = datagen.enwik_like(1 << 30)
+    src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    out, n = dfl.compress_device(src, dfl.Compression.Fast, dfl.ZLIB)
+    comp = bytes(out[:n].cpu().numpy())
+    assert _inflate_equals(comp, data, 15)
+    L = dfl._native.lib()
+    a, c = ctypes.c_uint32(), ctypes.c_uint32()
+    assert L.dfl_adler32_device(ctypes.c_void_p(src.data_ptr()), len(data), ctypes.byref(a), None) == 0
+    assert L.dfl_crc32_device(ctypes.c_void_p(src.data_ptr()), len(data), ctypes.byref(c), None) == 0
+    assert a.value == zlib.adler32(data) and c.value == zlib.crc32(data)
+    assert int.from_bytes(comp[-4:], "big") == a.value
+
+
+def test_inputs_of_4_gib_are_refused_not_truncated(dfl):
+    """Positions are 32 bit inside the kernels: a single call must say so instead of wrapping around."""
+    import torch
+    L = dfl._native.lib()
+    src = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    out = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    opts = dfl.CompressionOptions.default()._c()
+    sz = ctypes.c_size_t()
+    rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), 5 << 30, ctypes.byref(opts), dfl.RAW, None, 0,
+                               ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.byref(sz), None)
+    assert rc == -7   # DFL_E_UNSUPPORTED
