@@ -829,6 +829,7 @@ k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint3
                 const uint32_t below = grp & lt_mask;
                 const uint32_t pi = below ? li0 + (31u - (uint32_t)__clz((int)below)) : (uint32_t)head[lv * kChainSlots + sg];
                 const uint32_t dl = li - pi < 255u ? li - pi : 255u;
+                __syncwarp();                             // every lane has read its head before the group leaders replace them
                 if (valid) {
                     if (lv == kTop) prev7[li & MD] = (uint8_t)dl; else prevs[lv * kChainRingS + (li & MS)] = (uint8_t)dl;
                     if ((grp >> lane) == 1u) head[lv * kChainSlots + sg] = (uint16_t)li;

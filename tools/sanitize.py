@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel of both
+match paths, all containers, pieces and batches on inputs of a few hundred KiB."""
+import os, sys, zlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import deflate_rs_b200 as dfl
+from deflate_rs_b200 import sharding
+import datagen
+
+pg = open(os.path.join(ROOT, "tests/fixtures/pg11.txt"), "rb").read()
+inputs = [pg, datagen.silesia_mix(1 << 20)[: 300000], bytes(70000), b"", b"abc", pg[:65537]]
+for path in ("walk", "chains"):
+    dfl.set_match_path(path)
+    for d in inputs:
+        for opts in (dfl.Compression.Default, dfl.Compression.Fast, dfl.CompressionOptions.high(), dfl.CompressionOptions.rle()):
+            assert zlib.decompress(dfl.deflate_bytes_conf(d, opts), -15) == d
+        assert zlib.decompress(dfl.deflate_bytes_zlib(d)) == d
+        assert zlib.decompress(dfl.deflate_bytes_gzip(d), 31) == d
+    src = torch.frombuffer(bytearray(pg), dtype=torch.uint8).cuda()
+    got = b""
+    bounds = sharding.piece_bounds(len(pg), 2, 4096)
+    for g, (lo, hi) in enumerate(bounds):
+        out, n = sharding.encode_piece_device(src, lo, hi, dfl.Compression.Default, g == 1)
+        got += bytes(out[:n].cpu().numpy())
+    assert zlib.decompress(got, -15) == pg
+    outs, sizes = dfl.compress_device_batch([src[:50000], src[50000:120001], src[:0]], dfl.Compression.Default, dfl.ZLIB)
+    assert zlib.decompress(bytes(outs[1][:sizes[1]].cpu().numpy())) == pg[50000:120001]
+    enc = dfl.write.GzEncoder(bytearray(), dfl.Compression.Default)
+    enc.write_all(pg[:40000]); enc.flush(); enc.write_all(pg[40000:90000])
+    assert zlib.decompress(bytes(enc.finish()), 31) == pg[:90000]
+print("sanitize run ok")
