@@ -709,6 +709,7 @@ k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint3
                 l_busy = false;
             }
             dq_tail += __popc(dmask);
+            __syncwarp();                                 // the queue entries are visible before a deep iteration reads them
         }
     };
 
