@@ -145,7 +145,7 @@ struct Context {
         chains = chains || b.cap_chains;
         free_buffers();
         size_t n_win = (cap + kWindow - 1) / kWindow + 1;
-        size_t n_seg = (cap + kParseSeg - 1) / kParseSeg + 1;
+        size_t n_seg = (cap + 1023) / 1024 + 1;   // the shortest parse segment (parse_geom) gives the most segments
         size_t n_blk = max_blocks_for((uint32_t)cap) + 1;
         size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
         int rc = 0;
@@ -154,7 +154,7 @@ struct Context {
         if (chains && (rc = dev_alloc(b.M, n_win * kSpanSlots))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
-        if ((rc = dev_alloc(b.segtok, n_seg * kParseTokCap))) return rc;
+        if ((rc = dev_alloc(b.segtok, parse_buffer_words(cap)))) return rc;
         if ((rc = dev_alloc(b.seg_e_pos, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_e_key, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_e_tok, n_seg))) return rc;
@@ -338,7 +338,7 @@ int finish_pipeline(Context& c, cudaStream_t st, size_t n, size_t begin, size_t*
     const DevMeta& m = *c.h_meta;
     t_counters[0] = m.n_tokens;
     t_counters[1] = m.n_blocks;
-    t_counters[2] = (n - begin + kParseSeg - 1) / kParseSeg;
+    t_counters[2] = parse_n_seg(n - begin, parse_geom(n - begin));
     t_counters[3] = m.n_repaired_par;
     t_counters[4] = m.n_repaired_seq;
     t_counters[5] = (uint64_t)g_launch_count;

@@ -345,20 +345,28 @@ DFL_HD int rle_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t out
 // (step_1/step_2, :218-278), miniz-style limiter (:290-327), then lengths handed out from the
 // highest-frequency leaf down (:402-408).  `key` scratch must hold n_freq entries.  A leaf is
 // (freq << 9) | symbol, so an ordinary sort of the keys is the reference's stable sort.
+// `presorted` >= 0: key[] already holds that many leaves in ascending order (the kernel sorts them with the
+// whole warp); < 0: collect and sort them here.
 DFL_HD void huffman_lengths(const uint32_t* freqs, uint32_t n_freq, uint32_t max_len,
-                            uint8_t* lens /*n_lens*/, uint32_t n_lens, uint32_t* key) {
+                            uint8_t* lens /*n_lens*/, uint32_t n_lens, uint32_t* key, int presorted = -1) {
     for (uint32_t i = 0; i < n_lens; i++) lens[i] = 0;
     uint32_t n = 0;
-    for (uint32_t i = 0; i < n_freq; i++)
-        if (freqs[i] > 0) key[n++] = (freqs[i] << 9) | i;
+    if (presorted >= 0) {
+        n = (uint32_t)presorted;
+    } else {
+        for (uint32_t i = 0; i < n_freq; i++)
+            if (freqs[i] > 0) key[n++] = (freqs[i] << 9) | i;
+    }
     if (n == 0) return;
     if (n == 1) { lens[key[0] & 0x1ffu] = 1; return; }
     // insertion sort on unique keys == stable sort by freq (symbols were appended in index order)
-    for (uint32_t i = 1; i < n; i++) {
-        uint32_t k = key[i];
-        uint32_t j = i;
-        while (j > 0 && key[j - 1] > k) { key[j] = key[j - 1]; j--; }
-        key[j] = k;
+    if (presorted < 0) {
+        for (uint32_t i = 1; i < n; i++) {
+            uint32_t k = key[i];
+            uint32_t j = i;
+            while (j > 0 && key[j - 1] > k) { key[j] = key[j - 1]; j--; }
+            key[j] = k;
+        }
     }
     // From here `key[i] >> 9` plays the role of leaves[i].value and `key[i] & 511` of .symbol.
 #define DFL_VAL(i) (key[(i)] >> 9)
@@ -493,8 +501,11 @@ DFL_HD uint64_t stored_length(uint64_t n) {                         // huffman_l
     return (n + 4u * k + (k - 1u)) * 8u;
 }
 
+// ll_sorted / d_sorted (optional): the non-zero (freq << 9 | symbol) leaves of the two alphabets in ascending
+// order, n_ll / n_d of them, in buffers this function may overwrite.
 DFL_HD void build_block_codes(const uint32_t* ll_freq /*286*/, const uint32_t* d_freq /*30*/,
-                              uint64_t input_bytes, BlockCodes& bc, uint32_t* scratch /*>=288*/) {
+                              uint64_t input_bytes, BlockCodes& bc, uint32_t* scratch /*>=288*/,
+                              uint32_t* ll_sorted = nullptr, int n_ll = -1, uint32_t* d_sorted = nullptr, int n_d = -1) {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     bc.input_bytes = input_bytes;
     bc.tiny = input_bytes <= 4u ? 1u : 0u;
@@ -516,8 +527,8 @@ DFL_HD void build_block_codes(const uint32_t* ll_freq /*286*/, const uint32_t* d
     uint32_t nl = kNumLL; while (nl > 257u && ll_freq[nl - 1] == 0) nl--;   // remove_trailing_zeroes
     uint32_t nd = kNumDist; while (nd > 1u && d_freq[nd - 1] == 0) nd--;
     bc.hlit = nl; bc.hdist = nd;
-    huffman_lengths(ll_freq, nl, 15, bc.ll_len, 288, scratch);
-    huffman_lengths(d_freq, nd, 15, bc.d_len, 32, scratch);
+    huffman_lengths(ll_freq, nl, 15, bc.ll_len, 288, ll_sorted ? ll_sorted : scratch, ll_sorted ? n_ll : -1);
+    huffman_lengths(d_freq, nd, 15, bc.d_len, 32, d_sorted ? d_sorted : scratch, d_sorted ? n_d : -1);
     uint32_t f19[19];
     for (int i = 0; i < 19; i++) f19[i] = 0;
     uint8_t chained[288 + 32];

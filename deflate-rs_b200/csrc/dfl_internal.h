@@ -15,9 +15,30 @@ namespace dfl {
 #ifndef DFL_PARSE_WARM
 #define DFL_PARSE_WARM 1024
 #endif
-constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread
+constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread (large inputs)
 constexpr uint32_t kParseWarm = DFL_PARSE_WARM;   // speculative warm-up before the segment start
-constexpr uint32_t kParseTokCap = kParseSeg + kParseWarm + 264;   // tokens one thread can emit
+// One parse thread walks its segment sequentially, so for small inputs the segment length *is* the
+// latency of the stage: shorter segments there (any length gives the same tokens, hand-offs are
+// verified and repaired).  seg + warm + 264 tokens of buffer per segment.
+struct ParseGeom { uint32_t seg, warm; };
+inline ParseGeom parse_geom(size_t payload) {
+    if (payload <= (32u << 20)) return {1024u, 512u};
+    if (payload <= (256u << 20)) return {2048u, 512u};
+    return {kParseSeg, kParseWarm};
+}
+inline uint32_t parse_tok_cap(ParseGeom g) { return g.seg + g.warm + 264u; }
+inline size_t parse_n_seg(size_t payload, ParseGeom g) { return (payload + g.seg - 1) / g.seg; }
+// u32 words of segment token buffers needed for a payload of at most `cap` bytes, whatever its geometry
+inline size_t parse_buffer_words(size_t cap) {
+    size_t best = 0;
+    const size_t edges[3] = {cap < (32u << 20) ? cap : (32u << 20), cap < (256u << 20) ? cap : (256u << 20), cap};
+    for (size_t e : edges) {
+        ParseGeom g = parse_geom(e);
+        size_t w = (parse_n_seg(e, g) + 1) * parse_tok_cap(g);
+        if (w > best) best = w;
+    }
+    return best;
+}
 constexpr uint32_t kRepairRounds = 3;    // parallel repair rounds before the sequential fallback
 
 // Device-resident bookkeeping of one encode call (one instance per context).
@@ -65,7 +86,7 @@ struct Buffers {   // device scratch of one context, grown on demand
     uint2* M = nullptr;             // span entries (chain path only), n_windows * kSpanSlots
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
-    uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * kParseTokCap
+    uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * parse_tok_cap
     uint32_t* seg_e_pos = nullptr;  // hand-off records (SoA), n_pseg each
     uint32_t* seg_e_key = nullptr;
     uint32_t* seg_e_tok = nullptr;

@@ -870,11 +870,12 @@ struct ParseArgs {
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
     uint32_t n_seg;
+    uint32_t seg, warm, tok_cap;   // parse_geom of this call
 };
 
 // Runs the reference's token selection from `st` until the first iteration position >= b.
 __device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
-    uint32_t* tk = A.segtok + (size_t)s * kParseTokCap;
+    uint32_t* tk = A.segtok + (size_t)s * A.tok_cap;
     uint32_t nt = 0;
     bool have_e = false;
     uint32_t epos = 0, ekey = 0, etok = 0;
@@ -901,7 +902,7 @@ __device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uin
             // rle.rs runs over the buffer from its first byte; relative to `begin` for a resumed stream
             ne = rle_step(st, n, A.in, out);
         }
-        if (nt + (uint32_t)ne <= kParseTokCap) {
+        if (nt + (uint32_t)ne <= A.tok_cap) {
             if (ne > 0) tk[nt] = out[0];
             if (ne > 1) tk[nt + 1] = out[1];
         }
@@ -915,9 +916,9 @@ __device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uin
 __global__ void __launch_bounds__(128) k_parse_spec(ParseArgs A) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n_seg) return;
-    uint32_t a = A.begin + s * kParseSeg;
-    uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
-    uint32_t start = (s == 0) ? A.begin : (a - A.begin > kParseWarm ? a - kParseWarm : A.begin);
+    uint32_t a = A.begin + s * A.seg;
+    uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
+    uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
     parse_segment(A, s, parse_state_init(start), a, b);
 }
 
@@ -942,8 +943,8 @@ __global__ void __launch_bounds__(128) k_parse_repair(ParseArgs A, const uint8_t
                                                       const uint32_t* start_key, DevMeta* meta) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n_seg || !bad[s]) return;
-    uint32_t a = A.begin + s * kParseSeg;
-    uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
+    uint32_t a = A.begin + s * A.seg;
+    uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
     parse_segment(A, s, state_from_key(start_pos[s], start_key[s]), a, b);
     atomicAdd(&meta->n_repaired_par, 1u);
 }
@@ -956,8 +957,8 @@ __global__ void k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
     for (uint32_t s = 1; s < A.n_seg; s++) {
         uint32_t xp = A.x_pos[s - 1], xk = A.x_key[s - 1];
         if (xp != A.e_pos[s] || xk != A.e_key[s]) {
-            uint32_t a = A.begin + s * kParseSeg;
-            uint32_t b = a + kParseSeg < A.n ? a + kParseSeg : A.n;
+            uint32_t a = A.begin + s * A.seg;
+            uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
             parse_segment(A, s, state_from_key(xp, xk), a, b);
             meta->n_repaired_seq++;
             __threadfence();
@@ -998,11 +999,11 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_
 __global__ void __launch_bounds__(128) k_compact(const uint32_t* __restrict__ segtok, const uint32_t* __restrict__ e_tok,
                                                  const uint32_t* __restrict__ seg_cnt,
                                                  const unsigned long long* __restrict__ seg_off, uint32_t* __restrict__ tok,
-                                                 DevMeta* meta) {
+                                                 DevMeta* meta, uint32_t tok_cap) {
     uint32_t s = blockIdx.x;
     uint32_t c = seg_cnt[s];
-    if (e_tok[s] + c > kParseTokCap) { if (threadIdx.x == 0) meta->err = 1; return; }
-    const uint32_t* src = segtok + (size_t)s * kParseTokCap + e_tok[s];
+    if (e_tok[s] + c > tok_cap) { if (threadIdx.x == 0) meta->err = 1; return; }
+    const uint32_t* src = segtok + (size_t)s * tok_cap + e_tok[s];
     uint32_t* dst = tok + seg_off[s];
     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
 }
@@ -1057,35 +1058,83 @@ __global__ void __launch_bounds__(256) k_block_stats(const uint32_t* __restrict_
 // =====================================================================================
 // k_block_codes: one thread per block builds the three Huffman codes and the cost summary
 // =====================================================================================
-__global__ void __launch_bounds__(32) k_block_codes(const DevMeta* meta, const uint32_t* __restrict__ hist,
-                                                    BlockCost* __restrict__ cost, BlockTables* __restrict__ tables) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= meta->n_blocks) return;
-    uint32_t ll[kNumLL], dd[kNumDist], scratch[288];
-    for (uint32_t i = 0; i < kNumLL; i++) ll[i] = hist[(size_t)b * kHistStride + i];
-    for (uint32_t i = 0; i < kNumDist; i++) dd[i] = hist[(size_t)b * kHistStride + kNumLL + i];
+// One deflate block per warp.  The construction itself (sort, Moffat-Katajainen, limiter, header RLE:
+// dfl_core.h build_block_codes) is a chain of short data-dependent loops and runs on lane 0, with every
+// array it touches in shared memory -- as one thread per block with the arrays in local memory the stage
+// took 2.1 ms for any input size (32 divergent lanes per warp, local-memory latency); loading the
+// histograms, copying the tables out and summing the body size are done by all 32 lanes.
+constexpr uint32_t kCodesWarps = 4;
+struct CodesScratch {
+    uint32_t ll[288];
+    uint32_t dd[32];
+    uint32_t scratch[288];
+    uint32_t key_ll[288];      // leaves (freq << 9 | symbol) in ascending order
+    uint32_t key_d[32];
     BlockCodes bc;
-    build_block_codes(ll, dd, cost[b].input_bytes, bc, scratch);
-    BlockCost c;
-    c.dynamic_cost = bc.dynamic_cost; c.static_cost = bc.static_cost; c.stored_cost = bc.stored_cost;
-    c.dynamic_bits = bc.dynamic_bits; c.fixed_bits = bc.fixed_bits; c.input_bytes = bc.input_bytes;
-    c.tiny = bc.tiny;
-    BlockTables& t = tables[b];
-    uint64_t body = 0;
-    if (!bc.tiny) {
-        for (uint32_t i = 0; i < 288; i++) { t.ll_code[i] = bc.ll_code[i]; t.ll_len[i] = bc.ll_len[i]; }
-        for (uint32_t i = 0; i < 32; i++) { t.d_code[i] = bc.d_code[i]; t.d_len[i] = bc.d_len[i]; }
-        for (uint32_t i = 0; i < 19; i++) { t.cl_code[i] = bc.cl_code[i]; t.cl_len[i] = bc.cl_len[i]; }
-        for (uint32_t i = 0; i < bc.n_hdr_sym; i++) t.hdr_sym[i] = bc.hdr_sym[i];
-        for (uint32_t i = 0; i < bc.hlit; i++) {
-            uint32_t eb = i >= 257u ? length_extra_bits_of_code(i - 257u) : 0u;
-            body += (uint64_t)ll[i] * (bc.ll_len[i] + eb);
-        }
-        for (uint32_t i = 0; i < bc.hdist; i++) body += (uint64_t)dd[i] * (bc.d_len[i] + dist_extra_bits_of_code(i));
+};
+
+// Leaves of one alphabet, sorted: every lane ranks its own leaves against all of them (keys are unique, so
+// the rank is the number of smaller keys).  freq[] has n_sym entries (a multiple of 32, zero padded).
+__device__ __forceinline__ uint32_t warp_sorted_leaves(const uint32_t* freq, uint32_t n_sym, uint32_t* tmp, uint32_t* out) {
+    const uint32_t lane = lane_id();
+    uint32_t n = 0;
+    for (uint32_t base = 0; base < n_sym; base += 32) {          // compact the non-zero ones, symbol order
+        const uint32_t f = freq[base + lane];
+        const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+        if (f != 0u) tmp[n + __popc(m & ((1u << lane) - 1u))] = (f << 9) | (base + lane);
+        n += __popc(m);
     }
-    t.n_hdr_sym = bc.n_hdr_sym; t.hlit = bc.hlit; t.hdist = bc.hdist; t.used_hclens = bc.used_hclens;
-    c.hdr_bits = bc.tiny ? 0u : (uint32_t)(bc.dynamic_bits - body);
-    cost[b] = c;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t k = tmp[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n; j++) r += tmp[j] < k ? 1u : 0u;
+        out[r] = k;
+    }
+    __syncwarp();
+    return n;
+}
+
+__global__ void __launch_bounds__(32 * kCodesWarps) k_block_codes(const DevMeta* meta, const uint32_t* __restrict__ hist,
+                                                                  BlockCost* __restrict__ cost,
+                                                                  BlockTables* __restrict__ tables) {
+    __shared__ CodesScratch sm[kCodesWarps];
+    const uint32_t b = blockIdx.x * kCodesWarps + warp_id();
+    if (b >= meta->n_blocks) return;                       // warp-uniform
+    CodesScratch& S = sm[warp_id()];
+    const uint32_t lane = lane_id();
+    for (uint32_t i = lane; i < 288; i += 32) S.ll[i] = i < kNumLL ? hist[(size_t)b * kHistStride + i] : 0u;
+    S.dd[lane] = lane < kNumDist ? hist[(size_t)b * kHistStride + kNumLL + lane] : 0u;
+    __syncwarp();
+    const uint32_t n_ll = warp_sorted_leaves(S.ll, 288, S.scratch, S.key_ll);
+    const uint32_t n_d = warp_sorted_leaves(S.dd, 32, S.scratch, S.key_d);
+    if (lane == 0) build_block_codes(S.ll, S.dd, cost[b].input_bytes, S.bc, S.scratch, S.key_ll, (int)n_ll, S.key_d, (int)n_d);
+    __syncwarp();
+    const BlockCodes& bc = S.bc;
+    BlockTables& t = tables[b];
+    unsigned long long body = 0;
+    if (!bc.tiny) {
+        for (uint32_t i = lane; i < 288; i += 32) { t.ll_code[i] = bc.ll_code[i]; t.ll_len[i] = bc.ll_len[i]; }
+        t.d_code[lane] = bc.d_code[lane]; t.d_len[lane] = bc.d_len[lane];
+        if (lane < 19) { t.cl_code[lane] = bc.cl_code[lane]; t.cl_len[lane] = bc.cl_len[lane]; }
+        for (uint32_t i = lane; i < bc.n_hdr_sym; i += 32) t.hdr_sym[i] = bc.hdr_sym[i];
+        for (uint32_t i = lane; i < bc.hlit; i += 32) {
+            uint32_t eb = i >= 257u ? length_extra_bits_of_code(i - 257u) : 0u;
+            body += (unsigned long long)S.ll[i] * (bc.ll_len[i] + eb);
+        }
+        if (lane < bc.hdist) body += (unsigned long long)S.dd[lane] * (bc.d_len[lane] + dist_extra_bits_of_code(lane));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) body += __shfl_xor_sync(0xffffffffu, body, d);
+    if (lane == 0) {
+        BlockCost c;
+        c.dynamic_cost = bc.dynamic_cost; c.static_cost = bc.static_cost; c.stored_cost = bc.stored_cost;
+        c.dynamic_bits = bc.dynamic_bits; c.fixed_bits = bc.fixed_bits; c.input_bytes = bc.input_bytes;
+        c.tiny = bc.tiny;
+        t.n_hdr_sym = bc.n_hdr_sym; t.hlit = bc.hlit; t.hdist = bc.hdist; t.used_hclens = bc.used_hclens;
+        c.hdr_bits = bc.tiny ? 0u : (uint32_t)(bc.dynamic_bits - body);
+        cost[b] = c;
+    }
 }
 
 // =====================================================================================
@@ -1514,7 +1563,9 @@ static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
-    A.n_seg = (j.n - j.begin + kParseSeg - 1) / kParseSeg;
+    const ParseGeom g = parse_geom(j.n - j.begin);
+    A.seg = g.seg; A.warm = g.warm; A.tok_cap = parse_tok_cap(g);
+    A.n_seg = (uint32_t)parse_n_seg(j.n - j.begin, g);
     return A;
 }
 
@@ -1604,11 +1655,12 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
 }
 
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st) {
-    uint32_t n_seg = (j.n - j.begin + kParseSeg - 1) / kParseSeg;
+    const ParseGeom g = parse_geom(j.n - j.begin);
+    uint32_t n_seg = (uint32_t)parse_n_seg(j.n - j.begin, g);
     k_seg_scan<<<1, 1024, 0, st>>>(n_seg, b.seg_e_tok, b.seg_x_tok, b.seg_cnt, b.seg_off, b.meta);
     DFL_LAUNCH_CHECK();
     if (n_seg > 0) {
-        k_compact<<<n_seg, 128, 0, st>>>(b.segtok, b.seg_e_tok, b.seg_cnt, b.seg_off, b.tok, b.meta);
+        k_compact<<<n_seg, 128, 0, st>>>(b.segtok, b.seg_e_tok, b.seg_cnt, b.seg_off, b.tok, b.meta, parse_tok_cap(g));
         DFL_LAUNCH_CHECK();
     }
     return cudaSuccess;
@@ -1627,7 +1679,7 @@ cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st) 
 
 cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     uint32_t mb = max_blocks_for(j.n - j.begin);
-    k_block_codes<<<(mb + 31) / 32, 32, 0, st>>>(b.meta, b.hist, b.cost, b.tables);
+    k_block_codes<<<(mb + kCodesWarps - 1) / kCodesWarps, 32 * kCodesWarps, 0, st>>>(b.meta, b.hist, b.cost, b.tables);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
