@@ -22,6 +22,7 @@ namespace {
 
 thread_local std::string t_cuda_err;
 thread_local int t_profiling = 0;
+thread_local uint32_t t_peers = 1;   // pipelines issued concurrently by the calling thread
 thread_local std::vector<std::pair<const char*, float>> t_stage_ms;
 thread_local uint64_t t_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -263,6 +264,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     j.d_tokens_override = d_tokens_override;
     j.n_tokens_override = n_tokens_override;
     j.stop_after_tokens = stop_after_tokens;
+    j.peers = t_peers;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
 
     const bool need_match_stage = (d_tokens_override == nullptr) && j.prm.mode != kRle && j.prm.checks > 0;
@@ -505,6 +507,7 @@ extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, 
     int first_err = DFL_OK;
     const int saved_prof = t_profiling;
     t_profiling = 0;
+    t_peers = (uint32_t)lanes;
     g_launch_count = 0;
     for (size_t base = 0; base < count; base += lanes) {
         const size_t m = (count - base) < lanes ? (count - base) : lanes;
@@ -528,6 +531,7 @@ extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, 
         }
     }
     t_profiling = saved_prof;
+    t_peers = 1;
     return first_err;
 }
 

@@ -133,6 +133,7 @@ struct EncodeJob {
     const uint32_t* d_tokens_override;   // test hook: skip the LZ77 stage, use these tokens
     unsigned long long n_tokens_override;
     int stop_after_tokens;   // test hook: run only the LZ77 stage
+    uint32_t peers;          // pipelines running beside this one (dfl_compress_device_batch): they fill the GPU together
 };
 
 constexpr uint32_t kAdlerChunk = 1u << 16;

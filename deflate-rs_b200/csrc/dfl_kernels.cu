@@ -456,9 +456,13 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     const uint32_t qbudget = prm.checks_quarter;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 
-    for (uint32_t i0 = (threadIdx.x & ~31u); i0 < cnt; i0 += blockDim.x) {   // warp-uniform loop
+    // gridDim.y CTAs share one window when the input is small (the stage's latency is one CTA's run through
+    // 32768 entries otherwise): each takes a contiguous, 32-aligned slice of the sorted entries
+    const uint32_t slice = ((cnt + gridDim.y - 1) / gridDim.y + 31u) & ~31u;
+    const uint32_t i_lo = blockIdx.y * slice, i_hi = i_lo + slice < cnt ? i_lo + slice : cnt;
+    for (uint32_t i0 = i_lo + (threadIdx.x & ~31u); i0 < i_hi; i0 += blockDim.x) {   // warp-uniform loop
         const uint32_t i = i0 + lane_id();
-        bool act = i < cnt;
+        bool act = i < i_hi;
         Entry me;
         me.lo = 0; me.hi = 0;
         if (act) { uint2 v = __ldg(Kw + i); me.lo = v.x; me.hi = v.y; }
@@ -1622,10 +1626,15 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
         DFL_LAUNCH_CHECK();
         return cudaSuccess;
     }
+    // enough CTAs to fill the chip even for a handful of windows
+    const uint32_t n_w = w_hi - w_lo;
+    uint32_t parts = (148u * DFL_MATCH_CTAS + n_w - 1) / n_w / (j.peers ? j.peers : 1u);
+    parts = parts > 16u ? 16u : (parts < 1u ? 1u : parts);
+    const dim3 grid(n_w, parts);
     if (j.prm.need_quarter)
-        k_match<true><<<w_hi - w_lo, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     else
-        k_match<false><<<w_hi - w_lo, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
