@@ -142,13 +142,15 @@ def _oneshot(data, options, wrap, gz_hdr=None):
     data = bytes(data)
     opts = CompressionOptions.from_(options)._c()
     L = _native.lib()
+    import numpy as np
+
     hdr = bytes(gz_hdr) if gz_hdr else None
     cap = L.dfl_bound(len(data), wrap) + (len(hdr) if hdr else 0)
-    out = ctypes.create_string_buffer(cap)
+    out = np.empty(cap, dtype=np.uint8)          # not zero-filled: the library writes every byte it reports
     n = ctypes.c_size_t()
-    _native.check(L.dfl_compress(data, len(data), ctypes.byref(opts), wrap, hdr, len(hdr) if hdr else 0, out, cap,
-                                 ctypes.byref(n)), "dfl_compress")
-    return out.raw[: n.value]
+    _native.check(L.dfl_compress(data, len(data), ctypes.byref(opts), wrap, hdr, len(hdr) if hdr else 0,
+                                 out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n)), "dfl_compress")
+    return out[: n.value].tobytes()
 
 
 def deflate_bytes_conf(input, options):
