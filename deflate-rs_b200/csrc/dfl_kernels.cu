@@ -20,6 +20,13 @@
 
 #include "dfl_internal.h"
 
+// tuning knobs (tools/tune_variants.sh)
+#ifndef DFL_WALK_UNROLL
+#define DFL_WALK_UNROLL 2
+#endif
+#define DFL_PRAGMA_(x) _Pragma(#x)
+#define DFL_PRAGMA(x) DFL_PRAGMA_(x)
+
 namespace dfl {
 
 int g_launch_count = 0;
@@ -376,14 +383,11 @@ __device__ __forceinline__ void walk_visit(Walk& wk, const SmemBytes& data, uint
     const uint32_t fb = lds_u8_if((v.y >> 17) + foff, pass);
     if (fb == wk.myfb) {                            // implies pass (fb is 0x100 otherwise; myfb is a byte, or 0x200 = stopped)
         const uint32_t sq = (v.y >> 17) + SEG;
-        uint32_t l;
-        if (wk.best_len >= kEntryBytes) {
-            l = data.common_prefix(sp, sq, kEntryBytes, maxl);
-        } else {
-            l = entry_lcp(v.x ^ me.lo, v.y ^ me.hi);
-            if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
-            l = l < maxl ? l : maxl;
-        }
+        // (with 8 or more bytes already matched the entry test above means all entry bytes agree, so entry_lcp
+        // gives 8 there too: one copy of the comparison loop serves both cases)
+        uint32_t l = entry_lcp(v.x ^ me.lo, v.y ^ me.hi);
+        if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
+        l = l < maxl ? l : maxl;
         if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
             foff += l - wk.best_len;
             wk.best_len = l;
@@ -407,7 +411,7 @@ __device__ __forceinline__ void walk_segment(Walk& wk, const SmemBytes& data, ui
     uint32_t foff = sbase + SEG + wk.best_len;
     uint32_t k = 0;
     if (!NEEDQ) {
-#pragma unroll 4
+DFL_PRAGMA(unroll DFL_WALK_UNROLL)
         for (; k < tmin; k++, ptr--) walk_visit<SEG>(wk, data, sbase, foff, __ldg(ptr), true, me, sp, maxl, stop);
     }
     for (; k < tmax; k++, ptr--) {
