@@ -45,6 +45,10 @@ CONFIGS = {
                desc="synthetic binary", opts="CompressionOptions::high() (1768 checks, lazy<128), raw deflate"),
 }
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per input byte, from the ncu --set full
+# capture at 64 MiB (profiles/r01_v4_ncu_match_walk_64MiB.txt: 956.4 MB + 484.8 MB over 67 108 864 input bytes)
+NCU_DRAM_BYTES_PER_INPUT_BYTE = {"match": (956.368640e6 + 484.794368e6) / (64 << 20)}
+
 METRIC = "encode MiB/s (uncompressed in)"
 UNIT = "MiB/s"
 SEED = 0x51DE51A
@@ -407,7 +411,10 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel": dom,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": (NCU_DRAM_BYTES_PER_INPUT_BYTE[dom] * size if dom in NCU_DRAM_BYTES_PER_INPUT_BYTE
+                                     and cfg["preset"] == "default" else None),
+                         "traffic_unit": "bytes per launch (ncu capture at 64 MiB, scaled by input size)", "kernel": dom,
                          "kernel_ms": dom_ms, "peak_source": peak_src,
                          "note": "algorithmic bytes = N read + C written over the dominant kernel's duration; the path "
                                  "is instruction/shared-memory bound (SURVEY 8(d)), not HBM bound"},
