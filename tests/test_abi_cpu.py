@@ -81,3 +81,45 @@ def test_argument_validation():
         dfl.deflate_bytes_conf(b"x", "fast")
     with pytest.raises(ValueError):
         dfl.CompressionOptions(max_hash_checks=70000)._c()
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "deflate_file")
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "deflate_file.c"), "-o", exe, "-L", lib_dir, "-ldeflate_b200",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def test_c_caller_links_against_the_header_and_fails_loudly_without_a_device(tmp_path):
+    """examples/deflate_file.c is a plain-C caller of include/deflate_b200.h: it must compile against the header
+    as shipped (no C++-isms), link with the in-tree library, and -- on a box without a GPU -- stop with the
+    library's "no CUDA device" message instead of producing output."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU variant")
+    exe = _build_c_example(tmp_path)
+    out = tmp_path / "out.z"
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "fixtures", "pg11.txt"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    assert not out.exists()
+
+
+@pytest.mark.gpu
+def test_c_caller_output_equals_the_oracle(tmp_path):
+    import subprocess
+    import zlib
+    import oracle_lib as o
+    exe = _build_c_example(tmp_path)
+    src = os.path.join(ROOT, "tests", "fixtures", "pg11.txt")
+    data = open(src, "rb").read()
+    for level, opts in (("default", o.opts_default()), ("fast", o.opts_fast())):
+        for wrap, owrap, wbits in (("raw", o.RAW, -15), ("zlib", o.ZLIB, 15), ("gzip", o.GZIP, 31)):
+            out = tmp_path / f"{level}.{wrap}"
+            subprocess.check_call([exe, src, str(out), level, wrap])
+            got = out.read_bytes()
+            assert zlib.decompress(got, wbits) == data
+            assert got == o.compress(data, opts, owrap), (level, wrap)
