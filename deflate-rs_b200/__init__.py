@@ -253,6 +253,7 @@ class _Encoder:
         buf = bytes(buf)
         consumed = ctypes.c_size_t()
         _native.check(_native.lib().dfl_encoder_write(self._h, buf, len(buf), ctypes.byref(consumed)), "dfl_encoder_write")
+        self._drain()          # whatever a piece produced goes to the sink now, as the reference's writer does
         return consumed.value
 
     def write_all(self, buf):
@@ -268,6 +269,11 @@ class _Encoder:
         self._drain()
 
     # -- encoder specific ----------------------------------------------------------------------
+    def set_piece_bytes(self, n):
+        """dfl_encoder_set_piece_bytes: how much buffered input triggers an encode without a flush (the output
+        does not depend on it)."""
+        _native.check(_native.lib().dfl_encoder_set_piece_bytes(self._h, n), "dfl_encoder_set_piece_bytes")
+
     def finish(self):
         """finish(self) -> io::Result<W> (src/writer.rs:103-108, 209-214): returns the wrapped writer."""
         self._require_open()

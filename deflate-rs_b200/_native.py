@@ -19,7 +19,7 @@ E_OVERFLOW = -5
 EXPORTS = [
     "dfl_options_preset", "dfl_strerror", "dfl_last_cuda_error", "dfl_version", "dfl_device_count", "dfl_bound",
     "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters",
-    "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_take_output",
+    "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_set_piece_bytes", "dfl_encoder_take_output",
     "dfl_encoder_advance_output", "dfl_encoder_checksum", "dfl_encoder_reset", "dfl_encoder_free",
     "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens", "dfl_set_match_path",
 ]
@@ -78,6 +78,7 @@ def lib():
     L.dfl_encoder_new.restype = ctypes.c_void_p
     L.dfl_encoder_write.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, szp]
     L.dfl_encoder_flush.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dfl_encoder_set_piece_bytes.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.dfl_encoder_take_output.argtypes = [ctypes.c_void_p, ctypes.POINTER(u8p), szp]
     L.dfl_encoder_advance_output.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.dfl_encoder_advance_output.restype = None

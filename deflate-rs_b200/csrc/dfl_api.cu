@@ -241,6 +241,18 @@ uint32_t wrap_header_bytes(int wrap, size_t gz_hdr_len) {
 // (lib.rs:251, writer.rs:341-357): no flags, MTIME 0, XFL 0, OS 255 (unknown).
 const uint8_t kGzipDefaultHeader[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
 
+// Continuation of a stream in pieces without flushes (streaming handle): what the previous piece handed over.
+struct PieceIn {
+    uint32_t init_key = 0;                 // parser state at `begin`
+    uint32_t parse_end = 0;                // 0 = to the end of the data
+    int open_piece = 0;                    // more input follows without a flush: complete blocks only
+    const uint32_t* h_carry_tok = nullptr; // tokens not coded yet (host memory)
+    uint32_t n_carry_tok = 0;
+    uint32_t carry_in_pos = 0;             // offset in d_in of their first input byte
+    uint32_t bits_n = 0, bits_v = 0;       // the incomplete last byte of the output so far
+};
+thread_local const PieceIn* t_piece_in = nullptr;   // set by the streaming handle around its pipeline call
+
 // issue_pipeline queues every stage and the read-back of the bookkeeping on `st` without waiting;
 // finish_pipeline waits for it and turns the bookkeeping into the call's result.  dfl_compress_device_batch
 // keeps several of these in flight on different streams; everything else runs them back to back.
@@ -265,6 +277,15 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     j.n_tokens_override = n_tokens_override;
     j.stop_after_tokens = stop_after_tokens;
     j.peers = t_peers;
+    const PieceIn none;
+    const PieceIn& pin = t_piece_in ? *t_piece_in : none;
+    j.init_key = pin.init_key;
+    j.parse_end = pin.parse_end ? pin.parse_end : (uint32_t)n;
+    j.open_piece = pin.open_piece;
+    j.n_carry_tok = pin.n_carry_tok;
+    j.carry_in_pos = pin.carry_in_pos;
+    j.carry_bits_n = pin.bits_n;
+    j.carry_bits_v = pin.bits_v;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
 
     const bool need_match_stage = (d_tokens_override == nullptr) && j.prm.mode != kRle && j.prm.checks > 0;
@@ -311,6 +332,8 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
         CK(launch_crc32(d_in + begin, n - begin, b, st));
         tm.mark("crc32");
     }
+    if (need_lz && j.n_carry_tok)   // the lists the token array shares its memory with are dead by now
+        CK(cudaMemcpyAsync(b.tok, pin.h_carry_tok, (size_t)j.n_carry_tok * 4, cudaMemcpyHostToDevice, st));
     if (need_lz) {
         CK(launch_parse(j, b, st));
         tm.mark("parse");
@@ -611,29 +634,44 @@ extern "C" int dfl_lz77_tokens(const uint8_t* in, size_t n, const dfl_options* o
 }
 
 // ============================================================================ streaming
+// write() buffers input on the host; the buffered bytes are encoded
+//   * when flush(Sync) / flush(Finish) is called -- a *closed* piece: everything is parsed and coded, and
+//   * on their own once `piece_bytes` have accumulated -- an *open* piece: the reference's stream has no
+//     seam there (lib.rs:408-433: the bytes do not depend on how write() chops the input), so the piece
+//     stops parsing 259 bytes before the end of what it has (every decision before that point has seen its
+//     full 258-byte look-ahead), codes only complete 31744-token blocks, and hands the parser state, the
+//     uncoded tokens and the incomplete last output byte to the next piece.
+// Either way the last 32 KiB stay as dictionary, so memory is bounded and a stream may be longer than 4 GiB.
 struct dfl_encoder {
     dfl_options opt;
     int wrap;
     Context ctx;                 // per-handle stream and device buffers
-    std::vector<uint8_t> data;   // retained dictionary (<= 32 KiB) followed by unencoded input
-    size_t pending_from = 0;     // data[pending_from..] has not been encoded yet
+    std::vector<uint8_t> data;   // retained history (dictionary, input of carried tokens) followed by unparsed input
+    size_t parse_pos = 0;        // data[parse_pos..] has not been parsed yet
+    uint32_t parse_key = 0;      // parser state at parse_pos (parse_state_key)
+    std::vector<uint32_t> carry_tok;   // parsed but not yet coded (fewer than 31744)
+    size_t carry_in = 0;         // index in data of the first carried token's input byte
+    uint32_t bits_n = 0, bits_v = 0;   // incomplete last byte of the stream so far
     std::vector<uint8_t> out;    // produced bytes not yet handed to the caller
     size_t out_pos = 0;
     bool header_written = false;
     bool finished = false;
-    uint32_t adler = 1;          // Adler-32 of everything encoded so far (device-computed per piece)
+    uint32_t adler = 1;          // Adler-32 of everything written so far (device-computed per piece)
     uint32_t crc = 0;            // CRC-32 likewise (gzip)
-    size_t adler_upto = 0;       // data[pending_from..adler_upto) is already folded into the checksum
+    size_t sum_upto = 0;         // data[..sum_upto) is already folded into the checksum
     uint64_t total_in = 0;
+    size_t piece_bytes = 256u << 20;   // unparsed bytes that trigger an open piece
     std::vector<uint8_t> gz_hdr; // gzip member header to emit (GzBuilder::into_header(), writer.rs:341-357)
 };
 
 namespace {
 
-// Adler-32 / CRC-32 of data[from..to) on the device, folded into e->adler / e->crc.
+constexpr size_t kOpenTail = kMaxMatch + 1;   // bytes an open piece leaves unparsed
+
+// Adler-32 / CRC-32 of data[sum_upto..to) on the device, folded into e->adler / e->crc.
 int encoder_fold_checksum(dfl_encoder* e, size_t to) {
-    if (e->wrap == DFL_RAW) return DFL_OK;
-    size_t from = e->adler_upto < e->pending_from ? e->pending_from : e->adler_upto;
+    if (e->wrap == DFL_RAW) { e->sum_upto = to; return DFL_OK; }
+    const size_t from = e->sum_upto;
     if (to <= from) return DFL_OK;
     Context& c = e->ctx;
     int rc = c.init();
@@ -649,36 +687,77 @@ int encoder_fold_checksum(dfl_encoder* e, size_t to) {
     // arithmetic on two device results
     if (e->wrap == DFL_ZLIB) e->adler = adler32_combine(e->adler, c.h_meta->adler, len);
     else e->crc = crc32_combine(e->crc, c.h_meta->crc, len);
-    e->adler_upto = to;
+    e->sum_upto = to;
     return DFL_OK;
 }
+
+enum { kPieceOpen = 0 };   // besides DFL_FLUSH_SYNC / DFL_FLUSH_FINISH
 
 int encoder_emit(dfl_encoder* e, int mode) {
     Context& c = e->ctx;
     int rc = c.init();
     if (rc) return rc;
     const size_t n = e->data.size();
-    const size_t begin = e->pending_from;
+    const size_t begin = e->parse_pos;
+    const bool open = (mode == kPieceOpen);
+    if (open && n < begin + kOpenTail + 1) return DFL_OK;   // not enough look-ahead to decide anything yet
     if ((rc = encoder_fold_checksum(e, n))) return rc;
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
-    size_t bound = dfl_bound(n - begin, e->wrap) + e->gz_hdr.size() + 64;
+    const size_t coded_from = (!e->carry_tok.empty() && e->carry_in < begin) ? e->carry_in : begin;
+    size_t bound = dfl_bound(n - coded_from, e->wrap) + e->gz_hdr.size() + 64;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
     if (n) CK(cudaMemcpyAsync(c.d_in, e->data.data(), n, cudaMemcpyHostToDevice, c.stream));
     uint32_t hdr = 0;
     if (!e->header_written) hdr = wrap_header_bytes(e->wrap, e->gz_hdr.size());
+    PieceIn pin;
+    pin.init_key = e->parse_key;
+    pin.parse_end = open ? (uint32_t)(n - kOpenTail) : 0u;
+    pin.open_piece = open ? 1 : 0;
+    pin.h_carry_tok = e->carry_tok.data();
+    pin.n_carry_tok = (uint32_t)e->carry_tok.size();
+    pin.carry_in_pos = (uint32_t)e->carry_in;
+    pin.bits_n = e->bits_n;
+    pin.bits_v = e->bits_v;
     size_t produced = 0;
     // The trailer is appended here from the running checksum, so the kernels see wrap == RAW
     // unless the header still has to be written.
+    t_piece_in = &pin;
     rc = run_pipeline(c, c.stream, c.d_in, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr, mode == DFL_FLUSH_FINISH ? 1 : 0,
                       mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, &produced, nullptr, 0, 0,
                       e->gz_hdr.empty() ? nullptr : e->gz_hdr.data());
+    t_piece_in = nullptr;
     if (rc) return rc;
-    size_t stream_part = (size_t)c.h_meta->stream_bytes + hdr;
-    size_t old = e->out.size();
-    e->out.resize(old + stream_part);
-    if (stream_part) CK(cudaMemcpyAsync(e->out.data() + old, c.d_out, stream_part, cudaMemcpyDeviceToHost, c.stream));
+    const DevMeta m = *c.h_meta;
+    // bytes that are complete: all of them for a closed piece, all but the last partial one for an open piece
+    const size_t full = open ? (size_t)(m.stream_bits >> 3) : (size_t)m.stream_bytes;
+    const uint32_t left_bits = open ? (uint32_t)(m.stream_bits & 7ull) : 0u;
+    const size_t fetch = hdr + full + (left_bits ? 1 : 0);
+    const size_t old = e->out.size();
+    e->out.resize(old + fetch);
+    if (fetch) CK(cudaMemcpyAsync(e->out.data() + old, c.d_out, fetch, cudaMemcpyDeviceToHost, c.stream));
+    // tokens behind the last complete block wait for the next piece
+    const size_t coded = (size_t)m.n_blocks * kBlockTokens;
+    const size_t rem = open && m.n_tokens > coded ? (size_t)(m.n_tokens - coded) : 0;
+    std::vector<uint32_t> next_carry(rem);
+    if (rem) CK(cudaMemcpyAsync(next_carry.data(), c.buf.tok + coded, rem * 4, cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
+    if (left_bits) {
+        e->bits_v = e->out.back();
+        e->out.pop_back();
+    } else {
+        e->bits_v = 0;
+    }
+    e->bits_n = left_bits;
+    e->carry_tok.swap(next_carry);
+    e->carry_in = open ? (size_t)m.in_coded_end : n;
     e->header_written = true;
+    if (open) {
+        e->parse_pos = m.end_pos;
+        e->parse_key = m.end_key;
+    } else {
+        e->parse_pos = n;
+        e->parse_key = 0;
+    }
     if (mode == DFL_FLUSH_FINISH) {
         if (e->wrap == DFL_ZLIB) {   // lib.rs:192-196 / writer.rs:235-245: Adler-32, big endian
             uint32_t a = e->adler;
@@ -691,12 +770,15 @@ int encoder_emit(dfl_encoder* e, int mode) {
         }
         e->finished = true;
     }
-    // keep the last 32 KiB as dictionary for the next piece
-    if (n > kWindow) {
-        e->data.erase(e->data.begin(), e->data.begin() + (n - kWindow));
+    // keep the dictionary of the next position to parse and the input of the carried tokens
+    size_t keep = e->parse_pos > kWindow ? e->parse_pos - kWindow : 0;
+    if (!e->carry_tok.empty() && e->carry_in < keep) keep = e->carry_in;
+    if (keep > 0) {
+        e->data.erase(e->data.begin(), e->data.begin() + keep);
+        e->parse_pos -= keep;
+        e->carry_in -= keep;
+        e->sum_upto -= keep;
     }
-    e->pending_from = e->data.size();
-    e->adler_upto = e->pending_from;
     return DFL_OK;
 }
 
@@ -715,13 +797,27 @@ extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const 
 extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, size_t* consumed) {
     if (!e || (!buf && n)) return DFL_E_ARG;
     if (e->finished) return DFL_E_STATE;
-    if (e->data.size() + n >= 0xfff00000ull) return DFL_E_UNSUPPORTED;
-    try {
-        e->data.insert(e->data.end(), buf, buf + n);
-    } catch (const std::bad_alloc&) {
-        return DFL_E_NOMEM;
+    size_t done = 0;
+    while (done < n) {
+        // take at most one piece at a time, so that neither the host buffer nor a device call grows without bound
+        const size_t pending = e->data.size() - e->parse_pos;
+        const size_t room = e->piece_bytes > pending ? e->piece_bytes - pending : 0;
+        const size_t take = (n - done) < room ? (n - done) : room;
+        if (take) {
+            try {
+                e->data.insert(e->data.end(), buf + done, buf + done + take);
+            } catch (const std::bad_alloc&) {
+                if (consumed) *consumed = done;
+                return done ? DFL_OK : DFL_E_NOMEM;
+            }
+            e->total_in += take;
+            done += take;
+        }
+        if (e->data.size() - e->parse_pos >= e->piece_bytes) {
+            int rc = encoder_emit(e, kPieceOpen);
+            if (rc) { if (consumed) *consumed = done; return rc; }
+        }
     }
-    e->total_in += n;
     if (consumed) *consumed = n;
     return DFL_OK;
 }
@@ -748,6 +844,12 @@ extern "C" void dfl_encoder_advance_output(dfl_encoder* e, size_t n) {
     }
 }
 
+extern "C" int dfl_encoder_set_piece_bytes(dfl_encoder* e, size_t bytes) {
+    if (!e || bytes < 4096 || bytes > 0x80000000ull) return DFL_E_ARG;
+    e->piece_bytes = bytes;
+    return DFL_OK;
+}
+
 extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
     if (!e || e->wrap == DFL_RAW) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
     if (encoder_fold_checksum(e, e->data.size()) != DFL_OK) return 0;
@@ -761,12 +863,16 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
         if (rc) return rc;
     }
     e->data.clear();
-    e->pending_from = 0;
+    e->parse_pos = 0;
+    e->parse_key = 0;
+    e->carry_tok.clear();
+    e->carry_in = 0;
+    e->bits_n = e->bits_v = 0;
     e->header_written = false;
     e->finished = false;
     e->adler = 1;
     e->crc = 0;
-    e->adler_upto = 0;
+    e->sum_upto = 0;
     e->total_in = 0;
     // reset() installs the default header, reset_with_builder() the caller's (writer.rs:394-406)
     e->gz_hdr.clear();

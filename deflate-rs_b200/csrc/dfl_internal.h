@@ -56,6 +56,9 @@ struct DevMeta {
     uint32_t n_stored;
     uint32_t n_fixed;
     uint32_t err;                     // nonzero = internal invariant violated on the device
+    // open pieces of a stream (streaming handle): where the parse stopped and what is left for the next piece
+    uint32_t end_pos, end_key;        // parse state at the first iteration at or after EncodeJob::parse_end
+    unsigned long long in_coded_end;  // input offset (in d_in) of the first token that was not coded
 };
 
 // Per-block cost summary (SoA-friendly, read by the bit-offset scan).
@@ -134,6 +137,14 @@ struct EncodeJob {
     unsigned long long n_tokens_override;
     int stop_after_tokens;   // test hook: run only the LZ77 stage
     uint32_t peers;          // pipelines running beside this one (dfl_compress_device_batch): they fill the GPU together
+    // ---- continuation of a stream in pieces without flushes (streaming handle; all zero for a fresh stream)
+    uint32_t init_key;       // parse state at `begin` (parse_state_key), 0 = blank
+    uint32_t parse_end;      // positions >= parse_end are left to the next piece (n for a closed piece)
+    int open_piece;          // code complete 31744-token blocks only; the rest is carried
+    uint32_t n_carry_tok;    // tokens carried in front of this piece's (already at the start of Buffers::tok)
+    uint32_t carry_in_pos;   // offset in d_in of the first carried token's input byte
+    uint32_t carry_bits_n;   // bits (0..7) of the last, incomplete byte of the previous piece ...
+    uint32_t carry_bits_v;   // ... and their value
 };
 
 constexpr uint32_t kAdlerChunk = 1u << 16;

@@ -879,6 +879,8 @@ struct ParseArgs {
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
     uint32_t n_seg;
     uint32_t seg, warm, tok_cap;   // parse_geom of this call
+    uint32_t end;                  // parse bound (EncodeJob::parse_end)
+    uint32_t init_key;             // state at `begin`
 };
 
 // Runs the reference's token selection from `st` until the first iteration position >= b.
@@ -925,9 +927,9 @@ __global__ void __launch_bounds__(128) k_parse_spec(ParseArgs A) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n_seg) return;
     uint32_t a = A.begin + s * A.seg;
-    uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
+    uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
     uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
-    parse_segment(A, s, parse_state_init(start), a, b);
+    parse_segment(A, s, (s == 0) ? state_from_key(A.begin, A.init_key) : parse_state_init(start), a, b);
 }
 
 __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* start_pos,
@@ -952,7 +954,7 @@ __global__ void __launch_bounds__(128) k_parse_repair(ParseArgs A, const uint8_t
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n_seg || !bad[s]) return;
     uint32_t a = A.begin + s * A.seg;
-    uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
+    uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
     parse_segment(A, s, state_from_key(start_pos[s], start_key[s]), a, b);
     atomicAdd(&meta->n_repaired_par, 1u);
 }
@@ -966,7 +968,7 @@ __global__ void k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
         uint32_t xp = A.x_pos[s - 1], xk = A.x_key[s - 1];
         if (xp != A.e_pos[s] || xk != A.e_key[s]) {
             uint32_t a = A.begin + s * A.seg;
-            uint32_t b = a + A.seg < A.n ? a + A.seg : A.n;
+            uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
             parse_segment(A, s, state_from_key(xp, xk), a, b);
             meta->n_repaired_seq++;
             __threadfence();
@@ -981,7 +983,9 @@ __global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; }
 // token layout: exclusive scan of per-segment token counts (single CTA), then compaction
 // =====================================================================================
 __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_t* e_tok, const uint32_t* x_tok,
-                                                   uint32_t* seg_cnt, unsigned long long* seg_off, DevMeta* meta) {
+                                                   uint32_t* seg_cnt, unsigned long long* seg_off, DevMeta* meta,
+                                                   uint32_t n_carry, int open_piece, const uint32_t* x_pos,
+                                                   const uint32_t* x_key, uint32_t begin, uint32_t init_key) {
     __shared__ unsigned long long part[1024];
     uint32_t per = (n_seg + blockDim.x - 1) / blockDim.x;
     uint32_t lo = threadIdx.x * per, hi = lo + per < n_seg ? lo + per : n_seg;
@@ -994,10 +998,13 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_
     part[threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long run = 0;
+        unsigned long long run = n_carry;            // tokens carried over from the previous piece come first
         for (uint32_t t = 0; t < blockDim.x; t++) { unsigned long long v = part[t]; part[t] = run; run += v; }
         meta->n_tokens = run;
-        meta->n_blocks = (uint32_t)(run / kBlockTokens) + 1u;
+        // an open piece codes complete blocks only; a closed one always ends with a (possibly empty) last block
+        meta->n_blocks = (uint32_t)(run / kBlockTokens) + (open_piece ? 0u : 1u);
+        meta->end_pos = n_seg ? x_pos[n_seg - 1] : begin;
+        meta->end_key = n_seg ? x_key[n_seg - 1] : init_key;
     }
     __syncthreads();
     unsigned long long run = part[threadIdx.x];
@@ -1164,7 +1171,7 @@ __device__ __forceinline__ int choose_block_dev(const BlockCost& c, uint32_t pen
 
 __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCost* __restrict__ cost, int* blk_type,
                                                     unsigned long long* blk_bit, unsigned long long* blk_in,
-                                                    int sync_marker, uint32_t in_begin) {
+                                                    int sync_marker, uint32_t in_begin, uint32_t carry_bits_n) {
     __shared__ unsigned long long tot[256 * 8];   // bits consumed by a thread's run per entry alignment
     __shared__ unsigned long long inb[256];
     __shared__ unsigned long long entry_bit[256];
@@ -1191,7 +1198,8 @@ __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCo
     inb[threadIdx.x] = ib;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long bit = 0, in_off = in_begin;
+        // a piece that continues a stream starts inside the byte the previous piece left incomplete
+        unsigned long long bit = carry_bits_n, in_off = in_begin;
         for (uint32_t t = 0; t < blockDim.x; t++) {
             entry_bit[t] = bit;
             bit += tot[t * 8 + (bit & 7ull)];
@@ -1199,6 +1207,7 @@ __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCo
             inb[t] = in_off;
             in_off += v;
         }
+        meta->in_coded_end = in_off;
         if (sync_marker) {            // compress.rs:258-261: empty stored block 00 00 FF FF, byte aligned
             bit += 3ull;
             bit = (bit + 7ull) & ~7ull;
@@ -1534,10 +1543,11 @@ __global__ void __launch_bounds__(1024) k_crc32_combine(const unsigned long long
 // k_finalize: sync marker bytes, container header and trailer (zlib.rs:59-62, lib.rs:192-196)
 // =====================================================================================
 __global__ void k_finalize(DevMeta* meta, uint8_t* out, unsigned long long out_cap, uint32_t hdr_bytes, int wrap,
-                           int sync_marker, int write_trailer, uint32_t isize) {
+                           int sync_marker, int write_trailer, uint32_t isize, uint32_t carry_bits_n, uint32_t carry_bits_v) {
     unsigned long long end = hdr_bytes + meta->stream_bytes;
     const unsigned long long trailer = write_trailer ? (wrap == 1 ? 4ull : (wrap == 2 ? 8ull : 0ull)) : 0ull;
     if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = end + trailer; return; }
+    if (carry_bits_n) out[hdr_bytes] |= (uint8_t)carry_bits_v;   // the bits the previous piece left in its last byte
     if (sync_marker && end >= 4 && end <= out_cap) {
         out[end - 2] = 0xff;
         out[end - 1] = 0xff;
@@ -1573,7 +1583,8 @@ static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin);
     A.seg = g.seg; A.warm = g.warm; A.tok_cap = parse_tok_cap(g);
-    A.n_seg = (uint32_t)parse_n_seg(j.n - j.begin, g);
+    A.end = j.parse_end; A.init_key = j.init_key;
+    A.n_seg = j.parse_end > j.begin ? (uint32_t)parse_n_seg(j.parse_end - j.begin, g) : 0u;
     return A;
 }
 
@@ -1669,8 +1680,9 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
 
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     const ParseGeom g = parse_geom(j.n - j.begin);
-    uint32_t n_seg = (uint32_t)parse_n_seg(j.n - j.begin, g);
-    k_seg_scan<<<1, 1024, 0, st>>>(n_seg, b.seg_e_tok, b.seg_x_tok, b.seg_cnt, b.seg_off, b.meta);
+    uint32_t n_seg = j.parse_end > j.begin ? (uint32_t)parse_n_seg(j.parse_end - j.begin, g) : 0u;
+    k_seg_scan<<<1, 1024, 0, st>>>(n_seg, b.seg_e_tok, b.seg_x_tok, b.seg_cnt, b.seg_off, b.meta, j.n_carry_tok, j.open_piece,
+                                   b.seg_x_pos, b.seg_x_key, j.begin, j.init_key);
     DFL_LAUNCH_CHECK();
     if (n_seg > 0) {
         k_compact<<<n_seg, 128, 0, st>>>(b.segtok, b.seg_e_tok, b.seg_cnt, b.seg_off, b.tok, b.meta, parse_tok_cap(g));
@@ -1685,20 +1697,21 @@ cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st) 
         k_set_tokens<<<1, 1, 0, st>>>(b.meta, j.n_tokens_override);
         DFL_LAUNCH_CHECK();
     }
-    k_block_stats<<<max_blocks_for(j.n - j.begin), 256, 0, st>>>(tok, b.meta, b.hist, b.cost);
+    k_block_stats<<<max_blocks_for(j.n - j.begin + j.n_carry_tok), 256, 0, st>>>(tok, b.meta, b.hist, b.cost);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
 cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st) {
-    uint32_t mb = max_blocks_for(j.n - j.begin);
+    uint32_t mb = max_blocks_for(j.n - j.begin + j.n_carry_tok);
     k_block_codes<<<(mb + kCodesWarps - 1) / kCodesWarps, 32 * kCodesWarps, 0, st>>>(b.meta, b.hist, b.cost, b.tables);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
 cudaError_t launch_block_scan(const EncodeJob& j, Buffers& b, cudaStream_t st) {
-    k_block_scan<<<1, 256, 0, st>>>(b.meta, b.cost, b.blk_type, b.blk_bit, b.blk_in, j.sync_marker, j.begin);
+    k_block_scan<<<1, 256, 0, st>>>(b.meta, b.cost, b.blk_type, b.blk_bit, b.blk_in, j.sync_marker,
+                                    j.n_carry_tok ? j.carry_in_pos : j.begin, j.carry_bits_n);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1707,7 +1720,7 @@ cudaError_t launch_pack(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     const uint32_t* tok = j.d_tokens_override ? j.d_tokens_override : b.tok;
     k_zero_out<<<148 * 8, 256, 0, st>>>(b.meta, reinterpret_cast<uint4*>(j.d_out), (unsigned long long)j.out_cap, j.hdr_bytes);
     DFL_LAUNCH_CHECK();
-    k_pack<<<max_blocks_for(j.n - j.begin), kPackThreads, 0, st>>>(j.d_in, tok, b.meta, b.cost, b.tables, b.blk_type, b.blk_bit,
+    k_pack<<<max_blocks_for(j.n - j.begin + j.n_carry_tok), kPackThreads, 0, st>>>(j.d_in, tok, b.meta, b.cost, b.tables, b.blk_type, b.blk_bit,
                                                                     b.blk_in, reinterpret_cast<uint32_t*>(j.d_out),
                                                                     (unsigned long long)j.hdr_bytes * 8ull, j.final_block,
                                                                     (unsigned long long)j.out_cap);
@@ -1739,7 +1752,7 @@ cudaError_t launch_crc32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t
 
 cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st) {
     k_finalize<<<1, 1, 0, st>>>(b.meta, j.d_out, (unsigned long long)j.out_cap, j.hdr_bytes, wrap, j.sync_marker,
-                                j.final_block, j.isize);
+                                j.final_block, j.isize, j.carry_bits_n, j.carry_bits_v);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -144,6 +144,11 @@ int dfl_encoder_write(dfl_encoder *e, const uint8_t *buf, size_t n, size_t *cons
 /* Write::flush = DFL_FLUSH_SYNC (writer.rs:134-136); finish()/Drop = DFL_FLUSH_FINISH
  * (writer.rs:103-108,139-152).  After FINISH the trailer is part of the output. */
 int dfl_encoder_flush(dfl_encoder *e, int mode);
+/* Buffered input is encoded at every flush and, on its own, whenever `bytes` of it have accumulated
+ * (default 256 MiB; 4096 <= bytes <= 2 GiB), so memory stays bounded and a stream can be longer than
+ * 4 GiB.  The output does not depend on this value: without a flush the reference's stream has no seam
+ * (lib.rs:408-433), and neither has this one. */
+int dfl_encoder_set_piece_bytes(dfl_encoder *e, size_t bytes);
 int dfl_encoder_take_output(dfl_encoder *e, const uint8_t **p, size_t *len);
 void dfl_encoder_advance_output(dfl_encoder *e, size_t n);
 /* ZlibEncoder::checksum (writer.rs:248) / GzEncoder::checksum (writer.rs:429): checksum of the

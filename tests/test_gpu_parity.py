@@ -489,3 +489,76 @@ def test_inputs_of_4_gib_are_refused_not_truncated(dfl):
     rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), 5 << 30, ctypes.byref(opts), dfl.RAW, None, 0,
                                ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.byref(sz), None)
     assert rc == -7   # DFL_E_UNSUPPORTED
+
+
+def test_writer_pieces_without_flush_equal_oneshot(dfl, pg11):
+    """The streaming handle encodes buffered input by itself once enough has accumulated (open pieces: parser
+    state, uncoded tokens and the incomplete output byte are carried over).  Without a flush the reference's
+    stream has no seam (lib.rs:408-433), so whatever the piece size, the bytes must equal the one-shot result."""
+    import datagen
+    mix = datagen.silesia_mix(3 << 20)
+    cases = [(pg11, dfl.Compression.Default, o.opts_default()), (pg11, dfl.Compression.Fast, o.opts_fast()),
+             (mix, dfl.Compression.Default, o.opts_default()), (pg11, dfl.CompressionOptions.rle(), o.PRESETS["rle"]()),
+             (pg11, dfl.CompressionOptions.huffman_only(), o.PRESETS["huffman_only"]()),
+             (bytes(300000), dfl.Compression.Default, o.opts_default()),
+             (pg11[:100000], dfl.CompressionOptions.high(), o.PRESETS["high"]())]
+    for data, opts, oopts in cases:
+        for cls, owrap in ((dfl.write.DeflateEncoder, o.RAW), (dfl.write.ZlibEncoder, o.ZLIB), (dfl.write.GzEncoder, o.GZIP)):
+            want = o.compress(data, oopts, owrap)
+            for piece, chunk in ((4096, 1000), (20000, 7777), (65536, 65536), (100000, 250000), (1 << 20, 300000)):
+                sink = bytearray()
+                enc = cls(sink, opts)
+                enc.set_piece_bytes(piece)
+                for i in range(0, len(data), chunk):
+                    enc.write_all(data[i:i + chunk])
+                enc.finish()
+                assert bytes(sink) == want, (len(data), cls.__name__, piece, chunk, len(sink), len(want))
+
+
+def test_writer_pieces_with_flushes_equal_the_reference_writer(dfl, pg11):
+    """Open pieces and explicit sync flushes mixed (all flushes beyond the first window, see the divergence test)."""
+    s = o.Stream(o.opts_default(), o.ZLIB)
+    sink = bytearray()
+    enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Default)
+    enc.set_piece_bytes(8192)
+    for lo, hi, fl in ((0, 50000, True), (50000, 50010, False), (50010, 120000, True), (120000, len(pg11), False)):
+        s.write(pg11[lo:hi]); enc.write_all(pg11[lo:hi])
+        if fl:
+            s.flush(); enc.flush()
+    enc.finish()
+    assert bytes(sink) == s.finish()
+
+
+def test_writer_stream_longer_than_4_gib(dfl, pg11):
+    """A single stream of 4.5 GiB through write::ZlibEncoder: pieces are encoded as the input arrives (positions are
+    32 bit per piece only), the host buffer stays bounded, zlib inflates the result to the input and accepts the
+    Adler-32 folded over all pieces."""
+    block = (pg11 * 7)[: 1 << 20]
+    total_blocks = 4608                      # 4.5 GiB
+    class Sink:
+        def __init__(self):
+            self.d = zlib.decompressobj(15)
+            self.pos = 0
+            self.ok = True
+            self.n_in = 0
+        def write(self, b):
+            self.n_in += len(b)
+            out = self.d.decompress(bytes(b))
+            # the input is periodic with period len(block): compare against the right rotation
+            off = self.pos % len(block)
+            k = 0
+            while k < len(out):
+                take = min(len(out) - k, len(block) - off)
+                if out[k:k + take] != block[off:off + take]:
+                    self.ok = False
+                k += take
+                off = 0
+            self.pos += len(out)
+            return len(b)
+    sink = Sink()
+    enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Fast)
+    for _ in range(total_blocks):
+        enc.write_all(block)
+    enc.finish()
+    assert sink.ok and sink.pos == total_blocks * len(block) and sink.d.eof
+    assert sink.n_in < sink.pos // 2
