@@ -471,11 +471,40 @@ extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options
                         0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len, nullptr, 0, 0, gz_hdr);
 }
 
+// Inputs too long for one pipeline run (32-bit positions) take the streaming handle's route: the same bytes, in
+// bounded pieces.  DFL_ONESHOT_PIECE_LIMIT lowers the switch-over point (test hook).
+static size_t oneshot_piece_limit() {
+    static const size_t v = [] {
+        const char* e = getenv("DFL_ONESHOT_PIECE_LIMIT");
+        size_t x = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        return x ? x : ((size_t)3 << 30);
+    }();
+    return v;
+}
+
 extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
                             size_t gz_hdr_len, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!opt || !out || !out_len || (!in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
     if (wrap != DFL_GZIP || !gz_hdr || gz_hdr_len == 0) { gz_hdr = nullptr; gz_hdr_len = 0; }
     if (gz_hdr_len > 0xffffu) return DFL_E_ARG;
+    if (n >= oneshot_piece_limit()) {
+        dfl_encoder* e = dfl_encoder_new(opt, wrap, gz_hdr, gz_hdr_len);
+        if (!e) return DFL_E_NOMEM;
+        const size_t lim = oneshot_piece_limit();
+        if (lim < ((size_t)1 << 28)) dfl_encoder_set_piece_bytes(e, lim < 4096 ? 4096 : lim);
+        int rc = dfl_encoder_write(e, in, n, nullptr);
+        if (rc == DFL_OK) rc = dfl_encoder_flush(e, DFL_FLUSH_FINISH);
+        if (rc == DFL_OK) {
+            const uint8_t* p = nullptr;
+            size_t len = 0;
+            dfl_encoder_take_output(e, &p, &len);
+            *out_len = len;
+            if (len > out_cap) rc = DFL_E_OVERFLOW;
+            else memcpy(out, p, len);
+        }
+        dfl_encoder_free(e);
+        return rc;
+    }
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;

@@ -562,3 +562,24 @@ def test_writer_stream_longer_than_4_gib(dfl, pg11):
     enc.finish()
     assert sink.ok and sink.pos == total_blocks * len(block) and sink.d.eof
     assert sink.n_in < sink.pos // 2
+
+
+def test_oneshot_beyond_the_position_limit_goes_through_pieces(pg11):
+    """dfl_compress routes inputs too long for one pipeline run through the streaming handle's pieces; with the
+    switch-over point lowered (DFL_ONESHOT_PIECE_LIMIT) the same code path runs on small inputs, in a fresh
+    process, and must give the ordinary bytes."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, zlib; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import deflate_rs_b200 as d, oracle_lib as o\n"
+        "data = open(%r, 'rb').read()\n"
+        "for f, w in ((d.deflate_bytes, o.RAW), (d.deflate_bytes_zlib, o.ZLIB), (d.deflate_bytes_gzip, o.GZIP)):\n"
+        "    assert f(data) == o.compress(data, o.opts_default(), w)\n"
+        "assert d.deflate_bytes(b'abc') == o.compress(b'abc', o.opts_default(), o.RAW)\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+         os.path.join(FIXTURES, "pg11.txt"))
+    env = dict(os.environ, DFL_ONESHOT_PIECE_LIMIT="20000")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
