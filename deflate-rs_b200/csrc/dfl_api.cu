@@ -458,19 +458,6 @@ extern "C" int dfl_last_counters(uint64_t* out, int cap) {
 }
 
 // ============================================================================ one-shot
-extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
-                                   size_t gz_hdr_len, void* d_out, size_t out_cap, size_t* out_len, void* stream) {
-    if (!opt || !d_out || !out_len || (!d_in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
-    if (wrap != DFL_GZIP || !gz_hdr || gz_hdr_len == 0) { gz_hdr = nullptr; gz_hdr_len = 0; }
-    if (gz_hdr_len > 0xffffu) return DFL_E_ARG;
-    Context& c = tls_context();
-    int rc = c.init();
-    if (rc) return rc;
-    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
-    return run_pipeline(c, st, reinterpret_cast<const uint8_t*>(d_in), n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1,
-                        0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len, nullptr, 0, 0, gz_hdr);
-}
-
 // Inputs too long for one pipeline run (32-bit positions) take the streaming handle's route: the same bytes, in
 // bounded pieces.  DFL_ONESHOT_PIECE_LIMIT lowers the switch-over point (test hook).
 static size_t oneshot_piece_limit() {
@@ -480,6 +467,115 @@ static size_t oneshot_piece_limit() {
         return x ? x : ((size_t)3 << 30);
     }();
     return v;
+}
+
+
+// A device buffer too long for one pipeline run, encoded as open pieces straight from device memory (the
+// streaming handle's scheme without the host buffer): every piece sees the 32 KiB in front of it and the input
+// of the tokens it inherits, writes into the context's scratch output, and its complete bytes are appended to
+// the caller's buffer device-to-device.
+static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, const dfl_options* opt, int wrap,
+                                  const uint8_t* gz_hdr, size_t gz_hdr_len, uint8_t* d_out, size_t out_cap, size_t* out_len) {
+    const size_t piece = oneshot_piece_limit() < ((size_t)1 << 30) ? oneshot_piece_limit() : ((size_t)1 << 30);
+    size_t parse_pos = 0, carry_in = 0, out_off = 0, sum_upto = 0;
+    uint32_t parse_key = 0, bits_n = 0, bits_v = 0, adler = 1, crc = 0;
+    std::vector<uint32_t> carry_tok;
+    bool header_written = false;
+    int rc = DFL_OK;
+    for (;;) {
+        const size_t piece_end = (n - parse_pos) > piece ? parse_pos + piece : n;
+        const bool last = piece_end == n;
+        size_t base = parse_pos > kWindow ? parse_pos - kWindow : 0;
+        if (!carry_tok.empty() && carry_in < base) base = carry_in;
+        base &= ~(size_t)15;
+        const size_t n_piece = piece_end - base;
+        const uint32_t hdr = header_written ? 0u : wrap_header_bytes(wrap, gz_hdr_len);
+        const size_t bound = dfl_bound(n_piece, wrap) + gz_hdr_len + 64;
+        if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
+        PieceIn pin;
+        pin.init_key = parse_key;
+        pin.open_piece = last ? 0 : 1;
+        pin.parse_end = last ? 0u : (uint32_t)(n_piece - (kMaxMatch + 1));
+        pin.h_carry_tok = carry_tok.data();
+        pin.n_carry_tok = (uint32_t)carry_tok.size();
+        pin.carry_in_pos = (uint32_t)(carry_in - base);
+        pin.bits_n = bits_n;
+        pin.bits_v = bits_v;
+        size_t produced = 0;
+        t_piece_in = &pin;
+        rc = run_pipeline(c, st, d_in + base, n_piece, parse_pos - base, opt, hdr ? wrap : DFL_RAW, hdr, last ? 1 : 0, 0,
+                          c.d_out, c.d_out_cap, &produced, nullptr, 0, 0, gz_hdr);
+        t_piece_in = nullptr;
+        if (rc) return rc;
+        const DevMeta m = *c.h_meta;
+        // the container checksum is folded piece by piece (the scratch is sized for one piece) and written below
+        if (wrap != DFL_RAW && piece_end > sum_upto) {
+            const size_t len = piece_end - sum_upto;
+            if (wrap == DFL_ZLIB) CK(launch_adler32(d_in + sum_upto, len, c.buf, st));
+            else CK(launch_crc32(d_in + sum_upto, len, c.buf, st));
+            CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (wrap == DFL_ZLIB) adler = adler32_combine(adler, c.h_meta->adler, len);
+            else crc = crc32_combine(crc, c.h_meta->crc, len);
+            sum_upto = piece_end;
+        }
+        const size_t full = last ? (size_t)m.stream_bytes : (size_t)(m.stream_bits >> 3);
+        const uint32_t left_bits = last ? 0u : (uint32_t)(m.stream_bits & 7ull);
+        if (out_off + hdr + full + 16 > out_cap) { *out_len = out_off + hdr + full + 16; return DFL_E_OVERFLOW; }
+        if (hdr + full) CK(cudaMemcpyAsync(d_out + out_off, c.d_out, hdr + full, cudaMemcpyDeviceToDevice, st));
+        uint8_t last_byte = 0;
+        if (left_bits) CK(cudaMemcpyAsync(&last_byte, c.d_out + hdr + full, 1, cudaMemcpyDeviceToHost, st));
+        const size_t coded = (size_t)m.n_blocks * kBlockTokens;
+        const size_t rem = !last && m.n_tokens > coded ? (size_t)(m.n_tokens - coded) : 0;
+        std::vector<uint32_t> next_carry(rem);
+        if (rem) CK(cudaMemcpyAsync(next_carry.data(), c.buf.tok + coded, rem * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out_off += hdr + full;
+        header_written = true;
+        bits_n = left_bits;
+        bits_v = left_bits ? last_byte : 0u;
+        carry_tok.swap(next_carry);
+        if (last) break;
+        carry_in = base + (size_t)m.in_coded_end;
+        parse_pos = base + m.end_pos;
+        parse_key = m.end_key;
+    }
+    uint8_t tr[8];
+    size_t tr_len = 0;
+    if (wrap == DFL_ZLIB) {            // lib.rs:192-196
+        for (int k = 0; k < 4; k++) tr[k] = (uint8_t)(adler >> (24 - 8 * k));
+        tr_len = 4;
+    } else if (wrap == DFL_GZIP) {     // lib.rs:260-265
+        const uint32_t isize = (uint32_t)(n & 0xffffffffull);
+        for (int k = 0; k < 4; k++) { tr[k] = (uint8_t)(crc >> (8 * k)); tr[4 + k] = (uint8_t)(isize >> (8 * k)); }
+        tr_len = 8;
+    }
+    if (tr_len) {
+        if (out_off + tr_len > out_cap) { *out_len = out_off + tr_len; return DFL_E_OVERFLOW; }
+        CK(cudaMemcpyAsync(d_out + out_off, tr, tr_len, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        out_off += tr_len;
+    }
+    *out_len = out_off;
+    return DFL_OK;
+}
+
+extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,
+                                   size_t gz_hdr_len, void* d_out, size_t out_cap, size_t* out_len, void* stream) {
+    if (!opt || !d_out || !out_len || (!d_in && n) || !valid_wrap(wrap)) return DFL_E_ARG;
+    if (wrap != DFL_GZIP || !gz_hdr || gz_hdr_len == 0) { gz_hdr = nullptr; gz_hdr_len = 0; }
+    if (gz_hdr_len > 0xffffu) return DFL_E_ARG;
+    Context& c = tls_context();
+    int rc = c.init();
+    if (rc) return rc;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
+    if (n >= oneshot_piece_limit()) {
+        if (opt->special != 0 || (reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return opt->special ? DFL_E_UNSUPPORTED : DFL_E_ARG;
+        return compress_device_pieces(c, st, reinterpret_cast<const uint8_t*>(d_in), n, opt, wrap, gz_hdr, gz_hdr_len,
+                                      reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+    }
+    return run_pipeline(c, st, reinterpret_cast<const uint8_t*>(d_in), n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1,
+                        0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len, nullptr, 0, 0, gz_hdr);
 }
 
 extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt, int wrap, const uint8_t* gz_hdr,

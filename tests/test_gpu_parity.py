@@ -478,16 +478,17 @@ def test_full_size_fast_zlib_roundtrip(dfl):
     assert int.from_bytes(comp[-4:], "big") == a.value
 
 
-def test_inputs_of_4_gib_are_refused_not_truncated(dfl):
-    """Positions are 32 bit inside the kernels: a single call must say so instead of wrapping around."""
+def test_single_pipeline_runs_of_4_gib_are_refused_not_truncated(dfl):
+    """Positions are 32 bit inside one pipeline run.  dfl_compress / dfl_compress_device split longer inputs into
+    pieces themselves; the entry points that are one run by definition must refuse instead of wrapping around."""
     import torch
     L = dfl._native.lib()
     src = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
     out = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
     opts = dfl.CompressionOptions.default()._c()
     sz = ctypes.c_size_t()
-    rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), 5 << 30, ctypes.byref(opts), dfl.RAW, None, 0,
-                               ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.byref(sz), None)
+    rc = L.dfl_compress_device_piece(ctypes.c_void_p(src.data_ptr()), 5 << 30, 0, ctypes.byref(opts), 2,
+                                     ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.byref(sz), None)
     assert rc == -7   # DFL_E_UNSUPPORTED
 
 
@@ -577,9 +578,45 @@ def test_oneshot_beyond_the_position_limit_goes_through_pieces(pg11):
         "for f, w in ((d.deflate_bytes, o.RAW), (d.deflate_bytes_zlib, o.ZLIB), (d.deflate_bytes_gzip, o.GZIP)):\n"
         "    assert f(data) == o.compress(data, o.opts_default(), w)\n"
         "assert d.deflate_bytes(b'abc') == o.compress(b'abc', o.opts_default(), o.RAW)\n"
+        "import torch, datagen\n"
+        "for blob in (data, datagen.silesia_mix(3 << 20), bytes(100000)):\n"
+        "    src = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()\n"
+        "    for w, ow in ((d.RAW, o.RAW), (d.ZLIB, o.ZLIB), (d.GZIP, o.GZIP)):\n"
+        "        for opts, oo in ((d.Compression.Default, o.opts_default()), (d.Compression.Fast, o.opts_fast())):\n"
+        "            out, n = d.compress_device(src, opts, w)\n"
+        "            assert bytes(out[:n].cpu().numpy()) == o.compress(blob, oo, ow), (len(blob), w)\n"
         "print('ok')\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
          os.path.join(FIXTURES, "pg11.txt"))
     env = dict(os.environ, DFL_ONESHOT_PIECE_LIMIT="20000")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_device_call_longer_than_4_gib(dfl, pg11):
+    """dfl_compress_device on a 4.5 GiB device buffer: encoded as 1 GiB open pieces straight from HBM, one gzip
+    member out; zlib inflates it to the input and accepts CRC-32 and ISIZE (= length mod 2^32)."""
+    import torch
+    block = (pg11 * 7)[: 1 << 20]
+    total_blocks = 4608
+    src = torch.frombuffer(bytearray(block), dtype=torch.uint8).cuda().repeat(total_blocks)
+    assert src.numel() == total_blocks << 20
+    out, n = dfl.compress_device(src, dfl.Compression.Fast, dfl.GZIP)
+    comp = out[:n].cpu().numpy().tobytes()
+    del src, out
+    d = zlib.decompressobj(31)
+    pos = 0
+    ok = True
+    view = memoryview(comp)
+    for off in range(0, len(view), 4 << 20):
+        got = d.decompress(view[off:off + (4 << 20)])
+        k = 0
+        o0 = pos % len(block)
+        while k < len(got):
+            take = min(len(got) - k, len(block) - o0)
+            ok = ok and got[k:k + take] == block[o0:o0 + take]
+            k += take
+            o0 = 0
+        pos += len(got)
+    assert ok and pos == total_blocks << 20 and d.eof
+    assert int.from_bytes(comp[-4:], "little") == (total_blocks << 20) & 0xFFFFFFFF
