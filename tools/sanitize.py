@@ -30,4 +30,12 @@ for path in ("walk", "chains"):
     enc = dfl.write.GzEncoder(bytearray(), dfl.Compression.Default)
     enc.write_all(pg[:40000]); enc.flush(); enc.write_all(pg[40000:90000])
     assert zlib.decompress(bytes(enc.finish()), 31) == pg[:90000]
+    # open pieces (no flush): parser state, uncoded tokens and the partial byte are carried over
+    enc = dfl.write.ZlibEncoder(bytearray(), dfl.Compression.Default)
+    enc.set_piece_bytes(30000)
+    for i in range(0, len(pg), 11111):
+        enc.write_all(pg[i:i + 11111])
+    assert zlib.decompress(bytes(enc.finish())) == pg
+    # with DFL_ONESHOT_PIECE_LIMIT set, the one-shot calls above already ran as pieces; say which it was
+print("oneshot piece limit:", os.environ.get("DFL_ONESHOT_PIECE_LIMIT", "default"))
 print("sanitize run ok")
