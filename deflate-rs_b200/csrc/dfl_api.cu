@@ -90,6 +90,10 @@ struct Context {
     size_t d_in_cap = 0;
     uint8_t* d_out = nullptr;
     size_t d_out_cap = 0;
+    uint8_t* d_out2 = nullptr;      // second output scratch (pieces alternate, so one can be copied out while the other fills)
+    size_t d_out2_cap = 0;
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t d2h_ev[2] = {nullptr, nullptr};
     uint32_t* d_tok_in = nullptr;   // staging for dfl_encode_tokens
     size_t d_tok_cap = 0;
     DevMeta* h_meta = nullptr;  // pinned
@@ -103,6 +107,8 @@ struct Context {
         }
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+        for (auto& e : d2h_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMallocHost(reinterpret_cast<void**>(&h_meta), sizeof(DevMeta)));
         int rc = dev_alloc(buf.meta, 1);
         if (rc) return rc;
@@ -129,6 +135,9 @@ struct Context {
         dev_free(d_in); dev_free(d_out); dev_free(d_tok_in);
         if (h_meta) cudaFreeHost(h_meta);
         for (auto e : copy_ev) cudaEventDestroy(e);
+        for (auto e : d2h_ev) if (e) cudaEventDestroy(e);
+        if (d2h_stream) cudaStreamDestroy(d2h_stream);
+        dev_free(d_out2);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -470,20 +479,37 @@ static size_t oneshot_piece_limit() {
 }
 
 
-// A device buffer too long for one pipeline run, encoded as open pieces straight from device memory (the
-// streaming handle's scheme without the host buffer): every piece sees the 32 KiB in front of it and the input
-// of the tokens it inherits, writes into the context's scratch output, and its complete bytes are appended to
-// the caller's buffer device-to-device.
-static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, const dfl_options* opt, int wrap,
-                                  const uint8_t* gz_hdr, size_t gz_hdr_len, uint8_t* d_out, size_t out_cap, size_t* out_len) {
-    const size_t piece = oneshot_piece_limit() < ((size_t)1 << 30) ? oneshot_piece_limit() : ((size_t)1 << 30);
-    size_t parse_pos = 0, carry_in = 0, out_off = 0, sum_upto = 0;
+// One stream encoded as open pieces straight from a device buffer (the streaming handle's scheme without the
+// host copy of the input): every piece sees the 32 KiB in front of it and the input of the tokens it inherits,
+// and writes into one of two scratch outputs; its complete bytes then go to the caller's buffer -- device to
+// device, or to host memory on a separate stream while the next piece is already running.  Used for device
+// buffers too long for one pipeline run and for large host calls (where it overlaps both copy directions with
+// the kernels: the input keeps arriving in slices on the copy stream).
+struct PieceIO {
+    size_t piece = (size_t)1 << 30;         // bytes parsed per piece
+    const InputArrival* arrival = nullptr;  // the device buffer is still being filled from the host
+    uint8_t* d_out = nullptr;               // device sink ...
+    uint8_t* h_out = nullptr;               // ... or host sink
+    size_t out_cap = 0;
+};
+
+static int compress_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, size_t n, const dfl_options* opt, int wrap,
+                           const uint8_t* gz_hdr, size_t gz_hdr_len, const PieceIO& io, size_t* out_len) {
+    size_t parse_pos = 0, carry_in = 0, out_off = 0, sum_upto = 0, fed = 0;
     uint32_t parse_key = 0, bits_n = 0, bits_v = 0, adler = 1, crc = 0;
     std::vector<uint32_t> carry_tok;
     bool header_written = false;
+    bool d2h_pending[2] = {false, false};
     int rc = DFL_OK;
-    for (;;) {
-        const size_t piece_end = (n - parse_pos) > piece ? parse_pos + piece : n;
+    const int saved_prof = t_profiling;
+    auto feed_to = [&](size_t upto) -> int {   // issue the host-to-device slices covering [0, upto)
+        if (!io.arrival) return DFL_OK;
+        const size_t want = (upto + kCopySlice - 1) / kCopySlice;
+        for (; fed < want && fed < io.arrival->n_slices; fed++) CK(io.arrival->feed(fed));
+        return DFL_OK;
+    };
+    for (uint32_t k = 0;; k++) {
+        const size_t piece_end = (n - parse_pos) > io.piece ? parse_pos + io.piece : n;
         const bool last = piece_end == n;
         size_t base = parse_pos > kWindow ? parse_pos - kWindow : 0;
         if (!carry_tok.empty() && carry_in < base) base = carry_in;
@@ -491,7 +517,16 @@ static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_
         const size_t n_piece = piece_end - base;
         const uint32_t hdr = header_written ? 0u : wrap_header_bytes(wrap, gz_hdr_len);
         const size_t bound = dfl_bound(n_piece, wrap) + gz_hdr_len + 64;
-        if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
+        uint8_t*& scratch = (k & 1u) ? c.d_out2 : c.d_out;
+        size_t& scratch_cap = (k & 1u) ? c.d_out2_cap : c.d_out_cap;
+        if (d2h_pending[k & 1u]) {              // the bytes of piece k - 2 must have left this scratch buffer
+            CK(cudaEventSynchronize(c.d2h_ev[k & 1u]));
+            d2h_pending[k & 1u] = false;
+        }
+        if ((rc = c.ensure_stage(scratch, scratch_cap, bound))) return rc;
+        if ((rc = feed_to(piece_end))) return rc;
+        if (io.arrival)
+            for (size_t q = 0; q < fed; q++) CK(cudaStreamWaitEvent(st, (*io.arrival->ev)[q], 0));
         PieceIn pin;
         pin.init_key = parse_key;
         pin.open_piece = last ? 0 : 1;
@@ -501,12 +536,19 @@ static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_
         pin.carry_in_pos = (uint32_t)(carry_in - base);
         pin.bits_n = bits_n;
         pin.bits_v = bits_v;
-        size_t produced = 0;
         t_piece_in = &pin;
-        rc = run_pipeline(c, st, d_in + base, n_piece, parse_pos - base, opt, hdr ? wrap : DFL_RAW, hdr, last ? 1 : 0, 0,
-                          c.d_out, c.d_out_cap, &produced, nullptr, 0, 0, gz_hdr);
+        t_profiling = 0;
+        g_launch_count = 0;
+        StageTimer tm(st, false);
+        rc = issue_pipeline(c, st, tm, d_in + base, n_piece, parse_pos - base, opt, hdr ? wrap : DFL_RAW, hdr, last ? 1 : 0, 0,
+                            scratch, scratch_cap, nullptr, 0, 0, gz_hdr);
         t_piece_in = nullptr;
-        if (rc) return rc;
+        t_profiling = saved_prof;
+        if (rc) { cudaStreamSynchronize(st); return rc; }
+        // while this piece runs, the next one's input is put on its way (a blocking, staged copy for pageable memory)
+        if (!last && (rc = feed_to(piece_end + io.piece < n ? piece_end + io.piece : n))) return rc;
+        size_t produced = 0;
+        if ((rc = finish_pipeline(c, st, n_piece, parse_pos - base, &produced))) return rc;
         const DevMeta m = *c.h_meta;
         // the container checksum is folded piece by piece (the scratch is sized for one piece) and written below
         if (wrap != DFL_RAW && piece_end > sum_upto) {
@@ -521,10 +563,18 @@ static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_
         }
         const size_t full = last ? (size_t)m.stream_bytes : (size_t)(m.stream_bits >> 3);
         const uint32_t left_bits = last ? 0u : (uint32_t)(m.stream_bits & 7ull);
-        if (out_off + hdr + full + 16 > out_cap) { *out_len = out_off + hdr + full + 16; return DFL_E_OVERFLOW; }
-        if (hdr + full) CK(cudaMemcpyAsync(d_out + out_off, c.d_out, hdr + full, cudaMemcpyDeviceToDevice, st));
+        if (out_off + hdr + full + 16 > io.out_cap) { *out_len = out_off + hdr + full + 16; return DFL_E_OVERFLOW; }
+        if (hdr + full) {
+            if (io.h_out) {   // the pipeline has finished (its bookkeeping was read): copy out beside the next piece
+                CK(cudaMemcpyAsync(io.h_out + out_off, scratch, hdr + full, cudaMemcpyDeviceToHost, c.d2h_stream));
+                CK(cudaEventRecord(c.d2h_ev[k & 1u], c.d2h_stream));
+                d2h_pending[k & 1u] = true;
+            } else {
+                CK(cudaMemcpyAsync(io.d_out + out_off, scratch, hdr + full, cudaMemcpyDeviceToDevice, st));
+            }
+        }
         uint8_t last_byte = 0;
-        if (left_bits) CK(cudaMemcpyAsync(&last_byte, c.d_out + hdr + full, 1, cudaMemcpyDeviceToHost, st));
+        if (left_bits) CK(cudaMemcpyAsync(&last_byte, scratch + hdr + full, 1, cudaMemcpyDeviceToHost, st));
         const size_t coded = (size_t)m.n_blocks * kBlockTokens;
         const size_t rem = !last && m.n_tokens > coded ? (size_t)(m.n_tokens - coded) : 0;
         std::vector<uint32_t> next_carry(rem);
@@ -540,6 +590,7 @@ static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_
         parse_pos = base + m.end_pos;
         parse_key = m.end_key;
     }
+    if (io.h_out) CK(cudaStreamSynchronize(c.d2h_stream));
     uint8_t tr[8];
     size_t tr_len = 0;
     if (wrap == DFL_ZLIB) {            // lib.rs:192-196
@@ -551,9 +602,12 @@ static int compress_device_pieces(Context& c, cudaStream_t st, const uint8_t* d_
         tr_len = 8;
     }
     if (tr_len) {
-        if (out_off + tr_len > out_cap) { *out_len = out_off + tr_len; return DFL_E_OVERFLOW; }
-        CK(cudaMemcpyAsync(d_out + out_off, tr, tr_len, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        if (out_off + tr_len > io.out_cap) { *out_len = out_off + tr_len; return DFL_E_OVERFLOW; }
+        if (io.h_out) memcpy(io.h_out + out_off, tr, tr_len);
+        else {
+            CK(cudaMemcpyAsync(io.d_out + out_off, tr, tr_len, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
         out_off += tr_len;
     }
     *out_len = out_off;
@@ -571,8 +625,11 @@ extern "C" int dfl_compress_device(const void* d_in, size_t n, const dfl_options
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     if (n >= oneshot_piece_limit()) {
         if (opt->special != 0 || (reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return opt->special ? DFL_E_UNSUPPORTED : DFL_E_ARG;
-        return compress_device_pieces(c, st, reinterpret_cast<const uint8_t*>(d_in), n, opt, wrap, gz_hdr, gz_hdr_len,
-                                      reinterpret_cast<uint8_t*>(d_out), out_cap, out_len);
+        PieceIO io;
+        io.piece = oneshot_piece_limit() < ((size_t)1 << 30) ? oneshot_piece_limit() : ((size_t)1 << 30);
+        io.d_out = reinterpret_cast<uint8_t*>(d_out);
+        io.out_cap = out_cap;
+        return compress_pieces(c, st, reinterpret_cast<const uint8_t*>(d_in), n, opt, wrap, gz_hdr, gz_hdr_len, io, out_len);
     }
     return run_pipeline(c, st, reinterpret_cast<const uint8_t*>(d_in), n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1,
                         0, reinterpret_cast<uint8_t*>(d_out), out_cap, out_len, nullptr, 0, 0, gz_hdr);
@@ -614,6 +671,23 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c.copy_ev.push_back(e);
+    }
+    // Optional (DFL_HOST_PIECE_MIB): run large calls as open pieces, so that the copy of a piece's output overlaps
+    // the next piece's kernels as well.  Measured on B200 it does not pay -- 1 GiB at Default 6162 vs 6161 MiB/s,
+    // at Fast 20998 vs 24088 MiB/s with 256 MiB pieces, worse with smaller ones (the per-piece synchronisation
+    // costs what the overlap saves) -- so it is off unless asked for.
+    static const size_t host_piece = [] {
+        const char* e = getenv("DFL_HOST_PIECE_MIB");
+        size_t x = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        return x << 20;
+    }();
+    if (host_piece && n >= 2 * host_piece && opt->special == 0) {
+        PieceIO io;
+        io.piece = host_piece;
+        io.arrival = &arrival;
+        io.h_out = out;
+        io.out_cap = out_cap;
+        return compress_pieces(c, c.stream, c.d_in, n, opt, wrap, gz_hdr, gz_hdr_len, io, out_len);
     }
     size_t produced = 0;
     rc = run_pipeline(c, c.stream, c.d_in, n, 0, opt, wrap, wrap_header_bytes(wrap, gz_hdr_len), 1, 0, c.d_out, c.d_out_cap,
