@@ -620,3 +620,16 @@ def test_device_call_longer_than_4_gib(dfl, pg11):
         pos += len(got)
     assert ok and pos == total_blocks << 20 and d.eof
     assert int.from_bytes(comp[-4:], "little") == (total_blocks << 20) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("preset", list(o.PRESETS))
+def test_every_preset_on_every_kind_of_synthetic_data(dfl, preset):
+    """4 MiB of each generator of the BASELINE configs (tests/datagen.py) at every preset, against the oracle:
+    covers the quarter-budget walk (high), RLE and Huffman-only on data with long matches, many repairs of the
+    speculative parse (sparse, PNG-like) and stored / fixed block choices (random)."""
+    import datagen
+    opts = o.PRESETS[preset]()
+    for gen in (datagen.silesia_mix, datagen.enwik_like, datagen.png_idat_like, datagen.binary_like):
+        data = gen(4 << 20)
+        got = dfl.deflate_bytes_conf(data, _copts(dfl, opts))
+        assert got == o.compress(data, opts, o.RAW), (preset, gen.__name__, len(got))
