@@ -66,6 +66,10 @@ void dev_free(T*& p) {
 // Input that is still on its way to the device: slice k (kCopySlice bytes) is complete once
 // ev[k] has fired (recorded on the copy stream by dfl_compress).
 constexpr size_t kCopySlice = 128u << 20;
+constexpr size_t kCopyFirst = 32u << 20;   // the first slice is short, so that the kernels start early
+// slice k covers [slice_lo(k), slice_lo(k + 1))
+inline size_t slice_lo(size_t k) { return k == 0 ? 0 : kCopyFirst + (k - 1) * kCopySlice; }
+inline size_t slice_count(size_t n) { return n <= kCopyFirst ? (n ? 1 : 0) : 1 + (n - kCopyFirst + kCopySlice - 1) / kCopySlice; }
 struct InputArrival {
     std::vector<cudaEvent_t>* ev;
     size_t n_slices;
@@ -74,7 +78,7 @@ struct InputArrival {
     size_t n;                  // run while slice k + 1 is being staged
     cudaStream_t copy_stream;
     cudaError_t feed(size_t k) const {
-        const size_t lo = k * kCopySlice, len = (n - lo) < kCopySlice ? (n - lo) : kCopySlice;
+        const size_t lo = slice_lo(k), hi = slice_lo(k + 1) < n ? slice_lo(k + 1) : n, len = hi - lo;
         cudaError_t e = cudaMemcpyAsync(d_dst + lo, h_src + lo, len, cudaMemcpyHostToDevice, copy_stream);
         if (e != cudaSuccess) return e;
         return cudaEventRecord((*ev)[k], copy_stream);
@@ -313,7 +317,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
             for (size_t k = 0; k < arrival->n_slices; k++) {
                 CK(arrival->feed(k));
                 CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0));
-                const size_t have = (k + 1 == arrival->n_slices) ? n : (k + 1) * kCopySlice;
+                const size_t have = (k + 1 == arrival->n_slices) ? n : slice_lo(k + 1);
                 uint32_t w_ok = (have >= n) ? w_end : (uint32_t)((have - 272) / kWindow);
                 if (w_ok > w_end) w_ok = w_end;
                 CK(launch_window_sort(j, b, st, w_sorted, w_ok));
@@ -504,7 +508,7 @@ static int compress_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, siz
     const int saved_prof = t_profiling;
     auto feed_to = [&](size_t upto) -> int {   // issue the host-to-device slices covering [0, upto)
         if (!io.arrival) return DFL_OK;
-        const size_t want = (upto + kCopySlice - 1) / kCopySlice;
+        const size_t want = slice_count(upto);
         for (; fed < want && fed < io.arrival->n_slices; fed++) CK(io.arrival->feed(fed));
         return DFL_OK;
     };
@@ -666,7 +670,7 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound + 64))) return rc;
     // host -> device in slices on a second stream; the pipeline's first two stages start on a
     // slice as soon as it has landed (writer.rs callers pay PCIe: SURVEY 8(f) rank 1)
-    InputArrival arrival{&c.copy_ev, (n + kCopySlice - 1) / kCopySlice, in, c.d_in, n, c.copy_stream};
+    InputArrival arrival{&c.copy_ev, slice_count(n), in, c.d_in, n, c.copy_stream};
     while (c.copy_ev.size() < arrival.n_slices) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
