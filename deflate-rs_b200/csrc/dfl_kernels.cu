@@ -135,6 +135,9 @@ constexpr uint32_t kSortSmem = (kSortCntWords + kSortBufWords) * 4 + 256;
 static_assert(kSortItems == 32, "one item per bit of the digit/prefix packing below");
 static_assert(kWindow + 16 <= kSortCntWords * 4, "byte staging must fit in the counter area");
 
+// word w of a counter row is stored at slot_of(w): its 32-word group rotated by the group number
+__device__ __forceinline__ uint32_t sort_slot_of(uint32_t w) { return (w & ~31u) | ((w + (w >> 5)) & 31u); }
+
 template <bool ITEMS>   // ITEMS: emit the sorted (hash << 15 | position) words for k_span_scatter instead of entries
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
@@ -169,7 +172,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
     __syncthreads();
 
     // Items live in `buf` in blocked order (thread t owns buf[33 t .. 33 t + 31]) between passes.
-    const uint32_t cw = (t & 511u) * 2u + (t >> 9);     // u16 index of this thread's counter inside a digit row
+    // u16 index of this thread's counter inside a digit row.  Word w of a row holds the counters of threads w and
+    // 512 + w; the 32-word groups of a row are rotated by their group number (word w lives at slot_of(w)), which
+    // keeps the per-thread accesses of the counting and scattering loops conflict free *and* lets the row scan
+    // below read 16 consecutive words per lane without bank conflicts (unrotated, the lanes of a warp would meet
+    // in two bank groups: ncu showed 4x the ideal number of shared-memory wavefronts there).
+    const uint32_t cw = sort_slot_of(t & 511u) * 2u + (t >> 9);
 #pragma unroll 1
     for (uint32_t pass = 0; pass < 3; pass++) {
         const uint32_t shift = 15u + 5u * pass;
@@ -190,10 +198,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
         // low halves are threads 0..511, high halves threads 512..1023.  Warp d scans row d.
         {
             const uint32_t d = t >> 5, l = t & 31u;
-            uint32_t* row = cntw + d * 512u + l * 16u;
+            uint32_t* row = cntw + d * 512u;
             uint32_t sum = 0;                              // packed (hi << 16 | lo); totals <= 32768 each
 #pragma unroll
-            for (uint32_t k = 0; k < 16; k++) sum += row[k];
+            for (uint32_t k = 0; k < 16; k++) sum += row[sort_slot_of(l * 16u + k)];
             uint32_t incl = sum;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) {
@@ -220,8 +228,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
             uint32_t run_hi = dbase + lo_tot + (excl >> 16);
 #pragma unroll
             for (uint32_t k = 0; k < 16; k++) {
-                uint32_t vk = row[k];
-                row[k] = run_lo | (run_hi << 16);          // both < 65536 (at most 32768 items)
+                uint32_t* slot = row + sort_slot_of(l * 16u + k);
+                uint32_t vk = *slot;
+                *slot = run_lo | (run_hi << 16);           // both < 65536 (at most 32768 items)
                 run_lo += vk & 0xffffu;
                 run_hi += vk >> 16;
             }
