@@ -10,10 +10,10 @@ namespace dfl {
 
 // Tunables of the parse stage (see DESIGN.md "parse").
 #ifndef DFL_PARSE_SEG
-#define DFL_PARSE_SEG 8192
+#define DFL_PARSE_SEG 4096
 #endif
 #ifndef DFL_PARSE_WARM
-#define DFL_PARSE_WARM 1024
+#define DFL_PARSE_WARM 512
 #endif
 constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread (large inputs)
 constexpr uint32_t kParseWarm = DFL_PARSE_WARM;   // speculative warm-up before the segment start
