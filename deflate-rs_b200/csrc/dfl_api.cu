@@ -63,25 +63,43 @@ void dev_free(T*& p) {
     p = nullptr;
 }
 
-// Input that is still on its way to the device: slice k (kCopySlice bytes) is complete once
-// ev[k] has fired (recorded on the copy stream by dfl_compress).
+// Input that is still on its way to the device: slice k = [lo[k], lo[k + 1]) is complete once
+// ev[k] has fired (recorded on the copy stream by feed(k)).
+// The pipeline launches its first two stages once per slice, and every launch ends in a partly idle last wave
+// (one k_match CTA runs 1.7 ms at Default), so slices should be few; the first must be short so that the kernels
+// start early.  At Default the link is ~7x faster than the kernels (19 ms against 134 ms per GiB): slices may grow
+// geometrically without the kernels ever waiting.  With a short chain budget copy and kernels run at about the
+// same pace and the CTAs are short: uniform slices.
 constexpr size_t kCopySlice = 128u << 20;
-constexpr size_t kCopyFirst = 32u << 20;   // the first slice is short, so that the kernels start early
-// slice k covers [slice_lo(k), slice_lo(k + 1))
-inline size_t slice_lo(size_t k) { return k == 0 ? 0 : kCopyFirst + (k - 1) * kCopySlice; }
-inline size_t slice_count(size_t n) { return n <= kCopyFirst ? (n ? 1 : 0) : 1 + (n - kCopyFirst + kCopySlice - 1) / kCopySlice; }
+constexpr size_t kCopyFirst = 32u << 20;
+inline std::vector<size_t> plan_slices(size_t n, bool long_kernels) {
+    std::vector<size_t> lo{0};
+    if (n == 0) return lo;
+    size_t at = kCopyFirst;
+    while (at < n) {
+        lo.push_back(at);
+        at = long_kernels ? (at == kCopyFirst ? (size_t)256u << 20 : at * 4) : at + kCopySlice;
+    }
+    lo.push_back(n);
+    return lo;
+}
 struct InputArrival {
     std::vector<cudaEvent_t>* ev;
+    std::vector<size_t> lo;    // slice boundaries, n_slices + 1 of them
     size_t n_slices;
     const uint8_t* h_src;      // host source; slice k is copied by feed(k) right before it is waited for, so
     uint8_t* d_dst;            // that with pageable memory (a blocking, staged copy) the kernels of slice k
     size_t n;                  // run while slice k + 1 is being staged
     cudaStream_t copy_stream;
     cudaError_t feed(size_t k) const {
-        const size_t lo = slice_lo(k), hi = slice_lo(k + 1) < n ? slice_lo(k + 1) : n, len = hi - lo;
-        cudaError_t e = cudaMemcpyAsync(d_dst + lo, h_src + lo, len, cudaMemcpyHostToDevice, copy_stream);
+        cudaError_t e = cudaMemcpyAsync(d_dst + lo[k], h_src + lo[k], lo[k + 1] - lo[k], cudaMemcpyHostToDevice, copy_stream);
         if (e != cudaSuccess) return e;
         return cudaEventRecord((*ev)[k], copy_stream);
+    }
+    size_t slices_covering(size_t upto) const {   // how many leading slices hold [0, upto)
+        size_t m = 0;
+        while (m < n_slices && lo[m] < upto) m++;
+        return m;
     }
 };
 
@@ -317,7 +335,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
             for (size_t k = 0; k < arrival->n_slices; k++) {
                 CK(arrival->feed(k));
                 CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0));
-                const size_t have = (k + 1 == arrival->n_slices) ? n : slice_lo(k + 1);
+                const size_t have = (k + 1 == arrival->n_slices) ? n : arrival->lo[k + 1];
                 uint32_t w_ok = (have >= n) ? w_end : (uint32_t)((have - 272) / kWindow);
                 if (w_ok > w_end) w_ok = w_end;
                 CK(launch_window_sort(j, b, st, w_sorted, w_ok));
@@ -508,7 +526,7 @@ static int compress_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, siz
     const int saved_prof = t_profiling;
     auto feed_to = [&](size_t upto) -> int {   // issue the host-to-device slices covering [0, upto)
         if (!io.arrival) return DFL_OK;
-        const size_t want = slice_count(upto);
+        const size_t want = io.arrival->slices_covering(upto);
         for (; fed < want && fed < io.arrival->n_slices; fed++) CK(io.arrival->feed(fed));
         return DFL_OK;
     };
@@ -668,14 +686,6 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
     size_t bound = dfl_bound(n, wrap) + gz_hdr_len;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound + 64))) return rc;
-    // host -> device in slices on a second stream; the pipeline's first two stages start on a
-    // slice as soon as it has landed (writer.rs callers pay PCIe: SURVEY 8(f) rank 1)
-    InputArrival arrival{&c.copy_ev, slice_count(n), in, c.d_in, n, c.copy_stream};
-    while (c.copy_ev.size() < arrival.n_slices) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c.copy_ev.push_back(e);
-    }
     // Optional (DFL_HOST_PIECE_MIB): run large calls as open pieces, so that the copy of a piece's output overlaps
     // the next piece's kernels as well.  Measured on B200 it does not pay -- 1 GiB at Default 6162 vs 6161 MiB/s,
     // at Fast 20998 vs 24088 MiB/s with 256 MiB pieces, worse with smaller ones (the per-piece synchronisation
@@ -685,6 +695,16 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
         size_t x = e ? (size_t)strtoull(e, nullptr, 10) : 0;
         return x << 20;
     }();
+    // host -> device in slices on a second stream; the pipeline's first two stages start on a
+    // slice as soon as it has landed (writer.rs callers pay PCIe: SURVEY 8(f) rank 1)
+    InputArrival arrival{&c.copy_ev, {}, 0, in, c.d_in, n, c.copy_stream};
+    arrival.lo = plan_slices(n, opt->max_hash_checks >= 16 && !(host_piece && n >= 2 * host_piece));
+    arrival.n_slices = arrival.lo.size() - 1;
+    while (c.copy_ev.size() < arrival.n_slices) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c.copy_ev.push_back(e);
+    }
     if (host_piece && n >= 2 * host_piece && opt->special == 0) {
         PieceIO io;
         io.piece = host_piece;
