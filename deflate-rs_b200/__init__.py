@@ -24,7 +24,7 @@ from ._native import DeflateB200Error, RAW, ZLIB, GZIP  # noqa: F401
 __all__ = [
     "Compression", "CompressionOptions", "MatchingType", "SpecialOptions", "deflate_bytes", "deflate_bytes_conf",
     "deflate_bytes_zlib", "deflate_bytes_zlib_conf", "deflate_bytes_gzip", "deflate_bytes_gzip_conf", "GzBuilder",
-    "write", "compress_device", "compress_device_batch", "DeflateB200Error",
+    "write", "compress_device", "compress_device_batch", "compress_batch", "DeflateB200Error",
 ]
 
 
@@ -232,6 +232,30 @@ def compress_device_batch(srcs, options=Compression.Default, wrap=ZLIB, outs=Non
         rc = L.dfl_compress_device_batch(k, d_in, n, ctypes.byref(opts), wrap, d_out, cap, out_len, status)
     _native.check(rc, "dfl_compress_device_batch")
     return outs, [int(x) for x in out_len]
+
+
+def compress_batch(inputs, options=Compression.Default, wrap=ZLIB):
+    """dfl_compress_batch: independent streams from host memory (bytes-like objects), encoded concurrently.
+    Returns a list of bytes, member i equal to deflate_bytes*_conf(inputs[i]) (lib.rs:137,182,242)."""
+    import numpy as np
+
+    L = _native.lib()
+    k = len(inputs)
+    if k == 0:
+        return []
+    srcs = [np.frombuffer(b, dtype=np.uint8) for b in inputs]
+    caps = [L.dfl_bound(s.size, wrap) + 64 for s in srcs]
+    outs = [np.empty(c, dtype=np.uint8) for c in caps]
+    opts = CompressionOptions.from_(options)._c()
+    p_in = (ctypes.c_void_p * k)(*[s.ctypes.data if s.size else None for s in srcs])
+    p_out = (ctypes.c_void_p * k)(*[o.ctypes.data for o in outs])
+    n = (ctypes.c_size_t * k)(*[s.size for s in srcs])
+    cap = (ctypes.c_size_t * k)(*caps)
+    out_len = (ctypes.c_size_t * k)()
+    status = (ctypes.c_int * k)()
+    rc = L.dfl_compress_batch(k, p_in, n, ctypes.byref(opts), wrap, p_out, cap, out_len, status)
+    _native.check(rc, "dfl_compress_batch")
+    return [o[:int(m)].tobytes() for o, m in zip(outs, out_len)]
 
 
 class _Encoder:

@@ -18,7 +18,7 @@ E_OVERFLOW = -5
 # every symbol include/deflate_b200.h declares
 EXPORTS = [
     "dfl_options_preset", "dfl_strerror", "dfl_last_cuda_error", "dfl_version", "dfl_device_count", "dfl_bound",
-    "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters",
+    "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_compress_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters",
     "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_set_piece_bytes", "dfl_encoder_take_output",
     "dfl_encoder_advance_output", "dfl_encoder_checksum", "dfl_encoder_reset", "dfl_encoder_free",
     "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens", "dfl_set_match_path",
@@ -71,6 +71,8 @@ def lib():
                                             ctypes.c_void_p, ctypes.c_size_t, szp, ctypes.c_void_p]
     L.dfl_compress_device_batch.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), szp, optp, ctypes.c_int,
                                             ctypes.POINTER(ctypes.c_void_p), szp, szp, ctypes.POINTER(ctypes.c_int)]
+    L.dfl_compress_batch.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), szp, optp, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_void_p), szp, szp, ctypes.POINTER(ctypes.c_int)]
     L.dfl_set_profiling.argtypes = [ctypes.c_int]
     L.dfl_last_stage_times.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     L.dfl_last_counters.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]

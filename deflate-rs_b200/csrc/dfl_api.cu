@@ -781,6 +781,61 @@ extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, 
     return first_err;
 }
 
+// Host-buffer batch: the members rotate over a pool of pipelines; while the host waits for one member's size
+// (needed for its device-to-host copy) the other lanes keep the GPU and both copy directions busy.
+extern "C" int dfl_compress_batch(size_t count, const uint8_t* const* in, const size_t* n, const dfl_options* opt, int wrap,
+                                  uint8_t* const* out, const size_t* out_cap, size_t* out_len, int* status) {
+    if (!opt || !valid_wrap(wrap) || (count && (!in || !n || !out || !out_cap || !out_len))) return DFL_E_ARG;
+    constexpr size_t kBatchLanes = 16;
+    thread_local std::vector<std::unique_ptr<Context>> pool;
+    const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
+    while (pool.size() < lanes) pool.emplace_back(new Context());
+    std::vector<size_t> member(lanes, SIZE_MAX);   // the member in flight on each lane
+    std::vector<int> lane_rc(lanes, DFL_OK);
+    int first_err = DFL_OK;
+    const int saved_prof = t_profiling;
+    t_profiling = 0;
+    t_peers = (uint32_t)lanes;
+    g_launch_count = 0;
+    auto settle = [&](size_t k) {   // member on lane k: wait for its size, put its bytes on their way to the host
+        const size_t i = member[k];
+        if (i == SIZE_MAX) return;
+        Context& c = *pool[k];
+        int rc = lane_rc[k];
+        if (rc == DFL_OK) rc = finish_pipeline(c, c.stream, n[i], 0, &out_len[i]);
+        else if (c.ok) cudaStreamSynchronize(c.stream);
+        if (rc == DFL_OK && out_len[i] > out_cap[i]) rc = DFL_E_OVERFLOW;
+        if (rc == DFL_OK && cudaMemcpyAsync(out[i], c.d_out, out_len[i], cudaMemcpyDeviceToHost, c.stream) != cudaSuccess)
+            rc = DFL_E_CUDA;
+        if (status) status[i] = rc;
+        if (rc != DFL_OK && first_err == DFL_OK) first_err = rc;
+        member[k] = SIZE_MAX;
+    };
+    for (size_t i = 0; i < count; i++) {
+        const size_t k = i % lanes;
+        settle(k);
+        Context& c = *pool[k];
+        int rc = (!out[i] || (!in[i] && n[i])) ? DFL_E_ARG : (n[i] >= ((size_t)1 << 32) - 64 ? DFL_E_UNSUPPORTED : c.init());
+        if (rc == DFL_OK) rc = c.ensure_stage(c.d_in, c.d_in_cap, n[i] + 64);
+        if (rc == DFL_OK) rc = c.ensure_stage(c.d_out, c.d_out_cap, dfl_bound(n[i], wrap) + 64);
+        // same stream as the previous member's copy out of d_out: ordered behind it
+        if (rc == DFL_OK && n[i] && cudaMemcpyAsync(c.d_in, in[i], n[i], cudaMemcpyHostToDevice, c.stream) != cudaSuccess)
+            rc = DFL_E_CUDA;
+        if (rc == DFL_OK) {
+            StageTimer tm(c.stream, false);
+            rc = issue_pipeline(c, c.stream, tm, c.d_in, n[i], 0, opt, wrap, wrap_header_bytes(wrap, 0), 1, 0, c.d_out, c.d_out_cap);
+        }
+        member[k] = i;
+        lane_rc[k] = rc;
+    }
+    for (size_t k = 0; k < lanes; k++) settle(k);
+    for (size_t k = 0; k < lanes; k++)
+        if (pool[k]->ok && cudaStreamSynchronize(pool[k]->stream) != cudaSuccess && first_err == DFL_OK) first_err = DFL_E_CUDA;
+    t_profiling = saved_prof;
+    t_peers = 1;
+    return first_err;
+}
+
 extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void* stream) {
     if (!crc || (!d_in && n)) return DFL_E_ARG;
     Context& c = tls_context();

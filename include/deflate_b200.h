@@ -120,6 +120,15 @@ int dfl_compress_device_piece(const void *d_in, size_t n_total, size_t dict_len,
 int dfl_compress_device_batch(size_t count, const void *const *d_in, const size_t *n, const dfl_options *opt,
                               int wrap, void *const *d_out, const size_t *out_cap, size_t *out_len, int *status);
 
+/* ---- many independent streams, host buffers ---------------------------------------------------
+ * The same `count` calls of deflate_bytes*_conf (lib.rs:137,182,242) for callers whose data lives in
+ * host memory (the image encoders this crate serves: one IDAT stream per picture).  The members rotate
+ * over a pool of pipelines, each with its own stream: a member's input copy, kernels and output copy
+ * overlap those of the others.  Pinned buffers copy asynchronously; pageable ones work, staged by the
+ * driver.  Byte-for-byte what dfl_compress returns for each member.  Blocking; status as above. */
+int dfl_compress_batch(size_t count, const uint8_t *const *in, const size_t *n, const dfl_options *opt, int wrap,
+                       uint8_t *const *out, const size_t *out_cap, size_t *out_len, int *status);
+
 /* Per-stage device timings of the most recent dfl_compress_device call on this thread, in
  * milliseconds (CUDA events on the launching stream): names[i] points to a static string.
  * Returns the number of stages (0 if timing was not enabled with dfl_set_profiling(1)). */

@@ -420,6 +420,44 @@ def test_batch_of_independent_streams(dfl, pg11):
             assert got == o.compress(d, o.opts_default(), owrap), len(d)
 
 
+def test_host_batch_of_independent_streams(dfl, pg11):
+    """dfl_compress_batch: host buffers in and out, more members than pipelines in the pool (the lanes are reused),
+    ragged sizes incl. empty; every member equals the reference algorithm's one-shot result."""
+    import datagen
+    datas = [datagen.png_idat_like(50000 + 7001 * i, 0xBA7C + i) for i in range(37)] + [b"", b"x", pg11, b""]
+    for wrap, owrap, opts, oopts in ((dfl.ZLIB, o.ZLIB, dfl.Compression.Default, o.opts_default()),
+                                     (dfl.RAW, o.RAW, dfl.Compression.Fast, o.opts_fast()),
+                                     (dfl.GZIP, o.GZIP, dfl.Compression.Best, o.opts_high())):
+        got = dfl.compress_batch(datas, opts, wrap)
+        assert len(got) == len(datas)
+        for d, g in zip(datas, got):
+            assert g == o.compress(d, oopts, owrap), len(d)
+
+
+def test_host_batch_reports_overflow_per_member(dfl):
+    """A member whose output buffer is too small gets DFL_E_OVERFLOW and its needed size; the others are unaffected."""
+    import ctypes
+    import numpy as np
+    L = dfl._native.lib()
+    datas = [bytes(range(256)) * 40, os.urandom(5000), b"abc" * 1000]
+    srcs = [np.frombuffer(d, dtype=np.uint8) for d in datas]
+    caps = [L.dfl_bound(len(d), dfl.ZLIB) + 64 for d in datas]
+    caps[1] = 100
+    outs = [np.zeros(c, dtype=np.uint8) for c in caps]
+    k = len(datas)
+    opts = dfl.CompressionOptions.default()._c()
+    out_len = (ctypes.c_size_t * k)()
+    status = (ctypes.c_int * k)()
+    rc = L.dfl_compress_batch(k, (ctypes.c_void_p * k)(*[s.ctypes.data for s in srcs]), (ctypes.c_size_t * k)(*map(len, datas)),
+                              ctypes.byref(opts), dfl.ZLIB, (ctypes.c_void_p * k)(*[x.ctypes.data for x in outs]),
+                              (ctypes.c_size_t * k)(*caps), out_len, status)
+    assert rc == dfl._native.E_OVERFLOW and list(status) == [0, dfl._native.E_OVERFLOW, 0]
+    want = [o.compress(d, o.opts_default(), o.ZLIB) for d in datas]
+    assert out_len[1] == len(want[1])
+    for i in (0, 2):
+        assert bytes(outs[i][:out_len[i]]) == want[i]
+
+
 # ---------------------------------------------------------------- BASELINE.json's full sizes
 def _inflate_equals(comp: bytes, data: bytes, wbits: int) -> bool:
     d = zlib.decompressobj(wbits)
