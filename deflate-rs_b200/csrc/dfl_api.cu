@@ -912,7 +912,7 @@ extern "C" int dfl_lz77_tokens(const uint8_t* in, size_t n, const dfl_options* o
 }
 
 // ============================================================================ streaming
-// write() buffers input on the host; the buffered bytes are encoded
+// write() sends input straight to the device; the bytes there are encoded
 //   * when flush(Sync) / flush(Finish) is called -- a *closed* piece: everything is parsed and coded, and
 //   * on their own once `piece_bytes` have accumulated -- an *open* piece: the reference's stream has no
 //     seam there (lib.rs:408-433: the bytes do not depend on how write() chops the input), so the piece
@@ -920,142 +920,318 @@ extern "C" int dfl_lz77_tokens(const uint8_t* in, size_t n, const dfl_options* o
 //     full 258-byte look-ahead), codes only complete 31744-token blocks, and hands the parser state, the
 //     uncoded tokens and the incomplete last output byte to the next piece.
 // Either way the last 32 KiB stay as dictionary, so memory is bounded and a stream may be longer than 4 GiB.
+//
+// Two device buffers alternate.  An open piece is only *issued* by write(); while its kernels run, further
+// writes land in the other buffer behind a reserved prefix, and when the piece is settled (at the next
+// piece, flush, or checksum) its tail -- dictionary, unparsed bytes, the input of carried tokens -- is
+// copied device-to-device into that prefix.  So the caller's copy-in overlaps the kernels, every input byte
+// crosses the link once, and the host keeps no copy of the input.
+namespace {
+
+struct ByteBuf {   // growable host bytes without value-initialisation
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    ~ByteBuf() { free(p); }
+    bool reserve(size_t need) {
+        if (need <= cap) return true;
+        size_t c = cap ? cap : 4096;
+        while (c < need) c += c / 2 + 4096;
+        uint8_t* q = static_cast<uint8_t*>(realloc(p, c));
+        if (!q) return false;
+        p = q;
+        cap = c;
+        return true;
+    }
+};
+
+// history an open piece can hand over: window + look-ahead tail + the input of < 31744 carried tokens
+constexpr size_t kStreamReserve = ((size_t)kBlockTokens * kMaxMatch + kWindow + 4 * (kMaxMatch + 1) + 4096 + 15) & ~(size_t)15;
+constexpr size_t kStreamSlack = 256;          // bytes behind the data that kernels may touch
+constexpr size_t kPendBytes = 1u << 20;       // small writes are gathered on the host first
+constexpr size_t kPendDirect = 256u << 10;    // writes of at least this size go to the device directly
+
+struct StreamBuf {
+    uint8_t* d = nullptr;
+    size_t cap = 0;
+    size_t org = kStreamReserve;   // position of stream offset `off_org`: appended bytes start here
+    uint64_t off_org = 0;
+    size_t lo = kStreamReserve;    // first valid byte (installed history), 16-byte aligned
+    size_t new_n = 0;              // bytes appended at org
+    size_t end() const { return org + new_n; }
+    size_t pos(uint64_t off) const { return (size_t)((int64_t)org + (int64_t)(off - off_org)); }
+};
+
+}  // namespace
+
 struct dfl_encoder {
     dfl_options opt;
     int wrap;
-    Context ctx;                 // per-handle stream and device buffers
-    std::vector<uint8_t> data;   // retained history (dictionary, input of carried tokens) followed by unparsed input
-    size_t parse_pos = 0;        // data[parse_pos..] has not been parsed yet
-    uint32_t parse_key = 0;      // parser state at parse_pos (parse_state_key)
+    Context ctx;                 // per-handle streams and scratch
+    StreamBuf sb[2];
+    int f = 0;                   // sb[f] receives writes
+    bool busy = false;           // an open piece is running on sb[1 - f]
+    size_t busy_n = 0, busy_begin = 0;
+    uint32_t busy_hdr = 0;
+    cudaEvent_t in_ev = nullptr;     // input copies issued so far are on the device (copy stream)
+    cudaEvent_t hist_ev = nullptr;   // the latest history hand-over has left its source buffer (compute stream)
+    std::vector<uint8_t> pend;   // small writes not yet sent to the device
+    uint64_t parse_off = 0;      // stream offset of the first byte not parsed yet
+    uint32_t parse_key = 0;      // parser state there (parse_state_key)
     std::vector<uint32_t> carry_tok;   // parsed but not yet coded (fewer than 31744)
-    size_t carry_in = 0;         // index in data of the first carried token's input byte
+    uint64_t carry_off = 0;      // stream offset of the first carried token's input byte
     uint32_t bits_n = 0, bits_v = 0;   // incomplete last byte of the stream so far
-    std::vector<uint8_t> out;    // produced bytes not yet handed to the caller
+    ByteBuf out;                 // produced bytes not yet handed to the caller
     size_t out_pos = 0;
     bool header_written = false;
     bool finished = false;
-    uint32_t adler = 1;          // Adler-32 of everything written so far (device-computed per piece)
+    uint32_t adler = 1;          // Adler-32 of stream bytes [0, sum_off) (device-computed, folded on the host)
     uint32_t crc = 0;            // CRC-32 likewise (gzip)
-    size_t sum_upto = 0;         // data[..sum_upto) is already folded into the checksum
-    uint64_t total_in = 0;
-    size_t piece_bytes = 256u << 20;   // unparsed bytes that trigger an open piece
+    uint64_t sum_off = 0;
+    uint64_t total_in = 0;       // bytes accepted by write()
+    size_t piece_bytes = 256u << 20;   // appended bytes that trigger an open piece
     std::vector<uint8_t> gz_hdr; // gzip member header to emit (GzBuilder::into_header(), writer.rs:341-357)
+    ~dfl_encoder() {
+        if (ctx.ok) {
+            cudaStreamSynchronize(ctx.stream);
+            cudaStreamSynchronize(ctx.copy_stream);
+        }
+        for (StreamBuf& b : sb) dev_free(b.d);
+        if (in_ev) cudaEventDestroy(in_ev);
+        if (hist_ev) cudaEventDestroy(hist_ev);
+    }
 };
 
 namespace {
 
 constexpr size_t kOpenTail = kMaxMatch + 1;   // bytes an open piece leaves unparsed
+enum { kPieceOpen = 0 };   // besides DFL_FLUSH_SYNC / DFL_FLUSH_FINISH
 
-// Adler-32 / CRC-32 of data[sum_upto..to) on the device, folded into e->adler / e->crc.
-int encoder_fold_checksum(dfl_encoder* e, size_t to) {
-    if (e->wrap == DFL_RAW) { e->sum_upto = to; return DFL_OK; }
-    const size_t from = e->sum_upto;
-    if (to <= from) return DFL_OK;
-    Context& c = e->ctx;
-    int rc = c.init();
+int encoder_init(dfl_encoder* e) {
+    int rc = e->ctx.init();
     if (rc) return rc;
-    size_t len = to - from;
-    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, e->data.size() + 64))) return rc;
-    if ((rc = c.ensure(len, false, false))) return rc;
-    CK(cudaMemcpyAsync(c.d_in, e->data.data() + from, len, cudaMemcpyHostToDevice, c.stream));
-    if (e->wrap == DFL_ZLIB) CK(launch_adler32(c.d_in, len, c.buf, c.stream));
-    else CK(launch_crc32(c.d_in, len, c.buf, c.stream));
+    if (!e->in_ev) CK(cudaEventCreateWithFlags(&e->in_ev, cudaEventDisableTiming));
+    if (!e->hist_ev) CK(cudaEventCreateWithFlags(&e->hist_ev, cudaEventDisableTiming));
+    return DFL_OK;
+}
+
+// Room for `more` further appended bytes in the fill buffer (grown geometrically up to one piece).
+int encoder_room(dfl_encoder* e, size_t more) {
+    StreamBuf& b = e->sb[e->f];
+    const size_t need = b.end() + more + kStreamSlack;
+    if (b.cap >= need) return DFL_OK;
+    size_t full = kStreamReserve + 16 + e->piece_bytes + kStreamSlack;
+    size_t want = b.cap ? b.cap * 2 : kStreamReserve + (1u << 20);
+    if (want < need) want = need;
+    if (want > full && full >= need) want = full;
+    Context& c = e->ctx;
+    CK(cudaStreamSynchronize(c.copy_stream));
+    CK(cudaStreamSynchronize(c.stream));
+    uint8_t* q = nullptr;
+    int rc = dev_alloc(q, want);
+    if (rc) return rc;
+    if (b.d) {
+        const size_t from = e->busy ? b.org : b.lo;   // the history arrives later while a piece is running
+        if (b.end() > from) CK(cudaMemcpy(q + from, b.d + from, b.end() - from, cudaMemcpyDeviceToDevice));
+        dev_free(b.d);
+    }
+    b.d = q;
+    b.cap = want;
+    return DFL_OK;
+}
+
+bool host_pointer_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Append host bytes to the fill buffer.  Returns once `src` may be reused.
+int encoder_append(dfl_encoder* e, const uint8_t* src, size_t len) {
+    if (!len) return DFL_OK;
+    int rc = encoder_init(e);
+    if (rc) return rc;
+    if ((rc = encoder_room(e, len))) return rc;
+    StreamBuf& b = e->sb[e->f];
+    Context& c = e->ctx;
+    // a pageable source is staged by the driver before the call returns; a pinned one is read later, by the DMA
+    const bool pageable = host_pointer_is_pageable(src);
+    CK(cudaMemcpyAsync(b.d + b.end(), src, len, cudaMemcpyHostToDevice, c.copy_stream));
+    if (!pageable) CK(cudaStreamSynchronize(c.copy_stream));
+    b.new_n += len;
+    return DFL_OK;
+}
+
+int encoder_push_pending(dfl_encoder* e) {
+    if (e->pend.empty()) return DFL_OK;
+    int rc = encoder_append(e, e->pend.data(), e->pend.size());
+    e->pend.clear();
+    return rc;
+}
+
+// Adler-32 / CRC-32 of stream bytes [sum_off, to) -- all inside buffer b -- folded into e->adler / e->crc.
+// Runs on the compute stream and waits for it.
+int encoder_fold_checksum(dfl_encoder* e, const StreamBuf& b, uint64_t to) {
+    if (e->wrap == DFL_RAW || to <= e->sum_off) { if (to > e->sum_off) e->sum_off = to; return DFL_OK; }
+    Context& c = e->ctx;
+    const size_t len = (size_t)(to - e->sum_off);
+    int rc = c.ensure(len, false, false);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->in_ev, c.copy_stream));
+    CK(cudaStreamWaitEvent(c.stream, e->in_ev, 0));
+    const uint8_t* src = b.d + b.pos(e->sum_off);
+    if (e->wrap == DFL_ZLIB) CK(launch_adler32(src, len, c.buf, c.stream));
+    else CK(launch_crc32(src, len, c.buf, c.stream));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
     // arithmetic on two device results
     if (e->wrap == DFL_ZLIB) e->adler = adler32_combine(e->adler, c.h_meta->adler, len);
     else e->crc = crc32_combine(e->crc, c.h_meta->crc, len);
-    e->sum_upto = to;
+    e->sum_off = to;
     return DFL_OK;
 }
 
-enum { kPieceOpen = 0 };   // besides DFL_FLUSH_SYNC / DFL_FLUSH_FINISH
-
-int encoder_emit(dfl_encoder* e, int mode) {
+// Queue the pipeline for everything in the fill buffer; writes continue in the other buffer.
+int encoder_issue(dfl_encoder* e, int mode) {
     Context& c = e->ctx;
-    int rc = c.init();
-    if (rc) return rc;
-    const size_t n = e->data.size();
-    const size_t begin = e->parse_pos;
+    StreamBuf& x = e->sb[e->f];
     const bool open = (mode == kPieceOpen);
-    if (open && n < begin + kOpenTail + 1) return DFL_OK;   // not enough look-ahead to decide anything yet
-    if ((rc = encoder_fold_checksum(e, n))) return rc;
-    if ((rc = c.ensure_stage(c.d_in, c.d_in_cap, n + 64))) return rc;
-    const size_t coded_from = (!e->carry_tok.empty() && e->carry_in < begin) ? e->carry_in : begin;
-    size_t bound = dfl_bound(n - coded_from, e->wrap) + e->gz_hdr.size() + 64;
+    const size_t n = x.end() - x.lo;
+    const size_t begin = x.pos(e->parse_off) - x.lo;
+    const size_t coded_from = (!e->carry_tok.empty() && e->carry_off < e->parse_off) ? x.pos(e->carry_off) - x.lo : begin;
+    int rc;
+    if (!x.d && (rc = encoder_room(e, 0))) return rc;   // an empty stream still needs a valid pointer
+    const size_t bound = dfl_bound(n - coded_from, e->wrap) + e->gz_hdr.size() + 64;
     if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
-    if (n) CK(cudaMemcpyAsync(c.d_in, e->data.data(), n, cudaMemcpyHostToDevice, c.stream));
-    uint32_t hdr = 0;
-    if (!e->header_written) hdr = wrap_header_bytes(e->wrap, e->gz_hdr.size());
+    CK(cudaEventRecord(e->in_ev, c.copy_stream));
+    CK(cudaStreamWaitEvent(c.stream, e->in_ev, 0));
+    const uint32_t hdr = e->header_written ? 0u : wrap_header_bytes(e->wrap, e->gz_hdr.size());
     PieceIn pin;
     pin.init_key = e->parse_key;
     pin.parse_end = open ? (uint32_t)(n - kOpenTail) : 0u;
     pin.open_piece = open ? 1 : 0;
     pin.h_carry_tok = e->carry_tok.data();
     pin.n_carry_tok = (uint32_t)e->carry_tok.size();
-    pin.carry_in_pos = (uint32_t)e->carry_in;
+    pin.carry_in_pos = (uint32_t)(e->carry_tok.empty() ? begin : x.pos(e->carry_off) - x.lo);
     pin.bits_n = e->bits_n;
     pin.bits_v = e->bits_v;
-    size_t produced = 0;
-    // The trailer is appended here from the running checksum, so the kernels see wrap == RAW
+    // The trailer is appended on the host from the running checksum, so the kernels see wrap == RAW
     // unless the header still has to be written.
     t_piece_in = &pin;
-    rc = run_pipeline(c, c.stream, c.d_in, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr, mode == DFL_FLUSH_FINISH ? 1 : 0,
-                      mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, &produced, nullptr, 0, 0,
-                      e->gz_hdr.empty() ? nullptr : e->gz_hdr.data());
+    g_launch_count = 0;
+    StageTimer tm(c.stream, false);
+    rc = issue_pipeline(c, c.stream, tm, x.d + x.lo, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr,
+                        mode == DFL_FLUSH_FINISH ? 1 : 0, mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, nullptr, 0, 0,
+                        e->gz_hdr.empty() ? nullptr : e->gz_hdr.data());
     t_piece_in = nullptr;
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    e->busy = true;
+    e->busy_n = n;
+    e->busy_begin = begin;
+    e->busy_hdr = hdr;
+    // the other buffer takes over; its origin is congruent to this one's end, which keeps the handed-over
+    // history 16-byte aligned whatever its length (see encoder_settle)
+    StreamBuf& y = e->sb[1 - e->f];
+    y.org = kStreamReserve + (x.end() & 15u);
+    y.off_org = x.off_org + x.new_n;
+    y.lo = y.org;
+    y.new_n = 0;
+    e->f = 1 - e->f;
+    return DFL_OK;
+}
+
+// Wait for the piece in flight, collect its bytes and state, hand its tail to the fill buffer.
+int encoder_settle(dfl_encoder* e, int mode) {
+    if (!e->busy) return DFL_OK;
+    Context& c = e->ctx;
+    StreamBuf& x = e->sb[1 - e->f];
+    StreamBuf& y = e->sb[e->f];
+    const bool open = (mode == kPieceOpen);
+    e->busy = false;
+    size_t produced = 0;
+    int rc = finish_pipeline(c, c.stream, e->busy_n, e->busy_begin, &produced);
     if (rc) return rc;
     const DevMeta m = *c.h_meta;
+    const uint32_t hdr = e->busy_hdr;
     // bytes that are complete: all of them for a closed piece, all but the last partial one for an open piece
     const size_t full = open ? (size_t)(m.stream_bits >> 3) : (size_t)m.stream_bytes;
     const uint32_t left_bits = open ? (uint32_t)(m.stream_bits & 7ull) : 0u;
     const size_t fetch = hdr + full + (left_bits ? 1 : 0);
-    const size_t old = e->out.size();
-    e->out.resize(old + fetch);
-    if (fetch) CK(cudaMemcpyAsync(e->out.data() + old, c.d_out, fetch, cudaMemcpyDeviceToHost, c.stream));
+    if (!e->out.reserve(e->out.n + fetch + 16)) return DFL_E_NOMEM;
+    if (fetch) CK(cudaMemcpyAsync(e->out.p + e->out.n, c.d_out, fetch, cudaMemcpyDeviceToHost, c.stream));
     // tokens behind the last complete block wait for the next piece
     const size_t coded = (size_t)m.n_blocks * kBlockTokens;
     const size_t rem = open && m.n_tokens > coded ? (size_t)(m.n_tokens - coded) : 0;
     std::vector<uint32_t> next_carry(rem);
     if (rem) CK(cudaMemcpyAsync(next_carry.data(), c.buf.tok + coded, rem * 4, cudaMemcpyDeviceToHost, c.stream));
+    const uint64_t x_lo_off = x.off_org - (uint64_t)(x.org - x.lo);   // stream offset of x.d[x.lo]
+    const uint64_t x_end_off = x.off_org + x.new_n;
+    if ((rc = encoder_fold_checksum(e, x, x_end_off))) return rc;   // ends with a wait for the stream
     CK(cudaStreamSynchronize(c.stream));
+    e->out.n += fetch;
     if (left_bits) {
-        e->bits_v = e->out.back();
-        e->out.pop_back();
+        e->bits_v = e->out.p[e->out.n - 1];
+        e->out.n--;
     } else {
         e->bits_v = 0;
     }
     e->bits_n = left_bits;
     e->carry_tok.swap(next_carry);
-    e->carry_in = open ? (size_t)m.in_coded_end : n;
     e->header_written = true;
     if (open) {
-        e->parse_pos = m.end_pos;
+        e->parse_off = x_lo_off + m.end_pos;
         e->parse_key = m.end_key;
+        e->carry_off = x_lo_off + m.in_coded_end;
     } else {
-        e->parse_pos = n;
+        e->parse_off = x_end_off;
         e->parse_key = 0;
+        e->carry_off = x_end_off;
     }
+    // keep the dictionary of the next position to parse and the input of the carried tokens: they move in
+    // front of the bytes written since.  y.org was chosen congruent to x.end(), the kept range starts on a
+    // 16-byte boundary of x (x.lo is one), so it lands on one in y.
+    uint64_t keep_off = e->parse_off - x_lo_off > kWindow ? e->parse_off - kWindow : x_lo_off;
+    if (!e->carry_tok.empty() && e->carry_off < keep_off) keep_off = e->carry_off;
+    const size_t keep_pos = x.pos(keep_off) & ~(size_t)15;
+    const size_t hist = x.end() - keep_pos;
+    if (hist > y.org || keep_pos < x.lo) {
+        t_cuda_err = "stream history exceeds its reserve";
+        return DFL_E_INTERNAL;
+    }
+    y.lo = y.org - hist;
+    if (hist) {
+        if (!y.d && (rc = encoder_room(e, 0))) return rc;
+        CK(cudaMemcpyAsync(y.d + y.lo, x.d + keep_pos, hist, cudaMemcpyDeviceToDevice, c.stream));
+        // x is the next buffer to be written to: not before this copy has read it
+        CK(cudaEventRecord(e->hist_ev, c.stream));
+        CK(cudaStreamWaitEvent(c.copy_stream, e->hist_ev, 0));
+    }
+    return DFL_OK;
+}
+
+int encoder_emit(dfl_encoder* e, int mode) {
+    int rc = encoder_init(e);
+    if (rc) return rc;
+    if ((rc = encoder_settle(e, kPieceOpen))) return rc;
+    if ((rc = encoder_push_pending(e))) return rc;
+    const StreamBuf& x = e->sb[e->f];
+    const bool open = (mode == kPieceOpen);
+    if (open && x.end() < x.pos(e->parse_off) + kOpenTail + 1) return DFL_OK;   // not enough look-ahead to decide anything yet
+    if ((rc = encoder_issue(e, mode))) return rc;
+    if (open) return DFL_OK;   // settled by whoever comes next
+    if ((rc = encoder_settle(e, mode))) return rc;
     if (mode == DFL_FLUSH_FINISH) {
+        if (!e->out.reserve(e->out.n + 8)) return DFL_E_NOMEM;
         if (e->wrap == DFL_ZLIB) {   // lib.rs:192-196 / writer.rs:235-245: Adler-32, big endian
-            uint32_t a = e->adler;
-            uint8_t t[4] = {(uint8_t)(a >> 24), (uint8_t)(a >> 16), (uint8_t)(a >> 8), (uint8_t)a};
-            e->out.insert(e->out.end(), t, t + 4);
+            const uint32_t a = e->adler;
+            const uint8_t t[4] = {(uint8_t)(a >> 24), (uint8_t)(a >> 16), (uint8_t)(a >> 8), (uint8_t)a};
+            memcpy(e->out.p + e->out.n, t, 4);
+            e->out.n += 4;
         } else if (e->wrap == DFL_GZIP) {   // writer.rs:408-426: CRC-32 and the input size, little endian
-            uint32_t v[2] = {e->crc, (uint32_t)(e->total_in & 0xffffffffull)};
-            for (uint32_t x : v)
-                for (int k = 0; k < 4; k++) e->out.push_back((uint8_t)(x >> (8 * k)));
+            const uint32_t v[2] = {e->crc, (uint32_t)(e->total_in & 0xffffffffull)};
+            for (uint32_t x32 : v)
+                for (int k = 0; k < 4; k++) e->out.p[e->out.n++] = (uint8_t)(x32 >> (8 * k));
         }
         e->finished = true;
-    }
-    // keep the dictionary of the next position to parse and the input of the carried tokens
-    size_t keep = e->parse_pos > kWindow ? e->parse_pos - kWindow : 0;
-    if (!e->carry_tok.empty() && e->carry_in < keep) keep = e->carry_in;
-    if (keep > 0) {
-        e->data.erase(e->data.begin(), e->data.begin() + keep);
-        e->parse_pos -= keep;
-        e->carry_in -= keep;
-        e->sum_upto -= keep;
     }
     return DFL_OK;
 }
@@ -1075,24 +1251,32 @@ extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const 
 extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, size_t* consumed) {
     if (!e || (!buf && n)) return DFL_E_ARG;
     if (e->finished) return DFL_E_STATE;
+    int rc = DFL_OK;
     size_t done = 0;
     while (done < n) {
-        // take at most one piece at a time, so that neither the host buffer nor a device call grows without bound
-        const size_t pending = e->data.size() - e->parse_pos;
-        const size_t room = e->piece_bytes > pending ? e->piece_bytes - pending : 0;
+        // take at most one piece at a time, so that neither buffer nor a device call grows without bound
+        const size_t have = e->sb[e->f].new_n + e->pend.size();
+        const size_t room = e->piece_bytes > have ? e->piece_bytes - have : 0;
         const size_t take = (n - done) < room ? (n - done) : room;
         if (take) {
-            try {
-                e->data.insert(e->data.end(), buf + done, buf + done + take);
-            } catch (const std::bad_alloc&) {
-                if (consumed) *consumed = done;
-                return done ? DFL_OK : DFL_E_NOMEM;
+            if (take < kPendDirect) {
+                try {
+                    e->pend.insert(e->pend.end(), buf + done, buf + done + take);
+                } catch (const std::bad_alloc&) {
+                    if (consumed) *consumed = done;
+                    return done ? DFL_OK : DFL_E_NOMEM;
+                }
+                rc = e->pend.size() >= kPendBytes ? encoder_push_pending(e) : DFL_OK;
+            } else {
+                rc = encoder_push_pending(e);
+                if (rc == DFL_OK) rc = encoder_append(e, buf + done, take);
             }
+            if (rc) { if (consumed) *consumed = done; return rc; }
             e->total_in += take;
             done += take;
         }
-        if (e->data.size() - e->parse_pos >= e->piece_bytes) {
-            int rc = encoder_emit(e, kPieceOpen);
+        if (e->sb[e->f].new_n + e->pend.size() >= e->piece_bytes) {
+            rc = encoder_emit(e, kPieceOpen);
             if (rc) { if (consumed) *consumed = done; return rc; }
         }
     }
@@ -1108,16 +1292,21 @@ extern "C" int dfl_encoder_flush(dfl_encoder* e, int mode) {
 
 extern "C" int dfl_encoder_take_output(dfl_encoder* e, const uint8_t** p, size_t* len) {
     if (!e || !p || !len) return DFL_E_ARG;
-    *p = e->out.data() + e->out_pos;
-    *len = e->out.size() - e->out_pos;
+    // bytes of a piece still running become visible once it is settled; do that here if it costs no wait
+    if (e->busy && cudaStreamQuery(e->ctx.stream) == cudaSuccess) {
+        int rc = encoder_settle(e, kPieceOpen);
+        if (rc) return rc;
+    }
+    *p = e->out.p + e->out_pos;
+    *len = e->out.n - e->out_pos;
     return DFL_OK;
 }
 
 extern "C" void dfl_encoder_advance_output(dfl_encoder* e, size_t n) {
     if (!e) return;
     e->out_pos += n;
-    if (e->out_pos >= e->out.size()) {
-        e->out.clear();
+    if (e->out_pos >= e->out.n) {
+        e->out.n = 0;
         e->out_pos = 0;
     }
 }
@@ -1130,7 +1319,9 @@ extern "C" int dfl_encoder_set_piece_bytes(dfl_encoder* e, size_t bytes) {
 
 extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
     if (!e || e->wrap == DFL_RAW) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
-    if (encoder_fold_checksum(e, e->data.size()) != DFL_OK) return 0;
+    if (encoder_init(e) != DFL_OK || encoder_settle(e, kPieceOpen) != DFL_OK || encoder_push_pending(e) != DFL_OK) return 0;
+    const StreamBuf& b = e->sb[e->f];
+    if (encoder_fold_checksum(e, b, b.off_org + b.new_n) != DFL_OK) return 0;
     return e->wrap == DFL_ZLIB ? e->adler : e->crc;
 }
 
@@ -1140,17 +1331,23 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
         int rc = encoder_emit(e, DFL_FLUSH_FINISH);   // output_all() (writer.rs:112-115,218-223)
         if (rc) return rc;
     }
-    e->data.clear();
-    e->parse_pos = 0;
+    for (StreamBuf& b : e->sb) {
+        b.org = b.lo = kStreamReserve;
+        b.off_org = 0;
+        b.new_n = 0;
+    }
+    e->busy = false;
+    e->pend.clear();
+    e->parse_off = 0;
     e->parse_key = 0;
     e->carry_tok.clear();
-    e->carry_in = 0;
+    e->carry_off = 0;
     e->bits_n = e->bits_v = 0;
     e->header_written = false;
     e->finished = false;
     e->adler = 1;
     e->crc = 0;
-    e->sum_upto = 0;
+    e->sum_off = 0;
     e->total_in = 0;
     // reset() installs the default header, reset_with_builder() the caller's (writer.rs:394-406)
     e->gz_hdr.clear();
