@@ -11,6 +11,11 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <vector>
 
 #include "../../include/deflate_b200.h"
@@ -83,23 +88,144 @@ inline std::vector<size_t> plan_slices(size_t n, bool long_kernels) {
     lo.push_back(n);
     return lo;
 }
-struct InputArrival {
-    std::vector<cudaEvent_t>* ev;
-    std::vector<size_t> lo;    // slice boundaries, n_slices + 1 of them
-    size_t n_slices;
-    const uint8_t* h_src;      // host source; slice k is copied by feed(k) right before it is waited for, so
-    uint8_t* d_dst;            // that with pageable memory (a blocking, staged copy) the kernels of slice k
-    size_t n;                  // run while slice k + 1 is being staged
-    cudaStream_t copy_stream;
-    cudaError_t feed(size_t k) const {
-        cudaError_t e = cudaMemcpyAsync(d_dst + lo[k], h_src + lo[k], lo[k + 1] - lo[k], cudaMemcpyHostToDevice, copy_stream);
-        if (e != cudaSuccess) return e;
-        return cudaEventRecord((*ev)[k], copy_stream);
+
+// ---- pageable host memory <-> device, staged by this library -------------------------------------------------
+// cudaMemcpyAsync on pageable memory is a single-threaded staged copy (measured on the B200 hosts: 6-10 GB/s in,
+// 4-5 GB/s out, against 55 GB/s for pinned memory) and would bound every host-facing call.  Large pageable
+// transfers go through a ring of pinned slots instead: a few worker threads move the bytes between the caller's
+// memory and the slots in parallel, the DMA engine moves the slots.  The workers only memcpy -- every CUDA call
+// stays on the calling thread.
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool();   // lives as long as the process: its threads never outlive it
+        return *p;
     }
-    size_t slices_covering(size_t upto) const {   // how many leading slices hold [0, upto)
-        size_t m = 0;
-        while (m < n_slices && lo[m] < upto) m++;
-        return m;
+    void submit(void* dst, const void* src, size_t n, std::atomic<int>* done) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(Job{dst, src, n, done});
+        }
+        cv_job_.notify_one();
+    }
+    void wait(const std::atomic<int>* done) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return done->load(std::memory_order_acquire) != 0; });
+    }
+
+private:
+    struct Job { void* dst; const void* src; size_t n; std::atomic<int>* done; };
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = hw >= 12 ? 4 : (hw >= 6 ? 3 : (hw >= 3 ? 2 : 1));
+        if (const char* e = getenv("DFL_COPY_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 32) n = (unsigned)v; }
+        for (unsigned i = 0; i < n; i++) std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_job_.wait(lk, [&] { return !q_.empty(); });
+                j = q_.front();
+                q_.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                j.done->store(1, std::memory_order_release);
+            }
+            cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_job_, cv_done_;
+    std::deque<Job> q_;
+};
+
+constexpr size_t kStageSlot = 1u << 20;     // bytes per pinned slot
+constexpr size_t kStageSlots = 32;          // slots per direction
+constexpr size_t kStageAhead = 16;          // device-to-host: DMAs kept in flight in front of the memcpy jobs
+constexpr size_t kStageMin = 2u << 20;      // smaller pageable transfers are left to the driver
+
+inline bool host_pointer_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+struct Stager {   // one per Context, allocated on first use
+    uint8_t* ring[2] = {nullptr, nullptr};   // [0] host-to-device, [1] device-to-host
+    cudaEvent_t ev[2][kStageSlots] = {};
+    uint64_t seq = 0;                         // host-to-device slots are handed out round robin across calls
+    bool ok = false;
+    int init() {
+        if (ok) return DFL_OK;
+        for (int d = 0; d < 2; d++) {
+            CK(cudaMallocHost(reinterpret_cast<void**>(&ring[d]), kStageSlot * kStageSlots));
+            for (auto& e : ev[d]) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        ok = true;
+        return DFL_OK;
+    }
+    ~Stager() {
+        for (int d = 0; d < 2; d++) {
+            if (ring[d]) cudaFreeHost(ring[d]);
+            for (auto e : ev[d]) if (e) cudaEventDestroy(e);
+        }
+    }
+    // Returns once h_src has been read completely; the last DMAs may still be running on `st`.
+    int h2d(uint8_t* d_dst, const uint8_t* h_src, size_t len, cudaStream_t st) {
+        int rc = init();
+        if (rc) return rc;
+        CopyPool& pool = CopyPool::get();
+        const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
+        std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_chunks]);
+        for (size_t i = 0; i < n_chunks; i++) done[i].store(0, std::memory_order_relaxed);
+        size_t enq = 0;   // chunks whose DMA has been queued (in order)
+        auto chunk_len = [&](size_t i) { return (i + 1 == n_chunks) ? len - i * kStageSlot : kStageSlot; };
+        auto queue_dma = [&](size_t i) -> int {
+            const size_t slot = (size_t)((seq + i) % kStageSlots);
+            CK(cudaMemcpyAsync(d_dst + i * kStageSlot, ring[0] + slot * kStageSlot, chunk_len(i), cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ev[0][slot], st));
+            return DFL_OK;
+        };
+        for (size_t i = 0; i < n_chunks; i++) {
+            while (enq < i && done[enq].load(std::memory_order_acquire)) { if ((rc = queue_dma(enq))) return rc; enq++; }
+            if (i >= kStageSlots)   // the slot's previous chunk of this call must be on its way before its event means anything
+                while (enq <= i - kStageSlots) { pool.wait(&done[enq]); if ((rc = queue_dma(enq))) return rc; enq++; }
+            const size_t slot = (size_t)((seq + i) % kStageSlots);
+            CK(cudaEventSynchronize(ev[0][slot]));   // the DMA that last read this slot (this call or an earlier one)
+            pool.submit(ring[0] + slot * kStageSlot, h_src + i * kStageSlot, chunk_len(i), &done[i]);
+        }
+        while (enq < n_chunks) { pool.wait(&done[enq]); if ((rc = queue_dma(enq))) return rc; enq++; }
+        seq += n_chunks;
+        return DFL_OK;
+    }
+    // Blocking: h_dst is complete on return.  d_src must be ready in stream order on `st`.
+    int d2h(uint8_t* h_dst, const uint8_t* d_src, size_t len, cudaStream_t st) {
+        int rc = init();
+        if (rc) return rc;
+        CopyPool& pool = CopyPool::get();
+        const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
+        std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_chunks]);
+        for (size_t i = 0; i < n_chunks; i++) done[i].store(0, std::memory_order_relaxed);
+        auto chunk_len = [&](size_t i) { return (i + 1 == n_chunks) ? len - i * kStageSlot : kStageSlot; };
+        for (size_t i = 0; i < n_chunks + kStageAhead; i++) {
+            if (i < n_chunks) {
+                if (i >= kStageSlots) pool.wait(&done[i - kStageSlots]);   // the slot has been emptied
+                const size_t slot = i % kStageSlots;
+                CK(cudaMemcpyAsync(ring[1] + slot * kStageSlot, d_src + i * kStageSlot, chunk_len(i), cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(ev[1][slot], st));
+            }
+            if (i >= kStageAhead && i - kStageAhead < n_chunks) {
+                const size_t j = i - kStageAhead, slot = j % kStageSlots;
+                CK(cudaEventSynchronize(ev[1][slot]));
+                pool.submit(h_dst + j * kStageSlot, ring[1] + slot * kStageSlot, chunk_len(j), &done[j]);
+            }
+        }
+        for (size_t i = 0; i < n_chunks; i++) pool.wait(&done[i]);
+        return DFL_OK;
     }
 };
 
@@ -119,7 +245,32 @@ struct Context {
     uint32_t* d_tok_in = nullptr;   // staging for dfl_encode_tokens
     size_t d_tok_cap = 0;
     DevMeta* h_meta = nullptr;  // pinned
+    std::unique_ptr<Stager> stager;
     bool ok = false;
+
+    // Host memory -> device on `st`; returns once `src` may be reused (pinned memory: only if wait_pinned).
+    int copy_in(uint8_t* d_dst, const uint8_t* src, size_t len, cudaStream_t st, bool wait_pinned) {
+        if (!len) return DFL_OK;
+        const bool pageable = host_pointer_is_pageable(src);
+        if (pageable && len >= kStageMin) {
+            if (!stager) stager.reset(new Stager());
+            return stager->h2d(d_dst, src, len, st);
+        }
+        CK(cudaMemcpyAsync(d_dst, src, len, cudaMemcpyHostToDevice, st));   // pageable: staged by the driver before it returns
+        if (!pageable && wait_pinned) CK(cudaStreamSynchronize(st));
+        return DFL_OK;
+    }
+    // Device -> host memory in stream order on `st`; blocking.
+    int copy_out(uint8_t* dst, const uint8_t* d_src, size_t len, cudaStream_t st) {
+        if (!len) return DFL_OK;
+        if (len >= kStageMin && host_pointer_is_pageable(dst)) {
+            if (!stager) stager.reset(new Stager());
+            return stager->d2h(dst, d_src, len, st);
+        }
+        CK(cudaMemcpyAsync(dst, d_src, len, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return DFL_OK;
+    }
 
     int init() {
         if (ok) return DFL_OK;
@@ -221,6 +372,28 @@ struct Context {
         if (rc) return rc;
         cap = c;
         return DFL_OK;
+    }
+};
+
+struct InputArrival {
+    std::vector<cudaEvent_t>* ev;
+    std::vector<size_t> lo;    // slice boundaries, n_slices + 1 of them
+    size_t n_slices;
+    const uint8_t* h_src;      // host source; slice k is copied by feed(k) right before it is waited for, so
+    uint8_t* d_dst;            // that with pageable memory (a blocking, staged copy) the kernels of slice k
+    size_t n;                  // run while slice k + 1 is being staged
+    cudaStream_t copy_stream;
+    Context* ctx;
+    int feed(size_t k) const {
+        int rc = ctx->copy_in(d_dst + lo[k], h_src + lo[k], lo[k + 1] - lo[k], copy_stream, false);
+        if (rc) return rc;
+        CK(cudaEventRecord((*ev)[k], copy_stream));
+        return DFL_OK;
+    }
+    size_t slices_covering(size_t upto) const {   // how many leading slices hold [0, upto)
+        size_t m = 0;
+        while (m < n_slices && lo[m] < upto) m++;
+        return m;
     }
 };
 
@@ -333,7 +506,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
             // (and the 272 bytes of look-ahead behind it) are on the device
             uint32_t w_sorted = w_sort0, w_matched = w_match0;
             for (size_t k = 0; k < arrival->n_slices; k++) {
-                CK(arrival->feed(k));
+                { int frc = arrival->feed(k); if (frc) return frc; }
                 CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0));
                 const size_t have = (k + 1 == arrival->n_slices) ? n : arrival->lo[k + 1];
                 uint32_t w_ok = (have >= n) ? w_end : (uint32_t)((have - 272) / kWindow);
@@ -346,14 +519,14 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
             tm.mark("window_sort+match");
         } else {
             if (arrival)
-                for (size_t k = 0; k < arrival->n_slices; k++) { CK(arrival->feed(k)); CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
+                for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
             CK(launch_window_sort(j, b, st, w_sort0, w_end));
             tm.mark("window_sort");
             CK(launch_match(j, b, st, w_match0, w_end));
             tm.mark("match");
         }
     } else if (arrival) {
-        for (size_t k = 0; k < arrival->n_slices; k++) { CK(arrival->feed(k)); CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
+        for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
     }
     if (wrap == DFL_ZLIB && final_block && !stop_after_tokens) {
         CK(launch_adler32(d_in + begin, n - begin, b, st));
@@ -527,7 +700,7 @@ static int compress_pieces(Context& c, cudaStream_t st, const uint8_t* d_in, siz
     auto feed_to = [&](size_t upto) -> int {   // issue the host-to-device slices covering [0, upto)
         if (!io.arrival) return DFL_OK;
         const size_t want = io.arrival->slices_covering(upto);
-        for (; fed < want && fed < io.arrival->n_slices; fed++) CK(io.arrival->feed(fed));
+        for (; fed < want && fed < io.arrival->n_slices; fed++) { int frc = io.arrival->feed(fed); if (frc) return frc; }
         return DFL_OK;
     };
     for (uint32_t k = 0;; k++) {
@@ -697,7 +870,7 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     }();
     // host -> device in slices on a second stream; the pipeline's first two stages start on a
     // slice as soon as it has landed (writer.rs callers pay PCIe: SURVEY 8(f) rank 1)
-    InputArrival arrival{&c.copy_ev, {}, 0, in, c.d_in, n, c.copy_stream};
+    InputArrival arrival{&c.copy_ev, {}, 0, in, c.d_in, n, c.copy_stream, &c};
     arrival.lo = plan_slices(n, opt->max_hash_checks >= 16 && !(host_piece && n >= 2 * host_piece));
     arrival.n_slices = arrival.lo.size() - 1;
     while (c.copy_ev.size() < arrival.n_slices) {
@@ -719,9 +892,7 @@ extern "C" int dfl_compress(const uint8_t* in, size_t n, const dfl_options* opt,
     if (rc) return rc;
     *out_len = produced;
     if (produced > out_cap) return DFL_E_OVERFLOW;
-    CK(cudaMemcpyAsync(out, c.d_out, produced, cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-    return DFL_OK;
+    return c.copy_out(out, c.d_out, produced, c.stream);
 }
 
 extern "C" int dfl_compress_device_piece(const void* d_in, size_t n_total, size_t dict_len, const dfl_options* opt, int flush_mode,
@@ -963,15 +1134,34 @@ struct StreamBuf {
 
 }  // namespace
 
+namespace {
+// Device resources of handles that were freed: streams, the pipeline's scratch, the two stream buffers.  A new
+// handle on the same device takes them over instead of allocating (cudaMalloc/cudaFree of a few GiB cost more than
+// encoding a piece; image encoders create one handle per picture).
+struct HandleRes {
+    std::unique_ptr<Context> ctx;
+    uint8_t* d[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    int device = -1;
+};
+constexpr size_t kHandlePoolMax = 4;
+std::mutex g_handle_pool_mu;
+std::vector<HandleRes> g_handle_pool;
+}  // namespace
+
 struct dfl_encoder {
     dfl_options opt;
     int wrap;
-    Context ctx;                 // per-handle streams and scratch
+    std::unique_ptr<Context> ctx;   // streams and scratch, taken from / returned to a pool (encoder_init, ~dfl_encoder)
+    int device = -1;
     StreamBuf sb[2];
     int f = 0;                   // sb[f] receives writes
     bool busy = false;           // an open piece is running on sb[1 - f]
     size_t busy_n = 0, busy_begin = 0;
     uint32_t busy_hdr = 0;
+    uint64_t n_issued = 0;       // pieces issued so far; piece k writes into output scratch k & 1
+    const uint8_t* bulk_src = nullptr;   // settled piece whose bytes are still in its scratch buffer
+    size_t bulk_n = 0;
     cudaEvent_t in_ev = nullptr;     // input copies issued so far are on the device (copy stream)
     cudaEvent_t hist_ev = nullptr;   // the latest history hand-over has left its source buffer (compute stream)
     std::vector<uint8_t> pend;   // small writes not yet sent to the device
@@ -990,10 +1180,23 @@ struct dfl_encoder {
     uint64_t total_in = 0;       // bytes accepted by write()
     size_t piece_bytes = 256u << 20;   // appended bytes that trigger an open piece
     std::vector<uint8_t> gz_hdr; // gzip member header to emit (GzBuilder::into_header(), writer.rs:341-357)
+    double t_append = 0, t_room = 0, t_wait = 0, t_small = 0, t_issue = 0, t_bulk = 0;   // host seconds (DFL_STREAM_TRACE)
     ~dfl_encoder() {
-        if (ctx.ok) {
-            cudaStreamSynchronize(ctx.stream);
-            cudaStreamSynchronize(ctx.copy_stream);
+        if (getenv("DFL_STREAM_TRACE"))
+            fprintf(stderr, "[dfl stream] pieces %llu: append %.1f ms (grow %.1f), wait for kernels %.1f, state %.1f, issue %.1f, bytes out %.1f\n",
+                    (unsigned long long)n_issued, 1e3 * t_append, 1e3 * t_room, 1e3 * t_wait, 1e3 * t_small, 1e3 * t_issue, 1e3 * t_bulk);
+        if (ctx && ctx->ok) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->d2h_stream);
+            std::lock_guard<std::mutex> lk(g_handle_pool_mu);
+            if (g_handle_pool.size() < kHandlePoolMax) {
+                HandleRes r;
+                r.ctx = std::move(ctx);
+                for (int i = 0; i < 2; i++) { r.d[i] = sb[i].d; r.cap[i] = sb[i].cap; sb[i].d = nullptr; }
+                r.device = device;
+                g_handle_pool.push_back(std::move(r));
+            }
         }
         for (StreamBuf& b : sb) dev_free(b.d);
         if (in_ev) cudaEventDestroy(in_ev);
@@ -1003,11 +1206,35 @@ struct dfl_encoder {
 
 namespace {
 
+struct HostTimer {   // adds the lifetime of the object to *acc
+    double* acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit HostTimer(double* a) : acc(a) {}
+    ~HostTimer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 constexpr size_t kOpenTail = kMaxMatch + 1;   // bytes an open piece leaves unparsed
 enum { kPieceOpen = 0 };   // besides DFL_FLUSH_SYNC / DFL_FLUSH_FINISH
 
 int encoder_init(dfl_encoder* e) {
-    int rc = e->ctx.init();
+    if (!e->ctx) {
+        int dev = -1;
+        if (device_count_cached() > 0) cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(g_handle_pool_mu);
+            for (size_t i = 0; i < g_handle_pool.size(); i++) {
+                if (g_handle_pool[i].device != dev) continue;
+                HandleRes r = std::move(g_handle_pool[i]);
+                g_handle_pool.erase(g_handle_pool.begin() + i);
+                e->ctx = std::move(r.ctx);
+                for (int k = 0; k < 2; k++) { e->sb[k].d = r.d[k]; e->sb[k].cap = r.cap[k]; }
+                break;
+            }
+        }
+        if (!e->ctx) e->ctx.reset(new Context());
+        e->device = dev;
+    }
+    int rc = e->ctx->init();
     if (rc) return rc;
     if (!e->in_ev) CK(cudaEventCreateWithFlags(&e->in_ev, cudaEventDisableTiming));
     if (!e->hist_ev) CK(cudaEventCreateWithFlags(&e->hist_ev, cudaEventDisableTiming));
@@ -1019,11 +1246,11 @@ int encoder_room(dfl_encoder* e, size_t more) {
     StreamBuf& b = e->sb[e->f];
     const size_t need = b.end() + more + kStreamSlack;
     if (b.cap >= need) return DFL_OK;
+    HostTimer ht(&e->t_room);
     size_t full = kStreamReserve + 16 + e->piece_bytes + kStreamSlack;
-    size_t want = b.cap ? b.cap * 2 : kStreamReserve + (1u << 20);
+    size_t want = b.cap ? full : kStreamReserve + (1u << 20);   // small streams stay small; the second request gets it all
     if (want < need) want = need;
-    if (want > full && full >= need) want = full;
-    Context& c = e->ctx;
+    Context& c = *e->ctx;
     CK(cudaStreamSynchronize(c.copy_stream));
     CK(cudaStreamSynchronize(c.stream));
     uint8_t* q = nullptr;
@@ -1039,24 +1266,18 @@ int encoder_room(dfl_encoder* e, size_t more) {
     return DFL_OK;
 }
 
-bool host_pointer_is_pageable(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
-    return a.type == cudaMemoryTypeUnregistered;
-}
-
 // Append host bytes to the fill buffer.  Returns once `src` may be reused.
 int encoder_append(dfl_encoder* e, const uint8_t* src, size_t len) {
     if (!len) return DFL_OK;
+    HostTimer ht(&e->t_append);
     int rc = encoder_init(e);
     if (rc) return rc;
     if ((rc = encoder_room(e, len))) return rc;
     StreamBuf& b = e->sb[e->f];
-    Context& c = e->ctx;
-    // a pageable source is staged by the driver before the call returns; a pinned one is read later, by the DMA
-    const bool pageable = host_pointer_is_pageable(src);
-    CK(cudaMemcpyAsync(b.d + b.end(), src, len, cudaMemcpyHostToDevice, c.copy_stream));
-    if (!pageable) CK(cudaStreamSynchronize(c.copy_stream));
+    Context& c = *e->ctx;
+    // pageable sources are staged (by this library's copy threads or, if small, by the driver) before this returns;
+    // a pinned one is read by the DMA itself, so wait for that
+    if ((rc = c.copy_in(b.d + b.end(), src, len, c.copy_stream, true))) return rc;
     b.new_n += len;
     return DFL_OK;
 }
@@ -1072,7 +1293,7 @@ int encoder_push_pending(dfl_encoder* e) {
 // Runs on the compute stream and waits for it.
 int encoder_fold_checksum(dfl_encoder* e, const StreamBuf& b, uint64_t to) {
     if (e->wrap == DFL_RAW || to <= e->sum_off) { if (to > e->sum_off) e->sum_off = to; return DFL_OK; }
-    Context& c = e->ctx;
+    Context& c = *e->ctx;
     const size_t len = (size_t)(to - e->sum_off);
     int rc = c.ensure(len, false, false);
     if (rc) return rc;
@@ -1092,7 +1313,8 @@ int encoder_fold_checksum(dfl_encoder* e, const StreamBuf& b, uint64_t to) {
 
 // Queue the pipeline for everything in the fill buffer; writes continue in the other buffer.
 int encoder_issue(dfl_encoder* e, int mode) {
-    Context& c = e->ctx;
+    HostTimer ht(&e->t_issue);
+    Context& c = *e->ctx;
     StreamBuf& x = e->sb[e->f];
     const bool open = (mode == kPieceOpen);
     const size_t n = x.end() - x.lo;
@@ -1101,7 +1323,10 @@ int encoder_issue(dfl_encoder* e, int mode) {
     int rc;
     if (!x.d && (rc = encoder_room(e, 0))) return rc;   // an empty stream still needs a valid pointer
     const size_t bound = dfl_bound(n - coded_from, e->wrap) + e->gz_hdr.size() + 64;
-    if ((rc = c.ensure_stage(c.d_out, c.d_out_cap, bound))) return rc;
+    // pieces alternate between two output buffers: the previous one's bytes leave theirs while this one runs
+    uint8_t*& scratch = (e->n_issued & 1u) ? c.d_out2 : c.d_out;
+    size_t& scratch_cap = (e->n_issued & 1u) ? c.d_out2_cap : c.d_out_cap;
+    if ((rc = c.ensure_stage(scratch, scratch_cap, bound))) return rc;
     CK(cudaEventRecord(e->in_ev, c.copy_stream));
     CK(cudaStreamWaitEvent(c.stream, e->in_ev, 0));
     const uint32_t hdr = e->header_written ? 0u : wrap_header_bytes(e->wrap, e->gz_hdr.size());
@@ -1120,10 +1345,11 @@ int encoder_issue(dfl_encoder* e, int mode) {
     g_launch_count = 0;
     StageTimer tm(c.stream, false);
     rc = issue_pipeline(c, c.stream, tm, x.d + x.lo, n, begin, &e->opt, (hdr ? e->wrap : DFL_RAW), hdr,
-                        mode == DFL_FLUSH_FINISH ? 1 : 0, mode == DFL_FLUSH_SYNC ? 1 : 0, c.d_out, c.d_out_cap, nullptr, 0, 0,
+                        mode == DFL_FLUSH_FINISH ? 1 : 0, mode == DFL_FLUSH_SYNC ? 1 : 0, scratch, scratch_cap, nullptr, 0, 0,
                         e->gz_hdr.empty() ? nullptr : e->gz_hdr.data());
     t_piece_in = nullptr;
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    e->n_issued++;
     e->busy = true;
     e->busy_n = n;
     e->busy_begin = begin;
@@ -1142,22 +1368,27 @@ int encoder_issue(dfl_encoder* e, int mode) {
 // Wait for the piece in flight, collect its bytes and state, hand its tail to the fill buffer.
 int encoder_settle(dfl_encoder* e, int mode) {
     if (!e->busy) return DFL_OK;
-    Context& c = e->ctx;
+    Context& c = *e->ctx;
     StreamBuf& x = e->sb[1 - e->f];
     StreamBuf& y = e->sb[e->f];
     const bool open = (mode == kPieceOpen);
     e->busy = false;
     size_t produced = 0;
-    int rc = finish_pipeline(c, c.stream, e->busy_n, e->busy_begin, &produced);
+    int rc;
+    {
+        HostTimer ht(&e->t_wait);
+        rc = finish_pipeline(c, c.stream, e->busy_n, e->busy_begin, &produced);
+    }
     if (rc) return rc;
+    HostTimer ht(&e->t_small);
     const DevMeta m = *c.h_meta;
     const uint32_t hdr = e->busy_hdr;
     // bytes that are complete: all of them for a closed piece, all but the last partial one for an open piece
     const size_t full = open ? (size_t)(m.stream_bits >> 3) : (size_t)m.stream_bytes;
     const uint32_t left_bits = open ? (uint32_t)(m.stream_bits & 7ull) : 0u;
-    const size_t fetch = hdr + full + (left_bits ? 1 : 0);
-    if (!e->out.reserve(e->out.n + fetch + 16)) return DFL_E_NOMEM;
-    if (fetch) CK(cudaMemcpyAsync(e->out.p + e->out.n, c.d_out, fetch, cudaMemcpyDeviceToHost, c.stream));
+    const uint8_t* scratch = ((e->n_issued - 1) & 1u) ? c.d_out2 : c.d_out;
+    uint8_t last_byte = 0;
+    if (left_bits) CK(cudaMemcpyAsync(&last_byte, scratch + hdr + full, 1, cudaMemcpyDeviceToHost, c.stream));
     // tokens behind the last complete block wait for the next piece
     const size_t coded = (size_t)m.n_blocks * kBlockTokens;
     const size_t rem = open && m.n_tokens > coded ? (size_t)(m.n_tokens - coded) : 0;
@@ -1167,13 +1398,9 @@ int encoder_settle(dfl_encoder* e, int mode) {
     const uint64_t x_end_off = x.off_org + x.new_n;
     if ((rc = encoder_fold_checksum(e, x, x_end_off))) return rc;   // ends with a wait for the stream
     CK(cudaStreamSynchronize(c.stream));
-    e->out.n += fetch;
-    if (left_bits) {
-        e->bits_v = e->out.p[e->out.n - 1];
-        e->out.n--;
-    } else {
-        e->bits_v = 0;
-    }
+    e->bulk_src = scratch;       // fetched by encoder_fetch_bulk, for an open piece after the next one is under way
+    e->bulk_n = hdr + full;
+    e->bits_v = left_bits ? last_byte : 0u;
     e->bits_n = left_bits;
     e->carry_tok.swap(next_carry);
     e->header_written = true;
@@ -1208,6 +1435,21 @@ int encoder_settle(dfl_encoder* e, int mode) {
     return DFL_OK;
 }
 
+// Bytes of the latest settled piece: device scratch -> e->out, on a stream of their own (the compute stream may
+// already be running the next piece).  A pageable destination makes this a blocking copy.
+int encoder_fetch_bulk(dfl_encoder* e) {
+    if (!e->bulk_n) { e->bulk_src = nullptr; return DFL_OK; }
+    HostTimer ht(&e->t_bulk);
+    Context& c = *e->ctx;
+    if (!e->out.reserve(e->out.n + e->bulk_n + 16)) return DFL_E_NOMEM;
+    int rc = c.copy_out(e->out.p + e->out.n, e->bulk_src, e->bulk_n, c.d2h_stream);
+    if (rc) return rc;
+    e->out.n += e->bulk_n;
+    e->bulk_n = 0;
+    e->bulk_src = nullptr;
+    return DFL_OK;
+}
+
 int encoder_emit(dfl_encoder* e, int mode) {
     int rc = encoder_init(e);
     if (rc) return rc;
@@ -1215,10 +1457,12 @@ int encoder_emit(dfl_encoder* e, int mode) {
     if ((rc = encoder_push_pending(e))) return rc;
     const StreamBuf& x = e->sb[e->f];
     const bool open = (mode == kPieceOpen);
-    if (open && x.end() < x.pos(e->parse_off) + kOpenTail + 1) return DFL_OK;   // not enough look-ahead to decide anything yet
+    if (open && x.end() < x.pos(e->parse_off) + kOpenTail + 1) return encoder_fetch_bulk(e);   // not enough look-ahead to decide anything yet
     if ((rc = encoder_issue(e, mode))) return rc;
+    if ((rc = encoder_fetch_bulk(e))) return rc;   // the previous piece's bytes, while this one runs
     if (open) return DFL_OK;   // settled by whoever comes next
     if ((rc = encoder_settle(e, mode))) return rc;
+    if ((rc = encoder_fetch_bulk(e))) return rc;
     if (mode == DFL_FLUSH_FINISH) {
         if (!e->out.reserve(e->out.n + 8)) return DFL_E_NOMEM;
         if (e->wrap == DFL_ZLIB) {   // lib.rs:192-196 / writer.rs:235-245: Adler-32, big endian
@@ -1293,8 +1537,9 @@ extern "C" int dfl_encoder_flush(dfl_encoder* e, int mode) {
 extern "C" int dfl_encoder_take_output(dfl_encoder* e, const uint8_t** p, size_t* len) {
     if (!e || !p || !len) return DFL_E_ARG;
     // bytes of a piece still running become visible once it is settled; do that here if it costs no wait
-    if (e->busy && cudaStreamQuery(e->ctx.stream) == cudaSuccess) {
+    if (e->busy && cudaStreamQuery(e->ctx->stream) == cudaSuccess) {
         int rc = encoder_settle(e, kPieceOpen);
+        if (rc == DFL_OK) rc = encoder_fetch_bulk(e);
         if (rc) return rc;
     }
     *p = e->out.p + e->out_pos;
@@ -1319,7 +1564,9 @@ extern "C" int dfl_encoder_set_piece_bytes(dfl_encoder* e, size_t bytes) {
 
 extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
     if (!e || e->wrap == DFL_RAW) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
-    if (encoder_init(e) != DFL_OK || encoder_settle(e, kPieceOpen) != DFL_OK || encoder_push_pending(e) != DFL_OK) return 0;
+    if (encoder_init(e) != DFL_OK || encoder_settle(e, kPieceOpen) != DFL_OK || encoder_fetch_bulk(e) != DFL_OK ||
+        encoder_push_pending(e) != DFL_OK)
+        return 0;
     const StreamBuf& b = e->sb[e->f];
     if (encoder_fold_checksum(e, b, b.off_org + b.new_n) != DFL_OK) return 0;
     return e->wrap == DFL_ZLIB ? e->adler : e->crc;
@@ -1337,6 +1584,8 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
         b.new_n = 0;
     }
     e->busy = false;
+    e->bulk_n = 0;
+    e->bulk_src = nullptr;
     e->pend.clear();
     e->parse_off = 0;
     e->parse_key = 0;
