@@ -554,6 +554,86 @@ def test_writer_pieces_without_flush_equal_oneshot(dfl, pg11):
                 assert bytes(sink) == want, (len(data), cls.__name__, piece, chunk, len(sink), len(want))
 
 
+def test_pageable_and_pinned_host_memory_give_the_same_bytes(dfl):
+    """Pageable buffers of 2 MiB and more travel through the library's pinned slot rings and copy threads, pinned
+    ones are copied directly: same bytes either way, for sizes on and around the slot (1 MiB) and ring (32 slots)
+    boundaries, one-shot and through the writer with large writes."""
+    import datagen
+    import torch
+    L = dfl._native.lib()
+    opts = dfl.CompressionOptions.fast()._c()
+    whole = datagen.silesia_mix((35 << 20) + 77, 0x57A6E)
+    for n in ((2 << 20) - 1, 2 << 20, (2 << 20) + 1, (3 << 20) + 12345, 32 << 20, (33 << 20) + 5, len(whole)):
+        data = whole[:n]
+        want = o.compress(data, o.opts_fast(), o.ZLIB)
+        cap = L.dfl_bound(n, dfl.ZLIB) + 64
+        got = []
+        for pinned in (False, True):
+            src = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+            dst = torch.empty(cap, dtype=torch.uint8)
+            if pinned:
+                src, dst = src.pin_memory(), dst.pin_memory()
+            m = ctypes.c_size_t()
+            rc = L.dfl_compress(ctypes.c_void_p(src.data_ptr()), n, ctypes.byref(opts), dfl.ZLIB, None, 0,
+                                ctypes.c_void_p(dst.data_ptr()), cap, ctypes.byref(m))
+            assert rc == 0
+            got.append(bytes(dst[:m.value].numpy()))
+        assert got[0] == want and got[1] == want, n
+    # the writer: writes large enough for the staged path, pieces small enough for several of them, both memory kinds
+    want = o.compress(whole, o.opts_fast(), o.ZLIB)
+    for pinned in (False, True):
+        src = torch.frombuffer(bytearray(whole), dtype=torch.uint8)
+        if pinned:
+            src = src.pin_memory()
+        e = L.dfl_encoder_new(ctypes.byref(opts), dfl.ZLIB, None, 0)
+        assert L.dfl_encoder_set_piece_bytes(e, 9 << 20) == 0
+        out = bytearray()
+        p, ln = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
+        step = (5 << 20) + 3
+        for off in range(0, len(whole), step):
+            assert L.dfl_encoder_write(e, ctypes.c_void_p(src.data_ptr() + off), min(step, len(whole) - off), None) == 0
+            L.dfl_encoder_take_output(e, ctypes.byref(p), ctypes.byref(ln))
+            out += ctypes.string_at(p, ln.value)
+            L.dfl_encoder_advance_output(e, ln.value)
+        assert L.dfl_encoder_flush(e, dfl._native.FLUSH_FINISH) == 0
+        L.dfl_encoder_take_output(e, ctypes.byref(p), ctypes.byref(ln))
+        out += ctypes.string_at(p, ln.value)
+        L.dfl_encoder_free(e)
+        assert bytes(out) == want, pinned
+
+
+def test_writers_on_several_threads(dfl, pg11):
+    """Handles are independent: four threads stream at the same time (they share the copy threads and the pool of
+    parked handle resources), several handles each; every stream equals the one-shot result."""
+    import threading
+    import datagen
+    datas = [datagen.silesia_mix((5 << 20) + 1000 * i, 0x7EAD + i) for i in range(4)]
+    wants = [o.compress(d, o.opts_fast(), o.ZLIB) for d in datas]
+    errors = []
+
+    def work(i):
+        try:
+            for rep in range(3):
+                sink = bytearray()
+                enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Fast)
+                enc.set_piece_bytes(1 << 20)
+                step = (2 << 20) + 17 if rep else 70000
+                for off in range(0, len(datas[i]), step):
+                    enc.write_all(datas[i][off:off + step])
+                enc.finish()
+                if bytes(sink) != wants[i]:
+                    errors.append((i, rep, len(sink), len(wants[i])))
+        except Exception as ex:   # noqa: BLE001
+            errors.append((i, repr(ex)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_writer_pieces_with_flushes_equal_the_reference_writer(dfl, pg11):
     """Open pieces and explicit sync flushes mixed (all flushes beyond the first window, see the divergence test)."""
     s = o.Stream(o.opts_default(), o.ZLIB)
