@@ -1144,7 +1144,15 @@ struct HandleRes {
     size_t cap[2] = {0, 0};
     int device = -1;
 };
-constexpr size_t kHandlePoolMax = 4;
+// DFL_HANDLE_POOL=n keeps up to n parked (0 = free everything with the handle); a parked handle that has run
+// 256 MiB pieces holds about 5 GiB of device memory.
+inline size_t handle_pool_max() {
+    static const size_t v = [] {
+        const char* e = getenv("DFL_HANDLE_POOL");
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)4;
+    }();
+    return v;
+}
 std::mutex g_handle_pool_mu;
 std::vector<HandleRes> g_handle_pool;
 }  // namespace
@@ -1190,7 +1198,7 @@ struct dfl_encoder {
             cudaStreamSynchronize(ctx->copy_stream);
             cudaStreamSynchronize(ctx->d2h_stream);
             std::lock_guard<std::mutex> lk(g_handle_pool_mu);
-            if (g_handle_pool.size() < kHandlePoolMax) {
+            if (g_handle_pool.size() < handle_pool_max()) {
                 HandleRes r;
                 r.ctx = std::move(ctx);
                 for (int i = 0; i < 2; i++) { r.d[i] = sb[i].d; r.cap[i] = sb[i].cap; sb[i].d = nullptr; }

@@ -27,6 +27,8 @@ for path in ("walk", "chains"):
     assert zlib.decompress(got, -15) == pg
     outs, sizes = dfl.compress_device_batch([src[:50000], src[50000:120001], src[:0]], dfl.Compression.Default, dfl.ZLIB)
     assert zlib.decompress(bytes(outs[1][:sizes[1]].cpu().numpy())) == pg[50000:120001]
+    hb = dfl.compress_batch([pg[:50000], pg[50000:120001], b"", pg[:300]] * 5, dfl.Compression.Default, dfl.ZLIB)
+    assert zlib.decompress(hb[5]) == pg[50000:120001] and zlib.decompress(hb[18]) == b""
     enc = dfl.write.GzEncoder(bytearray(), dfl.Compression.Default)
     enc.write_all(pg[:40000]); enc.flush(); enc.write_all(pg[40000:90000])
     assert zlib.decompress(bytes(enc.finish()), 31) == pg[:90000]
