@@ -1500,6 +1500,14 @@ extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const 
     return e;
 }
 
+// Appended bytes that trigger the next open piece: the first pieces of a stream are short, so that the kernels
+// start early (nothing runs while the first piece is being copied in), then piece_bytes.
+static size_t piece_target(const dfl_encoder* e) {
+    const uint64_t k = e->n_issued;
+    const size_t ramp = k == 0 ? ((size_t)32 << 20) : (k == 1 ? ((size_t)128 << 20) : e->piece_bytes);
+    return ramp < e->piece_bytes ? ramp : e->piece_bytes;
+}
+
 extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, size_t* consumed) {
     if (!e || (!buf && n)) return DFL_E_ARG;
     if (e->finished) return DFL_E_STATE;
@@ -1508,7 +1516,8 @@ extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, s
     while (done < n) {
         // take at most one piece at a time, so that neither buffer nor a device call grows without bound
         const size_t have = e->sb[e->f].new_n + e->pend.size();
-        const size_t room = e->piece_bytes > have ? e->piece_bytes - have : 0;
+        const size_t target = piece_target(e);
+        const size_t room = target > have ? target - have : 0;
         const size_t take = (n - done) < room ? (n - done) : room;
         if (take) {
             if (take < kPendDirect) {
@@ -1527,7 +1536,7 @@ extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, s
             e->total_in += take;
             done += take;
         }
-        if (e->sb[e->f].new_n + e->pend.size() >= e->piece_bytes) {
+        if (e->sb[e->f].new_n + e->pend.size() >= target) {
             rc = encoder_emit(e, kPieceOpen);
             if (rc) { if (consumed) *consumed = done; return rc; }
         }
@@ -1592,6 +1601,7 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
         b.new_n = 0;
     }
     e->busy = false;
+    e->n_issued = 0;
     e->bulk_n = 0;
     e->bulk_src = nullptr;
     e->pend.clear();
