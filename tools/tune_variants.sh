@@ -9,11 +9,11 @@ mode=$1; shift
 mkdir -p build/variants gpurun_out
 if [ "$mode" = build ]; then
   for v in "$@"; do
-    W=24; S=4; P=8; C=1024; M=3; PATHSEL=walk; PS=8192; PW=1024; U=4
+    W=24; S=4; P=8; C=1024; M=3; PATHSEL=walk; PS=4096; PW=512; U=2; X=""; TAG=base
     eval "$(echo "$v" | tr ',' ';')"
-    out=build/variants/lib_${PATHSEL}_W${W}_S${S}_P${P}_C${C}_M${M}_PS${PS}_PW${PW}_U${U}.so
+    out=build/variants/lib_${PATHSEL}_W${W}_S${S}_P${P}_C${C}_M${M}_PS${PS}_PW${PW}_U${U}_${TAG}.so
     (cd deflate-rs_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
-        -DDFL_CHAIN_WARPS=$W -DDFL_CHAIN_DEEP_STEPS=$S -DDFL_CHAIN_PARK_MIN=$P -DDFL_CHAIN_CHUNK=$C -DDFL_MATCH_CTAS=$M -DDFL_PARSE_SEG=$PS -DDFL_PARSE_WARM=$PW -DDFL_WALK_UNROLL=$U \
+        -DDFL_CHAIN_WARPS=$W -DDFL_CHAIN_DEEP_STEPS=$S -DDFL_CHAIN_PARK_MIN=$P -DDFL_CHAIN_CHUNK=$C -DDFL_MATCH_CTAS=$M -DDFL_PARSE_SEG=$PS -DDFL_PARSE_WARM=$PW -DDFL_WALK_UNROLL=$U $X \
         -o ../../$out dfl_kernels.cu dfl_api.cu) &
   done
   wait
