@@ -166,7 +166,7 @@ def run_reference(args):
                                                            "note": "8 MiB per core, one stream each; an upper bound, not the job"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_chunks(args):
@@ -289,7 +289,7 @@ def run_chunks(args):
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"one chunk ({chunk >> 20} MiB), oracle/, {cpu_dt:.1f} s", "ratio": cpu_csize / min(chunk, args.cpu_sample_mib << 20)},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -447,12 +447,34 @@ def run_ours(args):
                              "sample": f"first {cpu_sample >> 20} MiB of the same input, oracle/ (C port of the reference "
                                        f"algorithm), {cpu_dt:.1f} s", "ratio": cpu_csize / cpu_sample},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: whatever libraries print there on the way (NCCL's version banner
+    under NCCL_DEBUG=VERSION, for one) is sent to stderr instead, at the file-descriptor level."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
