@@ -567,7 +567,7 @@ int finish_pipeline(Context& c, cudaStream_t st, size_t n, size_t begin, size_t*
     const DevMeta& m = *c.h_meta;
     t_counters[0] = m.n_tokens;
     t_counters[1] = m.n_blocks;
-    t_counters[2] = parse_n_seg(n - begin, parse_geom(n - begin));
+    t_counters[2] = parse_n_seg(n - begin, parse_geom(n - begin, kLazy));   // (greedy runs on large inputs use half as many)
     t_counters[3] = m.n_repaired_par;
     t_counters[4] = m.n_repaired_seq;
     t_counters[5] = (uint64_t)g_launch_count;

@@ -1590,7 +1590,7 @@ static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
-    const ParseGeom g = parse_geom(j.n - j.begin);
+    const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
     A.seg = g.seg; A.warm = g.warm; A.tok_cap = parse_tok_cap(g);
     A.end = j.parse_end; A.init_key = j.init_key;
     A.n_seg = j.parse_end > j.begin ? (uint32_t)parse_n_seg(j.parse_end - j.begin, g) : 0u;
@@ -1688,7 +1688,7 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
 }
 
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st) {
-    const ParseGeom g = parse_geom(j.n - j.begin);
+    const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
     uint32_t n_seg = j.parse_end > j.begin ? (uint32_t)parse_n_seg(j.parse_end - j.begin, g) : 0u;
     k_seg_scan<<<1, 1024, 0, st>>>(n_seg, b.seg_e_tok, b.seg_x_tok, b.seg_cnt, b.seg_off, b.meta, j.n_carry_tok, j.open_piece,
                                    b.seg_x_pos, b.seg_x_key, j.begin, j.init_key);
