@@ -158,14 +158,12 @@ struct Stager {   // one per Context, allocated on first use
     uint8_t* ring[2] = {nullptr, nullptr};   // [0] host-to-device, [1] device-to-host
     cudaEvent_t ev[2][kStageSlots] = {};
     uint64_t seq = 0;                         // host-to-device slots are handed out round robin across calls
-    bool ok = false;
-    int init() {
-        if (ok) return DFL_OK;
-        for (int d = 0; d < 2; d++) {
-            CK(cudaMallocHost(reinterpret_cast<void**>(&ring[d]), kStageSlot * kStageSlots));
-            for (auto& e : ev[d]) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        ok = true;
+    bool ok[2] = {false, false};
+    int init(int d) {   // each direction's ring is pinned when it is first needed
+        if (ok[d]) return DFL_OK;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&ring[d]), kStageSlot * kStageSlots));
+        for (auto& e : ev[d]) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ok[d] = true;
         return DFL_OK;
     }
     ~Stager() {
@@ -176,7 +174,7 @@ struct Stager {   // one per Context, allocated on first use
     }
     // Returns once h_src has been read completely; the last DMAs may still be running on `st`.
     int h2d(uint8_t* d_dst, const uint8_t* h_src, size_t len, cudaStream_t st) {
-        int rc = init();
+        int rc = init(0);
         if (rc) return rc;
         CopyPool& pool = CopyPool::get();
         const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
@@ -202,9 +200,26 @@ struct Stager {   // one per Context, allocated on first use
         seq += n_chunks;
         return DFL_OK;
     }
+    // Small writes: the caller gathers bytes in the next host-to-device slot itself (one pass over the bytes,
+    // no driver staging) and sends it off when it is full.  No h2d() between gather_begin and gather_commit.
+    int gather_begin(uint8_t** slot_ptr) {
+        int rc = init(0);
+        if (rc) return rc;
+        const size_t slot = (size_t)(seq % kStageSlots);
+        CK(cudaEventSynchronize(ev[0][slot]));
+        *slot_ptr = ring[0] + slot * kStageSlot;
+        return DFL_OK;
+    }
+    int gather_commit(uint8_t* d_dst, size_t fill, cudaStream_t st) {
+        const size_t slot = (size_t)(seq % kStageSlots);
+        CK(cudaMemcpyAsync(d_dst, ring[0] + slot * kStageSlot, fill, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ev[0][slot], st));
+        seq++;
+        return DFL_OK;
+    }
     // Blocking: h_dst is complete on return.  d_src must be ready in stream order on `st`.
     int d2h(uint8_t* h_dst, const uint8_t* d_src, size_t len, cudaStream_t st) {
-        int rc = init();
+        int rc = init(1);
         if (rc) return rc;
         CopyPool& pool = CopyPool::get();
         const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
@@ -1172,7 +1187,10 @@ struct dfl_encoder {
     size_t bulk_n = 0;
     cudaEvent_t in_ev = nullptr;     // input copies issued so far are on the device (copy stream)
     cudaEvent_t hist_ev = nullptr;   // the latest history hand-over has left its source buffer (compute stream)
-    std::vector<uint8_t> pend;   // small writes not yet sent to the device
+    std::vector<uint8_t> pend;   // small writes not yet sent to the device (only while no device has been seen)
+    uint8_t* gather = nullptr;   // small writes are gathered in a pinned slot of the context's stager ...
+    size_t gather_n = 0;         // ... this many bytes so far
+    size_t pending() const { return pend.size() + gather_n; }
     uint64_t parse_off = 0;      // stream offset of the first byte not parsed yet
     uint32_t parse_key = 0;      // parser state there (parse_state_key)
     std::vector<uint32_t> carry_tok;   // parsed but not yet coded (fewer than 31744)
@@ -1291,6 +1309,17 @@ int encoder_append(dfl_encoder* e, const uint8_t* src, size_t len) {
 }
 
 int encoder_push_pending(dfl_encoder* e) {
+    if (e->gather_n) {
+        HostTimer ht(&e->t_append);
+        int rc = encoder_room(e, e->gather_n);
+        if (rc) return rc;
+        StreamBuf& b = e->sb[e->f];
+        Context& c = *e->ctx;
+        if ((rc = c.stager->gather_commit(b.d + b.end(), e->gather_n, c.copy_stream))) return rc;
+        b.new_n += e->gather_n;
+        e->gather = nullptr;
+        e->gather_n = 0;
+    }
     if (e->pend.empty()) return DFL_OK;
     int rc = encoder_append(e, e->pend.data(), e->pend.size());
     e->pend.clear();
@@ -1500,6 +1529,25 @@ extern "C" dfl_encoder* dfl_encoder_new(const dfl_options* opt, int wrap, const 
     return e;
 }
 
+// A small write: copied once, into pinned memory that the DMA engine reads.
+static int encoder_gather(dfl_encoder* e, const uint8_t* src, size_t len) {
+    HostTimer ht(&e->t_append);
+    int rc = encoder_init(e);
+    if (rc) return rc;
+    Context& c = *e->ctx;
+    if (!c.stager) c.stager.reset(new Stager());
+    while (len) {
+        if (!e->gather && (rc = c.stager->gather_begin(&e->gather))) return rc;
+        const size_t m = len < kStageSlot - e->gather_n ? len : kStageSlot - e->gather_n;
+        memcpy(e->gather + e->gather_n, src, m);
+        e->gather_n += m;
+        src += m;
+        len -= m;
+        if (e->gather_n == kStageSlot && (rc = encoder_push_pending(e))) return rc;
+    }
+    return DFL_OK;
+}
+
 // Appended bytes that trigger the next open piece: the first pieces of a stream are short, so that the kernels
 // start early (nothing runs while the first piece is being copied in), then piece_bytes.
 static size_t piece_target(const dfl_encoder* e) {
@@ -1515,12 +1563,14 @@ extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, s
     size_t done = 0;
     while (done < n) {
         // take at most one piece at a time, so that neither buffer nor a device call grows without bound
-        const size_t have = e->sb[e->f].new_n + e->pend.size();
+        const size_t have = e->sb[e->f].new_n + e->pending();
         const size_t target = piece_target(e);
         const size_t room = target > have ? target - have : 0;
         const size_t take = (n - done) < room ? (n - done) : room;
         if (take) {
-            if (take < kPendDirect) {
+            if (take < kPendDirect && device_count_cached() > 0) {
+                rc = encoder_gather(e, buf + done, take);
+            } else if (take < kPendDirect) {   // no device: keep the bytes, flush() will report it
                 try {
                     e->pend.insert(e->pend.end(), buf + done, buf + done + take);
                 } catch (const std::bad_alloc&) {
@@ -1536,7 +1586,7 @@ extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, s
             e->total_in += take;
             done += take;
         }
-        if (e->sb[e->f].new_n + e->pend.size() >= target) {
+        if (e->sb[e->f].new_n + e->pending() >= target) {
             rc = encoder_emit(e, kPieceOpen);
             if (rc) { if (consumed) *consumed = done; return rc; }
         }
@@ -1605,6 +1655,8 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
     e->bulk_n = 0;
     e->bulk_src = nullptr;
     e->pend.clear();
+    e->gather = nullptr;
+    e->gather_n = 0;
     e->parse_off = 0;
     e->parse_key = 0;
     e->carry_tok.clear();
