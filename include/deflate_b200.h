@@ -125,7 +125,7 @@ int dfl_compress_device_batch(size_t count, const void *const *d_in, const size_
  * host memory (the image encoders this crate serves: one IDAT stream per picture).  The members rotate
  * over a pool of pipelines, each with its own stream: a member's input copy, kernels and output copy
  * overlap those of the others.  Pinned buffers copy asynchronously; pageable ones work, staged by the
- * driver.  Byte-for-byte what dfl_compress returns for each member.  Blocking; status as above. */
+ * driver (members are small).  Byte-for-byte what dfl_compress returns for each member.  Blocking; status as above. */
 int dfl_compress_batch(size_t count, const uint8_t *const *in, const size_t *n, const dfl_options *opt, int wrap,
                        uint8_t *const *out, const size_t *out_cap, size_t *out_len, int *status);
 
@@ -148,16 +148,21 @@ typedef struct dfl_encoder dfl_encoder;
 
 dfl_encoder *dfl_encoder_new(const dfl_options *opt, int wrap, const uint8_t *gz_hdr,
                              size_t gz_hdr_len);                     /* ::new / from_builder */
-/* Write::write (writer.rs:124-127,254-267): consumes up to n bytes, *consumed <= n. */
+/* Write::write (writer.rs:124-127,254-267): consumes up to n bytes, *consumed <= n.  `buf` may be reused
+ * when the call returns: its bytes are on their way to the device (pageable memory goes through the
+ * library's pinned staging slots, pinned memory is copied directly and waited for). */
 int dfl_encoder_write(dfl_encoder *e, const uint8_t *buf, size_t n, size_t *consumed);
 /* Write::flush = DFL_FLUSH_SYNC (writer.rs:134-136); finish()/Drop = DFL_FLUSH_FINISH
  * (writer.rs:103-108,139-152).  After FINISH the trailer is part of the output. */
 int dfl_encoder_flush(dfl_encoder *e, int mode);
-/* Buffered input is encoded at every flush and, on its own, whenever `bytes` of it have accumulated
+/* Written input is encoded at every flush and, on its own, whenever `bytes` of it have accumulated
  * (default 256 MiB; 4096 <= bytes <= 2 GiB), so memory stays bounded and a stream can be longer than
  * 4 GiB.  The output does not depend on this value: without a flush the reference's stream has no seam
- * (lib.rs:408-433), and neither has this one. */
+ * (lib.rs:408-433), and neither has this one.  Such a piece runs while later writes arrive; its bytes
+ * become available at a later write, flush or take_output call, always in stream order. */
 int dfl_encoder_set_piece_bytes(dfl_encoder *e, size_t bytes);
+/* Lends the bytes produced so far and not yet advanced over; the pointer is valid until the next call on
+ * the handle.  After a flush everything up to the flush point is included. */
 int dfl_encoder_take_output(dfl_encoder *e, const uint8_t **p, size_t *len);
 void dfl_encoder_advance_output(dfl_encoder *e, size_t n);
 /* ZlibEncoder::checksum (writer.rs:248) / GzEncoder::checksum (writer.rs:429): checksum of the
