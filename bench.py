@@ -312,8 +312,6 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = dfl._native.lib()
-    if args.match_path:
-        dfl.set_match_path(args.match_path)
 
     cfg = CONFIGS[args.config]
     wrap = {"raw": dfl.RAW, "zlib": dfl.ZLIB}[cfg["wrap"]]
@@ -484,8 +482,6 @@ def main():
     ap.add_argument("--size-mib", type=int, default=None, help="input size per GPU (default: the config's own size)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
     ap.add_argument("--verify", default="prefix", choices=["none", "prefix", "full"])
-    ap.add_argument("--match-path", default=None, choices=["walk", "chains"],
-                    help="match kernels for the default options (identical output; default: the library's choice)")
     args = ap.parse_args()
     if args.size_mib is None:
         args.size_mib = CONFIGS[args.config]["size_mib"]

@@ -184,11 +184,6 @@ def deflate_bytes_gzip(input):
     return deflate_bytes_gzip_conf(input, Compression.Default, GzBuilder())
 
 
-def set_match_path(path):
-    """Tuning hook (dfl_set_match_path): "walk" or "chains".  Both produce identical bytes."""
-    return _native.lib().dfl_set_match_path({"walk": 0, "chains": 1}[path])
-
-
 def compress_device(src, options=Compression.Default, wrap=RAW, out=None, stream=None):
     """Device-resident encode: `src` and `out` are CUDA uint8 torch tensors.  Returns (out, n_bytes).
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_compress_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters",
     "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_set_piece_bytes", "dfl_encoder_take_output",
     "dfl_encoder_advance_output", "dfl_encoder_checksum", "dfl_encoder_reset", "dfl_encoder_free",
-    "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens", "dfl_set_match_path",
+    "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens",
 ]
 
 
@@ -91,7 +91,6 @@ def lib():
     L.dfl_encoder_free.restype = None
     L.dfl_adler32_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
     L.dfl_crc32_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
-    L.dfl_set_match_path.argtypes = [ctypes.c_int]
     L.dfl_encode_tokens.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                     ctypes.c_size_t, szp]
     L.dfl_lz77_tokens.argtypes = [ctypes.c_void_p, ctypes.c_size_t, optp, ctypes.c_void_p, ctypes.c_size_t, szp]

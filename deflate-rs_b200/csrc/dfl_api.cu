@@ -305,7 +305,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.off); dev_free(b.M); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -314,7 +314,6 @@ struct Context {
         b.tok = nullptr;
         b.cap_n = 0;
         b.cap_quarter = false;
-        b.cap_chains = false;
     }
     ~Context() {
         if (!ok) return;
@@ -331,16 +330,15 @@ struct Context {
     }
 
     // Scratch for inputs of up to n bytes (history + payload).
-    int ensure(size_t n, bool quarter, bool chains) {
+    int ensure(size_t n, bool quarter) {
         Buffers& b = buf;
-        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter) && (b.cap_chains || !chains)) return DFL_OK;
+        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter)) return DFL_OK;
         size_t cap = n + n / 8 + 65536;
         if (cap < b.cap_n) cap = b.cap_n;      // growing one kind of scratch never shrinks another
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
         if (cap < n) return DFL_E_ARG;
         cudaStreamSynchronize(stream);
         quarter = quarter || b.cap_quarter;
-        chains = chains || b.cap_chains;
         free_buffers();
         size_t n_win = (cap + kWindow - 1) / kWindow + 1;
         size_t n_seg = (cap + 1023) / 1024 + 1;   // the shortest parse segment (parse_geom) gives the most segments
@@ -349,7 +347,6 @@ struct Context {
         int rc = 0;
         if ((rc = dev_alloc(b.K, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
-        if (chains && (rc = dev_alloc(b.M, n_win * kSpanSlots))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
         if ((rc = dev_alloc(b.segtok, parse_buffer_words(cap)))) return rc;
@@ -374,7 +371,6 @@ struct Context {
         b.tok = reinterpret_cast<uint32_t*>(b.K);   // the candidate lists are dead once k_match has run; the token stream reuses them
         b.cap_n = cap;
         b.cap_quarter = quarter;
-        b.cap_chains = chains;
         return DFL_OK;
     }
     int ensure_stage(uint8_t*& p, size_t& cap, size_t need) {
@@ -507,8 +503,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     j.carry_bits_v = pin.bits_v;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
 
-    const bool need_match_stage = (d_tokens_override == nullptr) && j.prm.mode != kRle && j.prm.checks > 0;
-    int rc = c.ensure(n, j.prm.need_quarter != 0, need_match_stage && use_chains(j.prm));
+    int rc = c.ensure(n, j.prm.need_quarter != 0);
     if (rc) return rc;
     Buffers& b = c.buf;
     CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
@@ -516,7 +511,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
     if (need_match) {
         const uint32_t w_end = n_windows(j), w_sort0 = first_sort_window(j), w_match0 = first_match_window(j);
-        if (arrival && !use_chains(j.prm)) {
+        if (arrival) {
             // the input is still being copied: sort and match every window as soon as its bytes
             // (and the 272 bytes of look-ahead behind it) are on the device
             uint32_t w_sorted = w_sort0, w_matched = w_match0;
@@ -653,11 +648,6 @@ extern "C" size_t dfl_bound(size_t n, int wrap) {
     return n + 5 * (n / 32767 + 1) + 6 * (n / 31744 + 2) + 64 + (wrap == DFL_GZIP ? 320 : 0);
 }
 
-extern "C" int dfl_set_match_path(int path) {
-    int old = g_match_path;
-    g_match_path = path ? 1 : 0;
-    return old;
-}
 extern "C" int dfl_set_profiling(int enabled) {
     int old = t_profiling;
     t_profiling = enabled;
@@ -1027,7 +1017,7 @@ extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void*
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
-    if ((rc = c.ensure(n ? n : 1, false, false))) return rc;
+    if ((rc = c.ensure(n ? n : 1, false))) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     CK(launch_crc32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -1041,7 +1031,7 @@ extern "C" int dfl_adler32_device(const void* d_in, size_t n, uint32_t* adler, v
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
-    if ((rc = c.ensure(n ? n : 1, false, false))) return rc;
+    if ((rc = c.ensure(n ? n : 1, false))) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     CK(launch_adler32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -1332,7 +1322,7 @@ int encoder_fold_checksum(dfl_encoder* e, const StreamBuf& b, uint64_t to) {
     if (e->wrap == DFL_RAW || to <= e->sum_off) { if (to > e->sum_off) e->sum_off = to; return DFL_OK; }
     Context& c = *e->ctx;
     const size_t len = (size_t)(to - e->sum_off);
-    int rc = c.ensure(len, false, false);
+    int rc = c.ensure(len, false);
     if (rc) return rc;
     CK(cudaEventRecord(e->in_ev, c.copy_stream));
     CK(cudaStreamWaitEvent(c.stream, e->in_ev, 0));

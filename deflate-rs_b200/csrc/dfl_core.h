@@ -99,99 +99,65 @@ DFL_HD uint32_t entry_lcp(uint32_t xlo, uint32_t xhi) {
 }
 
 // ---------------------------------------------------------------- candidate walk
-// State of one longest_match call (matching.rs:87-166) while its candidates are visited most recent
-// first.  best_len == 1 means "nothing yet" (matching.rs:108 floors the running best at 1; results
-// shorter than MIN_MATCH are discarded by both parsers, so they are never recorded here).
-struct WalkState {
-    uint32_t best_len, best_dist;
+// One longest_match call (matching.rs:87-166) visits its candidates most recent first and keeps the first one
+// that is strictly longer than the running best, so the nearest candidate wins ties (:148-157).  The pipeline
+// splits that work in two:
+//   * the match stage (kernel k_match) walks the candidate *entries* only.  An entry proves common prefixes of
+//     up to 8 bytes exactly, so every result shorter than 8 bytes is final there; a position whose best
+//     candidate shares all 8 entry bytes is recorded as "long": only its rank in the window's sorted list and
+//     the visit index of the nearest such candidate are kept.
+//   * the parse stage resolves a long record on the data -- but only at the positions the reference's parser
+//     actually searches (lz77.rs:340-377 skips everything inside an emitted match).
+// best_len == 1 means "nothing yet" (matching.rs:108 floors the running best at 1; results shorter than
+// MIN_MATCH are discarded by both parsers, so they are never recorded).
+struct EntryWalk {
+    uint32_t best_len;    // 1, or 3..8 as proven by entries (clamped to the bytes left in the input)
+    uint32_t best_pos;    // position-in-window field of the best candidate
+    uint32_t best_k;      // its visit index (0 = nearest candidate)
     uint32_t mlo, mhi;    // entry_mask(best_len)
-    uint32_t done;        // the match reached max_len: the reference stops walking (matching.rs:152-156)
+    uint32_t stop;        // nothing can be longer as far as entries can tell (8 bytes, or the end of the input)
 };
-DFL_HD WalkState walk_init() {
-    WalkState s; s.best_len = 1; s.best_dist = 0; s.done = 0; entry_mask(1, s.mlo, s.mhi); return s;
+DFL_HD EntryWalk ewalk_init() {
+    EntryWalk s; s.best_len = 1; s.best_pos = 0; s.best_k = 0; s.stop = 0; entry_mask(1, s.mlo, s.mhi); return s;
 }
-// Necessary condition for candidate entry `ce` to beat the running best of target entry `me`.
-DFL_HD bool walk_passes(const WalkState& s, Entry me, Entry ce) {
-    return ((((ce.lo ^ me.lo) & s.mlo) | ((ce.hi ^ me.hi) & s.mhi)) == 0u);
-}
-// A candidate that passed: determine its exact length and keep it if strictly longer (so the nearest
-// candidate wins ties, matching.rs:148-157).  D gives access to the bytes: byte(i), common_prefix(a,b,from,maxl).
-// sp/sq are the data indices of the target and the candidate (sq < sp).
-template <class D>
-DFL_HD void walk_consider(WalkState& s, const D& data, uint32_t sp, uint32_t sq, Entry me, Entry ce, uint32_t maxl) {
-    uint32_t l;
-    if (s.best_len < kEntryBytes) {
-        l = entry_lcp(ce.lo ^ me.lo, ce.hi ^ me.hi);
-        if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
-    } else {
-        // the reference's quick reject looks at the byte that would extend the best match (matching.rs:141-143)
-        if (data.byte(sq + s.best_len) != data.byte(sp + s.best_len)) return;
-        l = data.common_prefix(sp, sq, kEntryBytes, maxl);
-    }
+// Visit number k: candidate entry `ce` against target entry `me`; maxl = min(258, bytes left at the target).
+DFL_HD void ewalk_visit(EntryWalk& s, Entry me, Entry ce, uint32_t k, uint32_t maxl) {
+    if (s.stop) return;
+    if ((((ce.lo ^ me.lo) & s.mlo) | ((ce.hi ^ me.hi) & s.mhi)) != 0u) return;
+    uint32_t l = entry_lcp(ce.lo ^ me.lo, ce.hi ^ me.hi);
     if (l > maxl) l = maxl;
     if (l > s.best_len) {
-        s.best_len = l;
-        s.best_dist = sp - sq;
+        s.best_len = l; s.best_pos = entry_pos(ce.hi); s.best_k = k;
         entry_mask(l, s.mlo, s.mhi);
-        if (l == maxl) s.done = 1;
+        if (l >= kEntryBytes || l == maxl) s.stop = 1;
     }
-}
-
-// ---------------------------------------------------------------- span entries (multi-level chains)
-// The fast match path (kernel k_match_chains, max_hash_checks <= kChainMaxChecks) works on *spans*:
-// kSpanWin target windows plus the window before them, merged into one list sorted by
-// (hash3, position).  In that list the candidates of a position are simply the entries in front of
-// it: the previous `max_hash_checks` of its own bucket, cut where the distance exceeds 32768
-// (matching.rs:102-106,127-134).  A span entry is 64 bits:
-//   lo = bytes p+3 .. p+6 (little endian)
-//   hi = tag9 | first-of-bucket << 9 | position-in-span << 15   (position counted from the start of
-//        the window in front of the first target window, so targets have position >= 32768)
-// Entries prove common prefixes of 3..7 bytes; longer ones are resolved on the data.
-constexpr uint32_t kSpanWin = 1;                       // target windows per span
-constexpr uint32_t kSpanSlots = (kSpanWin + 1) * kWindow;   // entries reserved per span
-constexpr uint32_t kChainMaxChecks = 128;              // ring capacity of the chain kernel
-constexpr uint32_t kChainLevels = 5;                   // prefix lengths 3, 4, 5, 6, 7
-constexpr uint32_t kSpanTagMask = 0x1ffu;
-constexpr uint32_t kSpanFirstBit = 0x200u;
-constexpr uint32_t kSpanEntryBytes = 7;                // prefix length a span entry can prove
-DFL_HD Entry make_span_entry(uint32_t pos_in_span, const uint8_t b[7], bool first_of_bucket) {
-    Entry e;
-    e.lo = b[3] | (b[4] << 8) | (b[5] << 16) | ((uint32_t)b[6] << 24);
-    e.hi = tag9(b[0], b[1]) | (first_of_bucket ? kSpanFirstBit : 0u) | (pos_in_span << 15);
-    return e;
-}
-DFL_HD uint32_t span_entry_pos(uint32_t hi) { return hi >> 15; }
-// bytes 3 .. L-1 of the entry, L = 3 + level
-DFL_HD uint32_t span_level_mask(uint32_t level) { return level == 0u ? 0u : (0xffffffffu >> (8u * (4u - level))); }
-// 8-bit chain slot of an entry at a level: a hash of exactly the bits that define the level's key
-DFL_HD uint32_t span_sig(uint32_t lo, uint32_t hi, uint32_t level) {
-    return (((lo & span_level_mask(level)) * 0x9E3779B1u) + ((hi & kSpanTagMask) * 0x7FEB352Du) + level * 0x3C6EF372u) >> 24;
-}
-// do two entries of one bucket share their first 3 + level bytes?
-DFL_HD bool span_key_equal(Entry a, Entry b, uint32_t level) {
-    return ((((a.lo ^ b.lo) & span_level_mask(level)) | ((a.hi ^ b.hi) & kSpanTagMask)) == 0u);
-}
-// common prefix (3..7) of two entries of one bucket with equal tags
-DFL_HD uint32_t span_entry_lcp(uint32_t xlo) {
-    if (xlo == 0u) return 7u;
-#if defined(__CUDA_ARCH__)
-    return 3u + ((uint32_t)(__ffs((int)xlo) - 1) >> 3);
-#else
-    return 3u + ((uint32_t)__builtin_ctz(xlo) >> 3);
-#endif
 }
 
 // ---------------------------------------------------------------- per-position match record
-// len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23.  0 == "no usable match".
+// Final:  len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23; 0 == "no usable match".
+// Long (bit 31): the best candidate shares >= 8 bytes and more bytes are left to compare.  Bits 0..14 = rank
+// of the position in its window's sorted list, bits 15..30 = visit index of the nearest candidate that shares
+// 8 bytes (every nearer one shares fewer, so a resolution starts there).
+constexpr uint32_t kRecLong = 0x80000000u;
 DFL_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 9); }
 DFL_HD uint32_t match_len(uint32_t m) { return m & 0x1ffu; }
 DFL_HD uint32_t match_dist(uint32_t m) { return ((m >> 9) & 0x7fffu) + 1u; }
+DFL_HD uint32_t rec_long(uint32_t rank, uint32_t k8) { return kRecLong | rank | (k8 << 15); }
+DFL_HD bool rec_is_long(uint32_t m) { return (m & kRecLong) != 0u; }
+DFL_HD uint32_t rec_rank(uint32_t m) { return m & 0x7fffu; }
+DFL_HD uint32_t rec_k8(uint32_t m) { return (m >> 15) & 0xffffu; }
 // lz77.rs:274-278 match_too_far applied to the result of matching.rs:87-166; results shorter than
 // MIN_MATCH are never used by either parser and are recorded as "no match".
 DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
     if (len < kMinMatch) return 0u;
     if (len == kMinMatch && dist > kTooFar) return 0u;
     return pack_match(len, dist);
+}
+// Record of a finished entry walk.  `rank` = index of the target in its window's sorted list, `dist` = distance
+// of the best candidate.
+DFL_HD uint32_t ewalk_record(const EntryWalk& s, uint32_t rank, uint32_t dist, uint32_t maxl) {
+    if (s.best_len >= kEntryBytes && maxl > kEntryBytes) return rec_long(rank, s.best_k);
+    return finalize_match(s.best_len, dist);
 }
 
 // ---------------------------------------------------------------- tokens

@@ -90,7 +90,6 @@ struct BlockTables {
 struct Buffers {   // device scratch of one context, grown on demand
     uint2* K = nullptr;             // candidate entries in bucket order (dfl_core.h Entry), n_windows * 32768
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
-    uint2* M = nullptr;             // span entries (chain path only), n_windows * kSpanSlots
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
     uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * parse_tok_cap
@@ -116,15 +115,7 @@ struct Buffers {   // device scratch of one context, grown on demand
     DevMeta* meta = nullptr;
     size_t cap_n = 0;               // input size the buffers were sized for
     bool cap_quarter = false;
-    bool cap_chains = false;
 };
-
-// The span/chain match path (k_span_scatter + k_match_chains) covers every option set whose chain
-// budget fits its ring; anything else takes the generic candidate walk (k_match).
-extern int g_match_path;   // 0 = candidate walk everywhere, 1 = chains where they apply (dfl_kernels.cu; DFL_MATCH_PATH)
-inline bool use_chains(const Params& p) {
-    return g_match_path == 1 && p.checks >= 1 && p.checks <= kChainMaxChecks && !p.need_quarter;
-}
 
 struct EncodeJob {
     const uint8_t* d_in;     // device input (history + payload)
@@ -169,6 +160,6 @@ cudaError_t launch_adler32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream
 cudaError_t launch_crc32(const uint8_t* d_in, size_t n, Buffers& b, cudaStream_t st);
 cudaError_t launch_finalize(const EncodeJob& j, Buffers& b, int wrap, cudaStream_t st);
 uint32_t max_blocks_for(uint32_t n_payload);
-extern int g_launch_count;   // kernels launched since the last reset (host-side counter)
+extern thread_local int g_launch_count;   // kernels launched by the calling thread since its last reset
 
 }  // namespace dfl

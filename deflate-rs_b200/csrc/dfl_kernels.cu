@@ -18,24 +18,20 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "dfl_internal.h"
 
 // tuning knobs (tools/tune_variants.sh)
 #ifndef DFL_WALK_UNROLL
-#define DFL_WALK_UNROLL 2
+#define DFL_WALK_UNROLL 4
 #endif
 #define DFL_PRAGMA_(x) _Pragma(#x)
 #define DFL_PRAGMA(x) DFL_PRAGMA_(x)
 
 namespace dfl {
 
-int g_launch_count = 0;
-// Which match path serves option sets both can handle.  Results are identical; the switch exists so
-// that the two can be timed against each other (bench.py --match-path, tools/).
-int g_match_path = [] {
-    const char* e = getenv("DFL_MATCH_PATH");
-    return (e && e[0] == 'c') ? 1 : 0;   // "chains" | "walk" (default)
-}();
+thread_local int g_launch_count = 0;   // kernels launched by the calling thread since it last reset the counter
 
 #define DFL_LAUNCH_CHECK()                         \
     do {                                           \
@@ -138,7 +134,6 @@ static_assert(kWindow + 16 <= kSortCntWords * 4, "byte staging must fit in the c
 // word w of a counter row is stored at slot_of(w): its 32-word group rotated by the group number
 __device__ __forceinline__ uint32_t sort_slot_of(uint32_t w) { return (w & ~31u) | ((w + (w >> 5)) & 31u); }
 
-template <bool ITEMS>   // ITEMS: emit the sorted (hash << 15 | position) words for k_span_scatter instead of entries
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
                                                                  uint16_t* __restrict__ off) {
@@ -250,10 +245,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
     }
 
     // ---- output: entries in bucket order
-    if (ITEMS) {
-        uint32_t* Iw = reinterpret_cast<uint32_t*>(K) + (size_t)w * kWindow;
-        for (uint32_t r = t; r < kWindow; r += kSortThreads) Iw[r] = buf[r + (r >> 5)];
-    } else {
+    {
     stage_bytes(smem, in, (long long)base, kWindow + 16, n);   // counters are dead; bytes again
     __syncthreads();
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
@@ -330,40 +322,25 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
 // k_match: one CTA per window; a thread owns one sorted entry (the target) and visits its candidates
 // most recent first: the entries before it in its own bucket, then the tail of the same bucket of
 // the previous window (only positions at distance <= 32768), at most max_hash_checks in total.
-//   A visit is a coalesced 8-byte load and three logic ops (walk_passes); only the few candidates
-//   that can still beat the running best touch the data (walk_consider).  Warps stay converged: the
-//   trip count is the warp maximum and the rare path is entered on a warp vote.
-//   shared: the previous and the current window plus 258 bytes of look-ahead
+//   Entries only: a visit is a coalesced 8-byte load and three logic ops against a pair of masks that
+//   tighten as the running best grows (dfl_core.h EntryWalk).  Results shorter than 8 bytes are final;
+//   a target whose best candidate shares all 8 entry bytes gets a "long" record (rank + visit index of
+//   the nearest such candidate) and is resolved on the data by the parse stage -- if the parser ever
+//   searches there.  No data is touched here beyond the three bytes that give a target its bucket.
+//   shared: the window's bytes (+16)
 // =====================================================================================
 constexpr uint32_t kMatchThreads = 512;
-constexpr uint32_t kMatchStage = 2 * kWindow + 272;   // multiple of 16
+constexpr uint32_t kMatchStage = kWindow + 16;        // multiple of 16
 constexpr uint32_t kMatchSmem = kMatchStage + 16;
 
-struct SmemBytes {
-    const uint8_t* b;
-    const uint32_t* w;
-    __device__ __forceinline__ uint32_t byte(uint32_t i) const { return b[i]; }
-    __device__ __forceinline__ uint32_t common_prefix(uint32_t a, uint32_t c, uint32_t from, uint32_t maxl) const {
-        uint32_t l = from;
-        while (l < maxl) {
-            uint32_t x = lds32(w, a + l) ^ lds32(w, c + l);
-            if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-            l += 4;
-        }
-        return l < maxl ? l : maxl;
-    }
-};
-
-// Per-lane state of one walk, kept in registers (the device-side form of dfl_core.h WalkState: the
-// model in tests/model runs walk_passes/walk_consider, this is the same logic with the frontier-byte
-// test pulled into the visit loop).
+// Per-lane state of one entry walk, kept in registers (the device-side form of dfl_core.h EntryWalk).
 struct Walk {
-    uint32_t best_len;    // 1 = nothing yet
-    uint32_t best_sq;     // shared-memory index of the best candidate
-    uint32_t mlo, mhi;    // entry_mask(best_len)
-    uint32_t myfb;        // target byte at offset best_len
-    uint32_t visited;
-    uint32_t q_len, q_sq; // snapshot after checks_quarter candidates
+    uint32_t me_lo, me_hi;   // the target's entry; me_hi is poisoned once the walk has stopped so that nothing passes
+    uint32_t mlo, mhi;       // entry_mask(best_len)
+    uint32_t best_len;       // 1 = nothing yet
+    uint32_t best_dist, best_k;
+    uint32_t stop;
+    uint32_t q_len, q_dist, q_k, q_stop;   // state after checks_quarter visits (NEEDQ)
 };
 
 __device__ __forceinline__ void walk_masks(uint32_t best_len, uint32_t& mlo, uint32_t& mhi) {
@@ -374,66 +351,51 @@ __device__ __forceinline__ void walk_masks(uint32_t best_len, uint32_t& mlo, uin
     mhi = kEntryTagHi | (uint32_t)(m >> 32);
 }
 
-__device__ __forceinline__ uint32_t lds_u8_if(uint32_t saddr, bool pred) {
-    uint32_t v;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0x100;\n\t@p ld.shared.u8 %0, [%1];\n\t}"
-                 : "=r"(v) : "r"(saddr), "r"((uint32_t)pred));
-    return v;
-}
-
-// One candidate.  `foff` = shared-window address of the segment's first byte + best_len, so that
-// (position of the candidate) + foff addresses the candidate byte that would extend the best match.
-template <uint32_t SEG>
-__device__ __forceinline__ void walk_visit(Walk& wk, const SmemBytes& data, uint32_t sbase, uint32_t& foff, uint2 v, bool valid,
-                                           Entry me, uint32_t sp, uint32_t maxl, uint32_t& stop) {
-    bool pass = valid && ((((v.x ^ me.lo) & wk.mlo) | ((v.y ^ me.hi) & wk.mhi)) == 0u);
-    // The reference's quick reject: the byte that would extend the best match (matching.rs:141-143).
-    // Below 8 bytes the entry test above already implies it; from 8 on it does the filtering.
-    const uint32_t fb = lds_u8_if((v.y >> 17) + foff, pass);
-    if (fb == wk.myfb) {                            // implies pass (fb is 0x100 otherwise; myfb is a byte, or 0x200 = stopped)
-        const uint32_t sq = (v.y >> 17) + SEG;
-        // (with 8 or more bytes already matched the entry test above means all entry bytes agree, so entry_lcp
-        // gives 8 there too: one copy of the comparison loop serves both cases)
-        uint32_t l = entry_lcp(v.x ^ me.lo, v.y ^ me.hi);
-        if (l >= kEntryBytes && maxl > kEntryBytes) l = data.common_prefix(sp, sq, kEntryBytes, maxl);
-        l = l < maxl ? l : maxl;
-        if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
-            foff += l - wk.best_len;
-            wk.best_len = l;
-            wk.best_sq = sq;
+// A candidate passed the masks: it shares more bytes with the target than the running best (unless the end
+// of the input clamps it).  kg = visit index, dist_base - position = distance.
+template <bool NEEDQ>
+__device__ __forceinline__ void walk_improve(Walk& wk, uint2 v, uint32_t kg, uint32_t dist_base, uint32_t maxl, uint32_t qbudget) {
+    if (wk.stop) return;
+    uint32_t l = entry_lcp(v.x ^ wk.me_lo, v.y ^ wk.me_hi);
+    l = l < maxl ? l : maxl;
+    if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
+        wk.best_len = l;
+        wk.best_dist = dist_base - (v.y >> 17);
+        wk.best_k = kg;
+        const bool stop = (l >= kEntryBytes) || (l == maxl);
+        if (NEEDQ) {
+            if (kg < qbudget) { wk.q_len = l; wk.q_dist = wk.best_dist; wk.q_k = kg; wk.q_stop = stop; }
+        }
+        if (stop) {                             // matching.rs:152-156, or nothing longer can be proven from entries
+            wk.stop = 1;
+            wk.mlo = 0xffffffffu; wk.mhi = kEntryKeyHi;
+            wk.me_hi ^= 0x100u;                 // a flipped tag bit: (almost) nothing passes any more; the guard above catches the rest
+        } else {
             walk_masks(l, wk.mlo, wk.mhi);
-            if (l == maxl) { stop = 1; wk.myfb = 0x200u; }     // matching.rs:152-156: nothing passes any more
-            else wk.myfb = data.b[sp + l];
         }
     }
 }
 
 // One pass over the candidates Kseg[idx], Kseg[idx - 1], ... : lane-private count n_seg, of which the
 // first `tmin` visits are valid in every lane of the warp (no per-visit bounds test) and the rest up
-// to `tmax` are ragged.  SEG is the shared-memory index of the segment's first byte (32768 for the
-// target's own window, 0 for the previous one).
-template <bool NEEDQ, uint32_t SEG>
-__device__ __forceinline__ void walk_segment(Walk& wk, const SmemBytes& data, uint32_t sbase, const uint2* __restrict__ Kseg,
-                                             int idx, uint32_t n_seg, uint32_t tmin, uint32_t tmax, Entry me, uint32_t sp,
-                                             uint32_t maxl, uint32_t qbudget, uint32_t& stop) {
+// to `tmax` are ragged.
+template <bool NEEDQ>
+__device__ __forceinline__ void walk_segment(Walk& wk, const uint2* __restrict__ Kseg, int idx, uint32_t n_seg, uint32_t tmin,
+                                             uint32_t tmax, uint32_t kbase, uint32_t dist_base, uint32_t maxl,
+                                             uint32_t qbudget) {
     const uint2* ptr = Kseg + idx;
-    uint32_t foff = sbase + SEG + wk.best_len;
     uint32_t k = 0;
-    if (!NEEDQ) {
 DFL_PRAGMA(unroll DFL_WALK_UNROLL)
-        for (; k < tmin; k++, ptr--) walk_visit<SEG>(wk, data, sbase, foff, __ldg(ptr), true, me, sp, maxl, stop);
+    for (; k < tmin; k++, ptr--) {
+        const uint2 v = __ldg(ptr);
+        if ((((v.x ^ wk.me_lo) & wk.mlo) | ((v.y ^ wk.me_hi) & wk.mhi)) == 0u)
+            walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
     }
     for (; k < tmax; k++, ptr--) {
-        const bool valid = k < n_seg;
-        uint2 v = make_uint2(0u, 0u);
-        if (valid) v = __ldg(ptr);
-        const uint32_t was_stopped = stop;
-        walk_visit<SEG>(wk, data, sbase, foff, v, valid, me, sp, maxl, stop);
-        if (NEEDQ) {
-            if (valid && !was_stopped) {            // candidates after the stop are never visited by the reference
-                wk.visited++;
-                if (wk.visited == qbudget) { wk.q_len = wk.best_len; wk.q_sq = wk.best_sq; }
-            }
+        if (k < n_seg) {
+            const uint2 v = __ldg(ptr);
+            if ((((v.x ^ wk.me_lo) & wk.mlo) | ((v.y ^ wk.me_hi) & wk.mhi)) == 0u)
+                walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
         }
     }
 }
@@ -442,7 +404,7 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_s
 __device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 
 #ifndef DFL_MATCH_CTAS
-#define DFL_MATCH_CTAS 3
+#define DFL_MATCH_CTAS 4
 #endif
 template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
@@ -450,14 +412,11 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
         const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
         uint32_t* __restrict__ Mq) {
     extern __shared__ __align__(16) uint8_t smem[];
-    SmemBytes data;
-    data.b = smem;
-    data.w = reinterpret_cast<const uint32_t*>(smem);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
     const uint32_t w = w_first + blockIdx.x;
     const uint32_t base = w * kWindow;
     const uint32_t cnt = window_count(n, w);
-    // shared index of absolute position a is a - base + 32768
-    stage_bytes(smem, in, (long long)base - (long long)kWindow, kMatchStage, n);
+    stage_bytes(smem, in, (long long)base, kMatchStage, n);
     __syncthreads();
 
     const uint2* Kw = K + (size_t)w * kWindow;
@@ -467,7 +426,6 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
     const uint32_t budget = prm.checks;
     const uint32_t qbudget = prm.checks_quarter;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 
     // gridDim.y CTAs share one window when the input is small (the stage's latency is one CTA's run through
     // 32768 entries otherwise): each takes a contiguous, 32-aligned slice of the sorted entries
@@ -476,17 +434,16 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     for (uint32_t i0 = i_lo + (threadIdx.x & ~31u); i0 < i_hi; i0 += blockDim.x) {   // warp-uniform loop
         const uint32_t i = i0 + lane_id();
         bool act = i < i_hi;
-        Entry me;
-        me.lo = 0; me.hi = 0;
-        if (act) { uint2 v = __ldg(Kw + i); me.lo = v.x; me.hi = v.y; }
-        const uint32_t pl = entry_pos(me.hi);
+        Walk wk;
+        wk.me_lo = 0; wk.me_hi = 0;
+        if (act) { uint2 v = __ldg(Kw + i); wk.me_lo = v.x; wk.me_hi = v.y; }
+        const uint32_t pl = entry_pos(wk.me_hi);
         const uint32_t p = base + pl;
         if (p < begin) act = false;
-        const uint32_t sp = pl + kWindow;
         uint32_t n_own = 0, n_prev = 0, pe = 0;
         uint32_t maxl = 0;
         if (act) {
-            const uint32_t w0 = lds32(data.w, sp);
+            const uint32_t w0 = lds32(sw, pl);
             const uint32_t h = hash3(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
             maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
             const uint32_t s0 = ow[h];
@@ -508,372 +465,28 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                 n_prev = pe - lo;
             }
         }
-        Walk wk;
-        wk.best_len = 1; wk.best_sq = 0; wk.mlo = 0; wk.mhi = kEntryTagHi; wk.visited = 0;
-        wk.myfb = data.b[sp + 1u];
-        wk.q_len = 1; wk.q_sq = 0;
-        uint32_t stop = 0;
-        walk_segment<NEEDQ, kWindow>(wk, data, sbase, Kw, (int)i - 1, n_own, warp_min(n_own), warp_max(n_own), me, sp, maxl,
-                                     qbudget, stop);
-        if (stop) n_prev = 0;
-        walk_segment<NEEDQ, 0u>(wk, data, sbase, Kp, (int)pe - 1, n_prev, warp_min(n_prev), warp_max(n_prev), me, sp, maxl,
-                                qbudget, stop);
+        wk.best_len = 1; wk.best_dist = 0; wk.best_k = 0; wk.stop = 0; wk.mlo = 0; wk.mhi = kEntryTagHi;
+        wk.q_len = 1; wk.q_dist = 0; wk.q_k = 0; wk.q_stop = 0;
+        walk_segment<NEEDQ>(wk, Kw, (int)i - 1, n_own, warp_min(n_own), warp_max(n_own), 0u, pl, maxl, qbudget);
+        if (wk.stop) n_prev = 0;
+        walk_segment<NEEDQ>(wk, Kp, (int)pe - 1, n_prev, warp_min(n_prev), warp_max(n_prev), n_own, pl + kWindow, maxl, qbudget);
         if (act) {
-            Mf[p] = finalize_match(wk.best_len, sp - wk.best_sq);
-            if (NEEDQ) {
-                if (wk.visited < qbudget) { wk.q_len = wk.best_len; wk.q_sq = wk.best_sq; }
-                Mq[p] = finalize_match(wk.q_len, sp - wk.q_sq);
-            }
+            Mf[p] = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, wk.best_dist);
+            if (NEEDQ) Mq[p] = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, wk.q_dist);
         }
     }
 }
 
 // =====================================================================================
-// k_span_scatter: one CTA per window.  Turns the window's sorted (hash, position) words into span
-// entries (dfl_core.h) and writes each into the one or two spans the window belongs to: as a target
-// window into span v, and as the history window into span v + 1.  Within a span the two windows'
-// lists are merged bucket by bucket (history first), so the slot of an entry is its rank in its own
-// window plus the number of entries of the other window that sort in front of it -- one lookup in
-// the other window's bucket offsets.
-// =====================================================================================
-constexpr uint32_t kScatterThreads = 512;
-
-__device__ __forceinline__ uint32_t off_at(const uint16_t* __restrict__ off, uint32_t n, uint32_t u, uint32_t h) {
-    return h < kWindow ? (uint32_t)__ldg(off + (size_t)u * kWindow + h) : window_count(n, u);
-}
-
-__global__ void __launch_bounds__(kScatterThreads) k_span_scatter(const uint8_t* __restrict__ in, uint32_t n, uint32_t w_first,
-                                                                  uint32_t w_begin, const uint32_t* __restrict__ items,
-                                                                  const uint16_t* __restrict__ off, uint2* __restrict__ M) {
-    __shared__ __align__(16) uint8_t sb[kWindow + 16];
-    const uint32_t v = w_first + blockIdx.x;
-    const uint32_t base = v * kWindow;
-    const uint32_t cnt = window_count(n, v);
-    const uint32_t n_win = (n + kWindow - 1) / kWindow;
-    stage_bytes(sb, in, (long long)base, kWindow + 16, n);
-    __syncthreads();
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb);
-    const uint32_t* Iv = items + (size_t)v * kWindow;
-    const bool as_target = v >= w_begin;             // span v exists (v is a window that gets encoded)
-    const bool as_history = v + 1 < n_win;           // span v + 1 exists
-    for (uint32_t r = threadIdx.x; r < cnt; r += kScatterThreads) {
-        const uint32_t it = __ldg(Iv + r);
-        const uint32_t h = it >> 15, pl = it & kWindowMask;
-        const bool first_own = (r == 0) || ((__ldg(Iv + r - 1) >> 15) != h);
-        const uint32_t a = pl >> 2, sh = (pl & 3u) * 8u;
-        const uint32_t w0 = sw[a], w1 = sw[a + 1], w2 = sw[a + 2];
-        const uint32_t v0 = __funnelshift_r(w0, w1, sh);       // bytes 0..3
-        const uint32_t v1 = __funnelshift_r(w1, w2, sh);       // bytes 4..7
-        const uint32_t lo = (v0 >> 24) | (v1 << 8);            // bytes 3..6
-        const uint32_t tg = tag9(v0 & 0xffu, (v0 >> 8) & 0xffu);
-        if (as_target) {
-            uint32_t idx = r;
-            bool first = first_own;
-            if (v > 0) {
-                const uint32_t e1 = off_at(off, n, v - 1, h + 1), e0 = off_at(off, n, v - 1, h);
-                idx += e1;
-                first = first && (e1 == e0);
-            }
-            M[(size_t)v * kSpanSlots + idx] = make_uint2(lo, tg | (first ? kSpanFirstBit : 0u) | ((pl + kWindow) << 15));
-        }
-        if (as_history) {
-            const uint32_t idx = r + off_at(off, n, v + 1, h);
-            M[(size_t)(v + 1) * kSpanSlots + idx] = make_uint2(lo, tg | (first_own ? kSpanFirstBit : 0u) | (pl << 15));
-        }
-    }
-}
-
-// =====================================================================================
-// k_match_chains: one CTA per span (the window being encoded plus the window in front of it).
-//   The span's merged entry list is cut into chunks; a warp runs through a chunk 32 entries at a
-//   time and keeps, per prefix length L = 3..7, a hash chain over the most recent entries:
-//   head[L][slot] = latest entry whose first L bytes hash to the slot, prevd[L][entry] = distance to
-//   the previous one.  The 32 entries of a step are linked among themselves with match.any.
-//   A target finds "the nearest candidate sharing at least L bytes" by following chain L until an
-//   entry with an equal key turns up or its candidate range ends -- the range being the previous
-//   max_hash_checks entries of its bucket (matching.rs:127: the chain budget counts every position
-//   with the same hash).  The reference keeps the first candidate that beats the running best;
-//   that is reproduced by asking for L = 3, then for (length found) + 1, and so on ("level walk").
-//   Once a candidate shares 7 bytes the remaining work is the reference's own loop restricted to
-//   chain 7: quick reject on the byte that would extend the best match (matching.rs:141-143), full
-//   comparison on the data staged in shared memory otherwise ("deep walk").
-//   Both walks are run as work loops: targets are queued, every lane of the warp owns one target at
-//   a time, makes one chain step per iteration and takes the next target when it is done, so lanes
-//   stay busy however uneven the chains are.  Full comparisons are batched: a lane whose candidate
-//   passed the quick reject parks until enough lanes wait.
-//   shared: 64 KiB + 272 B of data; per warp 256 entries, 4 x 256 + 512 chain links, 512 positions,
-//   5 x 128 heads and the two queues
-// =====================================================================================
-#ifndef DFL_CHAIN_WARPS
-#define DFL_CHAIN_WARPS 24
-#endif
-#ifndef DFL_CHAIN_DEEP_STEPS
-#define DFL_CHAIN_DEEP_STEPS 4
-#endif
-#ifndef DFL_CHAIN_PARK_MIN
-#define DFL_CHAIN_PARK_MIN 8
-#endif
-#ifndef DFL_CHAIN_CHUNK
-#define DFL_CHAIN_CHUNK 1024
-#endif
-constexpr uint32_t kChainWarps = DFL_CHAIN_WARPS;
-constexpr uint32_t kChainThreads = kChainWarps * 32;
-constexpr uint32_t kChainCtx = kChainMaxChecks;         // entries re-inserted in front of a chunk
-constexpr uint32_t kChainSlots = 128;                   // head slots per level
-constexpr uint32_t kChainRingS = 256;                   // entries + links of levels 3..6: alive during the level walk
-constexpr uint32_t kChainRingD = 512;                   // level-7 links + positions: alive during the deep walk
-constexpr uint32_t kChainLQ = 64, kChainDQ = 64;        // queue capacities (a step adds at most 32 to each)
-constexpr int kChainDeepSteps = DFL_CHAIN_DEEP_STEPS;                      // chain steps per iteration of the deep work loop
-constexpr uint32_t kChainParkMin = DFL_CHAIN_PARK_MIN;                   // parked lanes that trigger a comparison round
-constexpr uint32_t kChainData = 2 * kWindow + 272;
-constexpr uint32_t kChainWarpBytes = kChainRingS * 8 + (kChainLevels - 1) * kChainRingS + kChainRingD + kChainRingD * 2 +
-                                     kChainLevels * kChainSlots * 2 + kChainLQ * 4 + kChainDQ * 8;
-constexpr uint32_t kChainSmem = kChainData + kChainWarps * kChainWarpBytes + 16;
-static_assert(kChainCtx % 32 == 0 && kChainCtx + 96 <= kChainRingS, "the small ring must hold a step, its range and some slack");
-constexpr uint32_t kChainChunk = DFL_CHAIN_CHUNK;                  // entries per unit of work
-static_assert(kChainChunk + 32 + kChainCtx + kChainRingD < 65536, "local indices are 16 bit");
-static_assert(kChainSmem <= 227 * 1024, "shared memory budget");
-
-__global__ void __launch_bounds__(kChainThreads, 1)
-k_match_chains(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, uint32_t checks,
-               const uint2* __restrict__ M, uint32_t* __restrict__ Mf) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t w = w_first + blockIdx.x;
-    const uint32_t base = w * kWindow;                   // first byte of the target window
-    const uint32_t cnt_t = window_count(n, w);
-    const uint32_t ne = cnt_t + (w > 0 ? window_count(n, w - 1) : 0u);
-    if (cnt_t == 0) return;
-    // shared data index of absolute position a is a - base + 32768 == position-in-span
-    stage_bytes(smem, in, (long long)base - (long long)kWindow, kChainData, n);
-    uint32_t* next_chunk = reinterpret_cast<uint32_t*>(smem + kChainData + kChainWarps * kChainWarpBytes);
-    if (threadIdx.x == 0) *next_chunk = 0u;
-    __syncthreads();
-    const uint8_t* data = smem;
-    const uint32_t* dataw = reinterpret_cast<const uint32_t*>(smem);
-    uint8_t* wbase = smem + kChainData + warp_id() * kChainWarpBytes;
-    uint2* ring = reinterpret_cast<uint2*>(wbase);                                        // [kChainRingS]
-    uint8_t* prevs = wbase + kChainRingS * 8;                                             // [level 0..3][kChainRingS]
-    uint8_t* prev7 = prevs + (kChainLevels - 1) * kChainRingS;                            // [kChainRingD]
-    uint16_t* cpos16 = reinterpret_cast<uint16_t*>(prev7 + kChainRingD);                  // [kChainRingD]
-    uint16_t* head = cpos16 + kChainRingD;                                                // [level][slot]
-    uint32_t* lq = reinterpret_cast<uint32_t*>(head + kChainLevels * kChainSlots);        // li | lb << 16
-    uint2* dq = reinterpret_cast<uint2*>(lq + kChainLQ);                                  // + best_len | best_pos << 9
-    const uint2* E = M + (size_t)w * kSpanSlots;
-    const uint32_t lane = lane_id();
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    constexpr uint32_t MS = kChainRingS - 1, MD = kChainRingD - 1;
-    constexpr uint32_t kTop = kChainLevels - 1;
-
-    // ---- level walk state (one target per lane)
-    bool l_busy = false;
-    uint32_t l_elo = 0, l_ehi = 0, l_li = 0, l_lb = 0, l_j = 0, l_lvl = 0, l_mask = 0, l_best_len = 1, l_best_pos = 0, l_maxl = 0;
-    uint32_t lq_head = 0, lq_tail = 0;                   // warp-uniform
-    // ---- deep walk state
-    uint32_t d_state = 0;                                // 0 idle, 1 walking, 2 parked on a candidate that passed the quick reject
-    uint32_t d_link = 0, d_pos = 0, d_lb = 0, d_j = 0, d_best_len = 0, d_best_pos = 0, d_maxl = 0, d_myfb = 0, d_cpos = 0;
-    uint32_t dq_head = 0, dq_tail = 0;
-
-    auto level_iterate = [&]() {
-        const uint32_t idle = __ballot_sync(0xffffffffu, !l_busy);
-        const uint32_t avail = lq_tail - lq_head;
-        if (idle != 0u && avail != 0u) {
-            const uint32_t r = __popc(idle & lt_mask);
-            if (!l_busy && r < avail) {
-                const uint32_t t = lq[(lq_head + r) & (kChainLQ - 1)];
-                l_li = t & 0xffffu; l_lb = t >> 16;
-                const uint2 e = ring[l_li & MS];
-                l_elo = e.x; l_ehi = e.y;
-                const uint32_t p = base + span_entry_pos(e.y) - kWindow;
-                l_maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
-                l_j = l_li; l_lvl = 0; l_mask = 0; l_best_len = 1; l_best_pos = span_entry_pos(e.y);
-                l_busy = true;
-            }
-            const uint32_t taken = __popc(idle);
-            lq_head += taken < avail ? taken : avail;
-        }
-        bool to_deep = false;
-        if (l_busy) {
-            const uint32_t pos = span_entry_pos(l_ehi);
-            const uint32_t dl = (l_lvl == kTop) ? prev7[l_j & MD] : prevs[l_lvl * kChainRingS + (l_j & MS)];
-            l_j -= dl;                                    // a link of 255 means "none": it always leaves the range
-            bool fin = l_j < l_lb;
-            if (!fin) {
-                const uint2 ce = ring[l_j & MS];
-                const uint32_t xlo = ce.x ^ l_elo;
-                if (((xlo & l_mask) | ((ce.y ^ l_ehi) & kSpanTagMask)) == 0u) {             // else: slot collision, walk on
-                    const uint32_t cpos = span_entry_pos(ce.y);
-                    const uint32_t l = span_entry_lcp(xlo);
-                    if (pos - cpos > kWindow) fin = true;                                     // matching.rs:102-106
-                    else if (l >= l_maxl) { l_best_len = l_maxl; l_best_pos = cpos; fin = true; }
-                    else if (l < kSpanEntryBytes) {
-                        // the nearest candidate with >= lvl + 3 bytes has exactly l: now look for l + 1
-                        l_best_len = l; l_best_pos = cpos;
-                        l_lvl = l - 2u; l_mask = span_level_mask(l_lvl);
-                        l_j = l_li;
-                    } else to_deep = true;
-                }
-            }
-            if (fin) {
-                Mf[base + pos - kWindow] = finalize_match(l_best_len, pos - l_best_pos);
-                l_busy = false;
-            }
-        }
-        const uint32_t dmask = __ballot_sync(0xffffffffu, to_deep);
-        if (dmask) {
-            if (to_deep) {
-                dq[(dq_tail + __popc(dmask & lt_mask)) & (kChainDQ - 1)] =
-                    make_uint2(l_li | (l_lb << 16), l_best_len | (l_best_pos << 9));
-                l_busy = false;
-            }
-            dq_tail += __popc(dmask);
-            __syncwarp();                                 // the queue entries are visible before a deep iteration reads them
-        }
-    };
-
-    // unaligned 64-bit little-endian read from the staged data
-    auto lds64 = [&](uint32_t byte_idx, uint32_t& lo, uint32_t& hi) {
-        const uint32_t a = byte_idx >> 2, sh = (byte_idx & 3u) * 8u;
-        const uint32_t w0 = dataw[a], w1 = dataw[a + 1], w2 = dataw[a + 2];
-        lo = __funnelshift_r(w0, w1, sh);
-        hi = __funnelshift_r(w1, w2, sh);
-    };
-    auto deep_iterate = [&]() {
-        const uint32_t idle = __ballot_sync(0xffffffffu, d_state == 0u);
-        const uint32_t avail = dq_tail - dq_head;
-        if (idle != 0u && avail != 0u) {
-            const uint32_t r = __popc(idle & lt_mask);
-            if (d_state == 0u && r < avail) {
-                const uint2 t = dq[(dq_head + r) & (kChainDQ - 1)];
-                d_j = t.x & 0xffffu; d_lb = t.x >> 16;
-                d_best_len = t.y & 0x1ffu; d_best_pos = t.y >> 9;
-                d_pos = cpos16[d_j & MD];
-                d_link = prev7[d_j & MD];
-                const uint32_t p = base + d_pos - kWindow;
-                d_maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
-                d_myfb = data[d_pos + d_best_len];
-                d_state = 1u;
-            }
-            const uint32_t taken = __popc(idle);
-            dq_head += taken < avail ? taken : avail;
-        }
-#pragma unroll
-        for (int u = 0; u < kChainDeepSteps; u++) {       // chain steps of the walking lanes
-            if (d_state == 1u) {
-                d_j -= d_link;
-                const uint32_t a = d_j & MD;
-                d_link = prev7[a];
-                const uint32_t cpos = cpos16[a];
-                if (d_j < d_lb || d_pos - cpos > kWindow) d_state = 3u;                      // range end / matching.rs:102-106
-                else if (data[cpos + d_best_len] == d_myfb) { d_state = 2u; d_cpos = cpos; } // matching.rs:141-143
-            }
-        }
-        const uint32_t pmask = __ballot_sync(0xffffffffu, d_state == 2u);
-        if (pmask != 0u && ((uint32_t)__popc(pmask) >= kChainParkMin || !__any_sync(0xffffffffu, d_state == 1u))) {
-            // comparison round: real length of every parked candidate (any bucket member is a legal
-            // candidate, so the comparison starts at byte 0 and needs no key check)
-            if (d_state == 2u) {
-                uint32_t l = 0;
-                while (l < d_maxl) {
-                    uint32_t a0, a1, b0, b1;
-                    lds64(d_pos + l, a0, a1);
-                    lds64(d_cpos + l, b0, b1);
-                    const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1;
-                    if (x0 | x1) { l += x0 ? ((uint32_t)(__ffs((int)x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3); break; }
-                    l += 8;
-                }
-                l = l < d_maxl ? l : d_maxl;
-                d_state = 1u;
-                if (l > d_best_len) {                     // strictly longer: the nearest candidate wins ties
-                    d_best_len = l; d_best_pos = d_cpos;
-                    if (l == d_maxl) d_state = 3u;        // matching.rs:152-156
-                    else d_myfb = data[d_pos + l];
-                }
-            }
-        }
-        if (d_state == 3u) {
-            Mf[base + d_pos - kWindow] = finalize_match(d_best_len, d_pos - d_best_pos);
-            d_state = 0u;
-        }
-    };
-
-    // oldest local index a queued or running target can still look at
-    auto oldest_level = [&]() {
-        uint32_t mine = l_busy ? l_lb : 0xffffffffu;
-        if (lane == 0 && lq_tail != lq_head) { const uint32_t t = lq[lq_head & (kChainLQ - 1)] >> 16; mine = mine < t ? mine : t; }
-        return __reduce_min_sync(0xffffffffu, mine);
-    };
-    auto oldest_deep = [&]() {
-        uint32_t mine = d_state != 0u ? d_lb : 0xffffffffu;
-        if (lane == 0 && dq_tail != dq_head) { const uint32_t t = dq[dq_head & (kChainDQ - 1)].x >> 16; mine = mine < t ? mine : t; }
-        return __reduce_min_sync(0xffffffffu, mine);
-    };
-
-    // warps take chunks of the span's entries as they become free (chains are very uneven across buckets)
-    for (;;) {
-        uint32_t a = 0;
-        if (lane == 0) a = atomicAdd(next_chunk, kChainChunk);
-        a = __shfl_sync(0xffffffffu, a, 0);
-        if (a >= ne) break;
-        const uint32_t chunk = kChainChunk;
-        const uint32_t ctx = a >= kChainCtx ? a - kChainCtx : 0u;
-        const uint32_t b = a + chunk < ne ? a + chunk : ne;
-        for (uint32_t i = lane; i < kChainLevels * kChainSlots / 2; i += 32) reinterpret_cast<uint32_t*>(head)[i] = 0u;
-        __syncwarp();
-        uint32_t bs_carry = kChainRingD;                 // local index of the first entry of the current bucket
-        uint2 nxt = make_uint2(0u, 0u);
-        if (ctx + lane < b) nxt = __ldg(E + ctx + lane);
-        for (uint32_t m0 = ctx; m0 < b; m0 += 32) {
-            const uint32_t m = m0 + lane;
-            const bool valid = m < b;
-            const uint2 e = nxt;
-            if (m + 32 < b) nxt = __ldg(E + m + 32);
-            const uint32_t li0 = m0 - ctx + kChainRingD; // local index of lane 0; never 0, so a zero head means "none"
-            const uint32_t li = li0 + lane;
-            // the slots about to be overwritten must be dead
-            while (oldest_level() < li0 + 32u - kChainRingS) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
-            while (oldest_deep() < li0 + 32u - kChainRingD) deep_iterate();
-            __syncwarp();
-            const uint32_t pos = span_entry_pos(e.y);
-            if (valid) { ring[li & MS] = e; cpos16[li & MD] = (uint16_t)pos; }
-            const uint32_t fmask = __ballot_sync(0xffffffffu, valid && (e.y & kSpanFirstBit));
-            const uint32_t fle = fmask & (lt_mask | (1u << lane));
-            const uint32_t bs = fle ? li0 + (31u - (uint32_t)__clz((int)fle)) : bs_carry;
-            if (fmask) bs_carry = li0 + (31u - (uint32_t)__clz((int)fmask));
-            // ---- link the 32 entries into the chains of every level
-#pragma unroll
-            for (uint32_t lv = 0; lv < kChainLevels; lv++) {
-                const uint32_t sg = span_sig(e.x, e.y, lv) >> 1;                 // 7 bits
-                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? sg : (0x100u | lane));
-                const uint32_t below = grp & lt_mask;
-                const uint32_t pi = below ? li0 + (31u - (uint32_t)__clz((int)below)) : (uint32_t)head[lv * kChainSlots + sg];
-                const uint32_t dl = li - pi < 255u ? li - pi : 255u;
-                __syncwarp();                             // every lane has read its head before the group leaders replace them
-                if (valid) {
-                    if (lv == kTop) prev7[li & MD] = (uint8_t)dl; else prevs[lv * kChainRingS + (li & MS)] = (uint8_t)dl;
-                    if ((grp >> lane) == 1u) head[lv * kChainSlots + sg] = (uint16_t)li;
-                }
-            }
-            // ---- queue the targets of this step: entries of the window being encoded, at or after `begin`
-            const bool is_target = valid && m >= a && pos >= kWindow && base + pos - kWindow >= begin;
-            const uint32_t tmask = __ballot_sync(0xffffffffu, is_target);
-            if (is_target) {
-                const uint32_t lb = bs > li - checks ? bs : li - checks;
-                lq[(lq_tail + __popc(tmask & lt_mask)) & (kChainLQ - 1)] = li | (lb << 16);
-            }
-            lq_tail += __popc(tmask);
-            __syncwarp();
-            // lanes still walking keep their state across steps
-            while (lq_tail != lq_head) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
-            while (dq_tail != dq_head) deep_iterate();
-        }
-        // the next chunk restarts the local indices: finish everything
-        while (__any_sync(0xffffffffu, l_busy)) { level_iterate(); while (dq_tail - dq_head > 32u) deep_iterate(); }
-        while (dq_tail != dq_head || __any_sync(0xffffffffu, d_state != 0u)) deep_iterate();
-    }
-}
-
-// =====================================================================================
-// parse
+// parse: the reference's token selection (lz77.rs:305-547, rle.rs:23-71) over the match records, one lane per
+// segment, with the long records resolved on the data by the whole warp.
+//   A lane runs its parser until the position it examines has a long record; it then parks with a request
+//   (position, candidate range, floor = prev_length).  When few lanes are left running the warp serves the
+//   parked lanes one after the other: 32 candidates per round, lane-private entry test (all 8 entry bytes
+//   equal), the reference's quick reject on the byte that would extend the best match (matching.rs:141-143),
+//   a lock-step byte comparison 8 bytes at a time, and a warp max that keeps the nearest of the longest
+//   (matching.rs:148-157).  Only positions the reference's parser searches are ever resolved: everything
+//   inside an emitted match is skipped (lz77.rs:398-405), which is 70-85 % of all positions on text.
 // =====================================================================================
 __device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key) {
     ParseState s;
@@ -884,6 +497,7 @@ __device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key)
 struct ParseArgs {
     const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
     const uint32_t* Mf; const uint32_t* Mq;
+    const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window (long records refer to them)
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
     uint32_t n_seg;
@@ -892,8 +506,115 @@ struct ParseArgs {
     uint32_t init_key;             // state at `begin`
 };
 
-// Runs the reference's token selection from `st` until the first iteration position >= b.
-__device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
+// 8 bytes at in[idx ..] (idx < n), little endian; bytes past the last word of the input read as 0 (callers clamp
+// the lengths they derive to the bytes that exist).  Works for any alignment of `in`.
+__device__ __forceinline__ unsigned long long ld8(const uint8_t* __restrict__ in, const uint32_t* last_word, uint32_t idx) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t x0 = __ldg(w);
+    const uint32_t x1 = (w + 1 <= last_word) ? __ldg(w + 1) : 0u;
+    const uint32_t x2 = (w + 2 <= last_word) ? __ldg(w + 2) : 0u;
+    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// What a parked lane asks for.  Filled by the lane itself (its loads overlap the other lanes' parsing).
+struct Resolve {
+    uint32_t p;        // position
+    uint32_t rank;     // index of the position in its window's sorted list
+    uint32_t k0;       // first visit to look at (rec_k8)
+    uint32_t floor;    // prev_length: only a longer result is of use (matching.rs:161-165)
+    uint32_t n_own;    // visits k < n_own are Kw[rank - 1 - k]
+    uint32_t n_vis;    // visits allowed in total (chain budget; the previous window's share may end earlier)
+    uint32_t pe;       // visit k >= n_own is Kp[pe - 1 - (k - n_own)]
+    uint32_t me_lo, me_hi;
+};
+
+__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t p, uint32_t rec, uint32_t floor,
+                                                uint32_t budget) {
+    const uint32_t w = p >> 15, pl = p & kWindowMask;
+    r.p = p; r.rank = rec_rank(rec); r.k0 = rec_k8(rec); r.floor = floor;
+    const uint2 me = __ldg(A.K + (size_t)w * kWindow + r.rank);
+    r.me_lo = me.x; r.me_hi = me.y;
+    const uint32_t h = hash3(A.in[p], A.in[p + 1], A.in[p + 2]);
+    const uint16_t* ow = A.off + (size_t)w * kWindow;
+    const uint32_t full = A.prm.checks;
+    const uint32_t s0 = __ldg(ow + h);
+    r.n_own = r.rank - s0 < full ? r.rank - s0 : full;
+    uint32_t n_tot = r.n_own;
+    r.pe = 0;
+    if (w > 0 && r.n_own < full) {
+        const uint16_t* op = ow - kWindow;
+        const uint32_t ps = __ldg(op + h);
+        r.pe = (h + 1u < kWindow) ? (uint32_t)__ldg(op + h + 1u) : window_count(A.n, w - 1);
+        const uint32_t rem = full - r.n_own;
+        n_tot += (r.pe - ps > rem) ? rem : r.pe - ps;   // entries with a position below pl are cut off during the rounds
+    }
+    r.n_vis = n_tot < budget ? n_tot : budget;
+    (void)pl;
+}
+
+// Served by the whole warp; every argument is warp-uniform.  Returns a finalize_match record (0 = nothing longer
+// than the floor).
+__device__ __forceinline__ uint32_t resolve_warp(const ParseArgs& A, const Resolve& r) {
+    const uint32_t lane = lane_id();
+    const uint32_t p = r.p, w = p >> 15, pl = p & kWindowMask;
+    const uint32_t maxl = (A.n - p) < kMaxMatch ? (A.n - p) : kMaxMatch;
+    const uint32_t start = r.floor > kEntryBytes - 1u ? r.floor : kEntryBytes - 1u;
+    uint32_t best = start, best_q = 0;
+    if (best >= maxl) return 0u;
+    const uint2* Kw = A.K + (size_t)w * kWindow;
+    const uint2* Kp = Kw - kWindow;
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + A.n - 1) & ~(uintptr_t)3);
+    for (uint32_t kb = r.k0; kb < r.n_vis; kb += 32) {
+        const uint32_t k = kb + lane;
+        bool eq = false, ended = false;
+        uint32_t q = 0;
+        if (k < r.n_vis) {
+            const bool own = k < r.n_own;
+            const uint2 e = __ldg(own ? Kw + (r.rank - 1u - k) : Kp + (r.pe - 1u - (k - r.n_own)));
+            const uint32_t ep = entry_pos(e.y);
+            if (!own && ep < pl) ended = true;              // beyond the window (matching.rs:102-106); so is everything older
+            else {
+                eq = (e.x == r.me_lo) && (((e.y ^ r.me_hi) & kEntryKeyHi) == 0u);
+                q = (own ? w : w - 1u) * kWindow + ep;
+            }
+        }
+        // the byte that would extend the running best (matching.rs:141-143)
+        if (eq) eq = A.in[q + best] == A.in[p + best];
+        if (__any_sync(0xffffffffu, eq)) {
+            uint32_t l = kEntryBytes, mine = 0;
+            bool alive = eq;
+            while (__any_sync(0xffffffffu, alive)) {         // lock step: l is the same in every lane that is alive
+                if (alive) {
+                    const unsigned long long x = ld8(A.in, last_word, p + l) ^ ld8(A.in, last_word, q + l);
+                    if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
+                    else if (l + 8u >= maxl) { mine = maxl; alive = false; }
+                }
+                l += 8u;
+            }
+            mine = mine < maxl ? mine : maxl;
+            const uint32_t key = (eq && mine > best) ? ((mine << 5) | (31u - lane)) : 0u;
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+            if (mx != 0u) {                                   // the longest of the round; the nearest among equals
+                best = mx >> 5;
+                best_q = __shfl_sync(0xffffffffu, q, 31u - (mx & 31u));
+                if (best >= maxl) break;                      // matching.rs:152-156
+            }
+        }
+        if (__any_sync(0xffffffffu, ended)) break;
+    }
+    return best > start ? finalize_match(best, p - best_q) : 0u;
+}
+
+#ifndef DFL_PARSE_KEEP
+#define DFL_PARSE_KEEP 12     // keep parsing while at least this many lanes of a warp are running
+#endif
+
+// Every lane of the calling warp enters (work == false: the lane only helps with resolutions).  A lane with work
+// runs the reference's token selection from `st` until the first iteration position >= b.
+__device__ void parse_lanes(const ParseArgs& A, bool work, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
     uint32_t* tk = A.segtok + (size_t)s * A.tok_cap;
     uint32_t nt = 0;
     bool have_e = false;
@@ -901,44 +622,103 @@ __device__ void parse_segment(const ParseArgs& A, uint32_t s, ParseState st, uin
     const uint32_t n = A.n;
     const int mode = A.prm.mode;
     const bool has_m = (mode != kRle) && (A.prm.checks > 0);
-    uint32_t out[2];
-    while (st.pos < n) {
-        if (!have_e && st.pos >= a) { epos = st.pos; ekey = parse_state_key(st); etok = nt; have_e = true; }
-        if (st.pos >= b) break;
-        const uint32_t p = st.pos;
-        int ne;
-        if (mode == kLazy) {
-            uint32_t mf = 0, mq = 0;
-            if (p + 2u < n && !st.ign) {
-                if (st.prev_len >= 32u) mq = A.prm.need_quarter ? A.Mq[p] : 0u;
-                else mf = A.Mf[p];
+    const uint32_t lane = lane_id();
+    bool running = work, parked = false, have_m = false;
+    uint32_t m_ready = 0;
+    Resolve rq;
+    rq.p = rq.rank = rq.k0 = rq.floor = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = 0;
+    for (;;) {
+        // ---- parse: every running lane takes one step per iteration
+        for (;;) {
+            if (running && !parked) {
+                bool stop_here = st.pos >= n;
+                if (!stop_here) {
+                    if (!have_e && st.pos >= a) { epos = st.pos; ekey = parse_state_key(st); etok = nt; have_e = true; }
+                    stop_here = st.pos >= b;
+                }
+                if (stop_here) {
+                    if (!have_e) { epos = st.pos; ekey = parse_state_key(st); etok = nt; }
+                    A.e_pos[s] = epos; A.e_key[s] = ekey; A.e_tok[s] = etok;
+                    A.x_pos[s] = st.pos; A.x_key[s] = parse_state_key(st); A.x_tok[s] = nt;
+                    running = false;
+                } else {
+                    const uint32_t p = st.pos;
+                    uint32_t m = 0;
+                    if (have_m) { m = m_ready; have_m = false; }
+                    else if (has_m && p + 2u < n) {
+                        if (mode == kLazy) {
+                            if (!st.ign) {                                   // the only case in which the reference searches (lz77.rs:347)
+                                const bool quarter = st.prev_len >= 32u;     // lz77.rs:351-355
+                                if (!quarter || A.prm.need_quarter) {
+                                    m = quarter ? A.Mq[p] : A.Mf[p];
+                                    if (rec_is_long(m)) {
+                                        resolve_prepare(A, rq, p, m, st.prev_len, quarter ? A.prm.checks_quarter : A.prm.checks);
+                                        parked = true;
+                                    }
+                                }
+                            }
+                        } else {
+                            m = A.Mf[p];
+                            if (rec_is_long(m)) { resolve_prepare(A, rq, p, m, 0u, A.prm.checks); parked = true; }
+                        }
+                    }
+                    if (!parked) {
+                        uint32_t out[2];
+                        int ne;
+                        if (mode == kLazy) ne = lazy_step(st, n, A.in, m, m, A.prm.lazy, out);
+                        else if (mode == kGreedy) ne = greedy_step(st, n, A.in, m, out);
+                        else ne = rle_step(st, n, A.in, out);   // rle.rs runs over the buffer from its first byte
+                        if (nt + (uint32_t)ne <= A.tok_cap) {
+                            if (ne > 0) tk[nt] = out[0];
+                            if (ne > 1) tk[nt + 1] = out[1];
+                        }
+                        nt += (uint32_t)ne;
+                    }
+                }
             }
-            ne = lazy_step(st, n, A.in, mf, mq, A.prm.lazy, out);
-        } else if (mode == kGreedy) {
-            uint32_t mf = (has_m && p + 2u < n) ? A.Mf[p] : 0u;
-            ne = greedy_step(st, n, A.in, mf, out);
-        } else {
-            // rle.rs runs over the buffer from its first byte; relative to `begin` for a resumed stream
-            ne = rle_step(st, n, A.in, out);
+            const uint32_t going = __ballot_sync(0xffffffffu, running && !parked);
+            if (going == 0u) break;
+            if ((uint32_t)__popc(going) < DFL_PARSE_KEEP && __any_sync(0xffffffffu, parked)) break;
         }
-        if (nt + (uint32_t)ne <= A.tok_cap) {
-            if (ne > 0) tk[nt] = out[0];
-            if (ne > 1) tk[nt + 1] = out[1];
+        // ---- resolve: the warp serves its parked lanes in turn
+        uint32_t waiting = __ballot_sync(0xffffffffu, parked);
+        if (waiting == 0u) {
+            if (!__any_sync(0xffffffffu, running)) break;
+            continue;
         }
-        nt += (uint32_t)ne;
+        while (waiting) {
+            const int j = __ffs((int)waiting) - 1;
+            waiting &= waiting - 1u;
+            Resolve r;
+            r.p = __shfl_sync(0xffffffffu, rq.p, j);
+            r.rank = __shfl_sync(0xffffffffu, rq.rank, j);
+            r.k0 = __shfl_sync(0xffffffffu, rq.k0, j);
+            r.floor = __shfl_sync(0xffffffffu, rq.floor, j);
+            r.n_own = __shfl_sync(0xffffffffu, rq.n_own, j);
+            r.n_vis = __shfl_sync(0xffffffffu, rq.n_vis, j);
+            r.pe = __shfl_sync(0xffffffffu, rq.pe, j);
+            r.me_lo = __shfl_sync(0xffffffffu, rq.me_lo, j);
+            r.me_hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
+            const uint32_t res = resolve_warp(A, r);
+            if ((int)lane == j) { m_ready = res; have_m = true; parked = false; }
+        }
     }
-    if (!have_e) { epos = st.pos; ekey = parse_state_key(st); etok = nt; }
-    A.e_pos[s] = epos; A.e_key[s] = ekey; A.e_tok[s] = etok;
-    A.x_pos[s] = st.pos; A.x_key[s] = parse_state_key(st); A.x_tok[s] = nt;
 }
 
-__global__ void __launch_bounds__(128) k_parse_spec(ParseArgs A) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_seg) return;
-    uint32_t a = A.begin + s * A.seg;
-    uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
-    uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
-    parse_segment(A, s, (s == 0) ? state_from_key(A.begin, A.init_key) : parse_state_init(start), a, b);
+constexpr uint32_t kParseThreads = 128;
+
+__global__ void __launch_bounds__(kParseThreads) k_parse_spec(ParseArgs A) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool work = s < A.n_seg;
+    uint32_t a = 0, b = 0;
+    ParseState st = parse_state_init(0);
+    if (work) {
+        a = A.begin + s * A.seg;
+        b = a + A.seg < A.end ? a + A.seg : A.end;
+        const uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
+        st = (s == 0) ? state_from_key(A.begin, A.init_key) : parse_state_init(start);
+    }
+    parse_lanes(A, work, s, st, a, b);
 }
 
 __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* start_pos,
@@ -958,32 +738,45 @@ __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad,
     bad[s] = is_bad;
 }
 
-__global__ void __launch_bounds__(128) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
-                                                      const uint32_t* start_key, DevMeta* meta) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_seg || !bad[s]) return;
-    uint32_t a = A.begin + s * A.seg;
-    uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
-    parse_segment(A, s, state_from_key(start_pos[s], start_key[s]), a, b);
-    atomicAdd(&meta->n_repaired_par, 1u);
+__global__ void __launch_bounds__(kParseThreads) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
+                                                                const uint32_t* start_key, DevMeta* meta) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool work = s < A.n_seg && bad[s];
+    if (!__any_sync(0xffffffffu, work)) return;
+    uint32_t a = 0, b = 0;
+    ParseState st = parse_state_init(0);
+    if (work) {
+        a = A.begin + s * A.seg;
+        b = a + A.seg < A.end ? a + A.seg : A.end;
+        st = state_from_key(start_pos[s], start_key[s]);
+        atomicAdd(&meta->n_repaired_par, 1u);
+    }
+    parse_lanes(A, work, s, st, a, b);
 }
 
-// Sequential fallback: walks the segments in order and re-parses every one whose entry does not
-// continue its predecessor's exit.  Exact for any input; only slow on inputs whose speculative
-// parses never resynchronise (e.g. megabytes of a single repeated byte).
-__global__ void k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
+// Sequential fallback (one warp; lane 0 parses, the others help with resolutions): walks the segments in order
+// and re-parses every one whose entry does not continue its predecessor's exit.  Exact for any input; only slow
+// on inputs whose speculative parses never resynchronise (e.g. megabytes of a single repeated byte).
+__global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
     if (meta->n_bad == 0) return;
+    const uint32_t lane = lane_id();
     for (uint32_t s = 1; s < A.n_seg; s++) {
-        uint32_t xp = A.x_pos[s - 1], xk = A.x_key[s - 1];
-        if (xp != A.e_pos[s] || xk != A.e_key[s]) {
-            uint32_t a = A.begin + s * A.seg;
-            uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
-            parse_segment(A, s, state_from_key(xp, xk), a, b);
-            meta->n_repaired_seq++;
+        uint32_t xp = 0, xk = 0, isbad = 0;
+        if (lane == 0) {
+            xp = A.x_pos[s - 1]; xk = A.x_key[s - 1];
+            isbad = (xp != A.e_pos[s] || xk != A.e_key[s]) ? 1u : 0u;
+        }
+        isbad = __shfl_sync(0xffffffffu, isbad, 0);
+        if (isbad) {
+            const uint32_t a = A.begin + s * A.seg;
+            const uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
+            parse_lanes(A, lane == 0, s, state_from_key(xp, xk), a, b);
+            if (lane == 0) meta->n_repaired_seq++;
             __threadfence();
+            __syncwarp();
         }
     }
-    meta->n_bad = 0;
+    if (lane == 0) meta->n_bad = 0;
 }
 
 __global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; }
@@ -1588,6 +1381,7 @@ uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 
 static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     ParseArgs A;
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
+    A.K = b.K; A.off = b.off;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
@@ -1597,27 +1391,29 @@ static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     return A;
 }
 
-static bool g_attr_done = false;
+// cudaFuncSetAttribute applies to the current device: once per device that is used
 static cudaError_t ensure_attrs() {
-    if (g_attr_done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_window_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_window_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
-    g_attr_done = true;
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return cudaSuccess;
 }
 
 // Window ranges: the sort needs windows [first_sort_window(j), n_windows(j)), the match stage
 // [first_match_window(j), n_windows(j)).  Both can be issued in pieces [w_lo, w_hi) as the input
 // arrives (dfl_compress overlaps the host-to-device copy with them); matching window w needs the
-// sorted lists of w - 1 and w (the chain path also the bucket offsets of w + 1, so it is issued whole).
+// sorted lists of w - 1 and w.
 uint32_t n_windows(const EncodeJob& j) { return (j.n + kWindow - 1) / kWindow; }
 uint32_t first_match_window(const EncodeJob& j) { return j.begin / kWindow; }
 uint32_t first_sort_window(const EncodeJob& j) { uint32_t w = j.begin / kWindow; return w > 0 ? w - 1 : 0; }
@@ -1626,12 +1422,7 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, 
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
-    if (use_chains(j.prm)) {
-        k_window_sort<true><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
-        DFL_LAUNCH_CHECK();
-        return cudaSuccess;
-    }
-    k_window_sort<false><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
+    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1640,16 +1431,6 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
-    if (use_chains(j.prm)) {
-        // issued once, over every window: [w_lo, w_hi) must be the whole range here
-        const uint32_t w_sort = first_sort_window(j);
-        k_span_scatter<<<n_windows(j) - w_sort, kScatterThreads, 0, st>>>(j.d_in, j.n, w_sort, first_match_window(j),
-                                                                          reinterpret_cast<const uint32_t*>(b.K), b.off, b.M);
-        DFL_LAUNCH_CHECK();
-        k_match_chains<<<w_hi - w_lo, kChainThreads, kChainSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm.checks, b.M, b.Mf);
-        DFL_LAUNCH_CHECK();
-        return cudaSuccess;
-    }
     // enough CTAs to fill the chip even for a handful of windows
     const uint32_t n_w = w_hi - w_lo;
     uint32_t parts = (148u * DFL_MATCH_CTAS + n_w - 1) / n_w / (j.peers ? j.peers : 1u);
@@ -1666,8 +1447,8 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
 cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     ParseArgs A = make_parse_args(j, b);
     if (A.n_seg == 0) return cudaSuccess;
-    uint32_t grid = (A.n_seg + 127) / 128;
-    k_parse_spec<<<grid, 128, 0, st>>>(A);
+    uint32_t grid = (A.n_seg + kParseThreads - 1) / kParseThreads;
+    k_parse_spec<<<grid, kParseThreads, 0, st>>>(A);
     DFL_LAUNCH_CHECK();
     if (A.n_seg == 1) return cudaSuccess;
     for (uint32_t r = 0; r < kRepairRounds; r++) {
@@ -1675,14 +1456,14 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
         DFL_LAUNCH_CHECK();
         k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
-        k_parse_repair<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
+        k_parse_repair<<<grid, kParseThreads, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
     }
     k_reset_bad<<<1, 1, 0, st>>>(b.meta);
     DFL_LAUNCH_CHECK();
     k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
     DFL_LAUNCH_CHECK();
-    k_parse_repair_seq<<<1, 1, 0, st>>>(A, b.meta);
+    k_parse_repair_seq<<<1, 32, 0, st>>>(A, b.meta);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -190,13 +190,6 @@ int dfl_encode_tokens(const uint8_t *in, size_t n, const uint32_t *tokens, size_
 int dfl_lz77_tokens(const uint8_t *in, size_t n, const dfl_options *opt, uint32_t *tokens,
                     size_t tokens_cap, size_t *n_tokens);
 
-/* Tuning hook, process wide: which match kernels serve option sets that both paths can handle
- * (max_hash_checks 1..128 without quarter-budget searches).  0 = candidate walk (k_match, the
- * default), 1 = span entries + multi-level chains (k_span_scatter + k_match_chains).  The two
- * produce identical bytes; the switch exists to time them against each other.  Returns the
- * previous value.  Environment override at load time: DFL_MATCH_PATH=walk|chains. */
-int dfl_set_match_path(int path);
-
 #ifdef __cplusplus
 }
 #endif

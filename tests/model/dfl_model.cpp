@@ -54,231 +54,100 @@ void window_sort(const uint8_t* d, uint32_t n, std::vector<Entry>& K, std::vecto
     }
 }
 
-struct HostBytes {
-    const uint8_t* d;
-    uint32_t byte(uint32_t i) const { return d[i]; }
-    uint32_t common_prefix(uint32_t a, uint32_t c, uint32_t from, uint32_t maxl) const {
-        uint32_t l = from;
-        while (l < maxl && d[a + l] == d[c + l]) l++;
-        return l;
+// Candidates of sorted entry i of window s, most recent first (matching.rs:102-106,127): the entries in front of
+// it in its own bucket, then the tail of the same bucket of the previous window at distance <= 32768, at most
+// `budget` in total.  Visit k < n_own is Kw[i - 1 - k], visit k >= n_own is Kp[pe - 1 - (k - n_own)].
+struct CandRange { uint32_t n_own, n_tot, pe; const Entry* Kw; const Entry* Kp; };
+CandRange cand_range(const std::vector<Entry>& K, const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
+                     uint32_t s, uint32_t i, uint32_t h, uint32_t pl, uint32_t budget) {
+    CandRange c;
+    c.Kw = &K[(size_t)s * kWindow];
+    c.Kp = nullptr;
+    const uint16_t* ow = &off[(size_t)s * kWindow];
+    uint32_t s0 = ow[h];
+    c.n_own = std::min(budget, i - s0);
+    c.n_tot = c.n_own;
+    c.pe = 0;
+    if (s > 0 && c.n_own < budget) {
+        c.Kp = &K[(size_t)(s - 1) * kWindow];
+        const uint16_t* op = &off[(size_t)(s - 1) * kWindow];
+        uint32_t ps = op[h];
+        c.pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
+        uint32_t rem = budget - c.n_own;
+        uint32_t lo = (c.pe - ps > rem) ? c.pe - rem : ps;
+        while (lo < c.pe && entry_pos(c.Kp[lo].hi) < pl) lo++;
+        c.n_tot = c.n_own + (c.pe - lo);
     }
-};
+    return c;
+}
 
-// ---- stage 2: candidate walk per sorted entry (kernel k_match)
+// ---- stage 2: entry walk per sorted entry (kernel k_match): final records below 8 bytes, "long" records otherwise
 void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<Entry>& K,
                const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
                std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
     Mf.assign(n, 0);
     if (prm.need_quarter) Mq.assign(n, 0);
     uint32_t nseg = (uint32_t)cnt.size();
-    HostBytes data{d};
     for (uint32_t s = 0; s < nseg; s++) {
         const Entry* Kw = &K[(size_t)s * kWindow];
-        const uint16_t* ow = &off[(size_t)s * kWindow];
         for (uint32_t i = 0; i < cnt[s]; i++) {
             Entry me = Kw[i];
             uint32_t pl = entry_pos(me.hi);
             uint32_t p = s * kWindow + pl;
             uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
             uint32_t maxl = std::min(kMaxMatch, n - p);
-            uint32_t budget = prm.checks;
-            // own window, most recent first; then the previous window's bucket, positions at
-            // distance <= 32768 only (matching.rs:102-106,127)
-            uint32_t s0 = ow[h];
-            uint32_t n_own = std::min(budget, i - s0), n_tot = n_own, pe = 0;
-            const Entry* Kp = nullptr;
-            if (s > 0 && n_own < budget) {
-                Kp = &K[(size_t)(s - 1) * kWindow];
-                const uint16_t* op = &off[(size_t)(s - 1) * kWindow];
-                uint32_t ps = op[h];
-                pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
-                uint32_t rem = budget - n_own;
-                uint32_t lo = (pe - ps > rem) ? pe - rem : ps;
-                while (lo < pe && entry_pos(Kp[lo].hi) < pl) lo++;
-                n_tot = n_own + (pe - lo);
+            CandRange c = cand_range(K, off, cnt, s, i, h, pl, prm.checks);
+            EntryWalk st = ewalk_init(), sq = st;
+            uint32_t dist = 0, qdist = 0;
+            for (uint32_t k = 0; k < c.n_tot; k++) {
+                if (prm.need_quarter && k == prm.checks_quarter) { sq = st; qdist = dist; }
+                Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+                uint32_t before = st.best_len;
+                ewalk_visit(st, me, ce, k, maxl);
+                if (st.best_len != before) dist = (k < c.n_own ? pl : pl + kWindow) - entry_pos(ce.hi);
             }
-            WalkState st = walk_init();
-            uint32_t q_len = 1, q_dist = 0;
-            for (uint32_t k = 0; k < n_tot; k++) {
-                Entry ce = k < n_own ? Kw[i - 1 - k] : Kp[pe - 1 - (k - n_own)];
-                if (walk_passes(st, me, ce)) {
-                    uint32_t q = (k < n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
-                    walk_consider(st, data, p, q, me, ce, maxl);
-                    if (st.done) n_tot = k + 1;
-                }
-                if (prm.need_quarter && k + 1 == prm.checks_quarter) { q_len = st.best_len; q_dist = st.best_dist; }
-            }
-            if (prm.need_quarter && n_tot < prm.checks_quarter) { q_len = st.best_len; q_dist = st.best_dist; }
-            Mf[p] = finalize_match(st.best_len, st.best_dist);
-            if (prm.need_quarter) Mq[p] = finalize_match(q_len, q_dist);
+            if (prm.need_quarter && c.n_tot <= prm.checks_quarter) { sq = st; qdist = dist; }
+            Mf[p] = ewalk_record(st, i, dist, maxl);
+            if (prm.need_quarter) Mq[p] = ewalk_record(sq, i, qdist, maxl);
         }
     }
 }
 
-// ---- stage 1b/2b: the span path (kernels k_window_sort<items>, k_span_scatter, k_match_chains)
-// Sorted positions per window -> per-span merged entry lists -> multi-level chains walked per target.
-uint64_t g_chain_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // targets, level queries, chain steps, deep compares
-
-void window_sort_items(const uint8_t* d, uint32_t n, std::vector<uint32_t>& items, std::vector<uint16_t>& off,
-                       std::vector<uint32_t>& cnt) {
-    uint32_t nwin = (n + kWindow - 1) / kWindow;
-    items.assign((size_t)nwin * kWindow, 0);
-    off.assign((size_t)nwin * kWindow, 0);
-    cnt.assign(nwin, 0);
-    uint32_t hashable = n >= 2 ? n - 2 : 0;
-    for (uint32_t v = 0; v < nwin; v++) {
-        uint32_t base = v * kWindow;
-        uint32_t c = hashable > base ? std::min(kWindow, hashable - base) : 0;
-        cnt[v] = c;
-        std::vector<uint32_t> hist(kWindow + 1, 0);
-        for (uint32_t i = 0; i < c; i++) hist[hash3(d[base + i], d[base + i + 1], d[base + i + 2]) + 1]++;
-        for (uint32_t h = 0; h < kWindow; h++) hist[h + 1] += hist[h];
-        for (uint32_t h = 0; h < kWindow; h++) off[(size_t)v * kWindow + h] = (uint16_t)hist[h];
-        std::vector<uint32_t> cur(hist.begin(), hist.end() - 1);
-        for (uint32_t i = 0; i < c; i++) {
-            uint32_t h = hash3(d[base + i], d[base + i + 1], d[base + i + 2]);
-            items[(size_t)v * kWindow + cur[h]++] = (h << 15) | i;
-        }
+// ---- stage 3a: resolution of a long record at a position the parser searches (warp-cooperative in k_parse*)
+// Every candidate from visit k8 on that shares the target's 8 entry bytes is compared on the data; the first
+// strictly longer one wins (matching.rs:148-157), starting from max(floor, 7): the caller only uses a result
+// longer than `floor` (= prev_length, matching.rs:161-165) and the record proves a length of at least 8.
+uint64_t g_resolve_stats[4] = {0, 0, 0, 0};   // resolutions, candidates compared, bytes compared, visits scanned
+uint32_t resolve_long(const uint8_t* d, uint32_t n, const std::vector<Entry>& K, const std::vector<uint16_t>& off,
+                      const std::vector<uint32_t>& cnt, uint32_t p, uint32_t rec, uint32_t floor, uint32_t budget,
+                      uint32_t full_budget) {
+    const uint32_t s = p / kWindow, pl = p % kWindow, i = rec_rank(rec);
+    const Entry me = K[(size_t)s * kWindow + i];
+    const uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
+    const uint32_t maxl = std::min(kMaxMatch, n - p);
+    CandRange c = cand_range(K, off, cnt, s, i, h, pl, full_budget);
+    const uint32_t n_vis = std::min(c.n_tot, budget);
+    uint32_t best = std::max(floor, kEntryBytes - 1u), best_q = 0;
+    g_resolve_stats[0]++;
+    for (uint32_t k = rec_k8(rec); k < n_vis; k++) {
+        g_resolve_stats[3]++;
+        Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+        if (ce.lo != me.lo || ((ce.hi ^ me.hi) & kEntryKeyHi) != 0u) continue;
+        uint32_t q = (k < c.n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
+        g_resolve_stats[1]++;
+        if (best < maxl && d[q + best] != d[p + best]) continue;   // cannot be longer than the running best
+        uint32_t l = kEntryBytes;
+        while (l < maxl && d[p + l] == d[q + l]) l++;
+        g_resolve_stats[2] += l - kEntryBytes;
+        if (l > best) { best = l; best_q = q; if (l == maxl) break; }
     }
+    return best > std::max(floor, kEntryBytes - 1u) ? finalize_match(best, p - best_q) : 0u;
 }
 
-void span_scatter(const uint8_t* d, uint32_t n, const std::vector<uint32_t>& items, const std::vector<uint16_t>& off,
-                  const std::vector<uint32_t>& cnt, std::vector<Entry>& M, std::vector<uint32_t>& span_cnt) {
-    uint32_t nwin = (uint32_t)cnt.size();
-    uint32_t nspan = (nwin + kSpanWin - 1) / kSpanWin;
-    M.assign((size_t)nspan * kSpanSlots, Entry{0, 0});
-    span_cnt.assign(nspan, 0);
-    auto offx = [&](uint32_t u, uint32_t h) { return h < kWindow ? (uint32_t)off[(size_t)u * kWindow + h] : cnt[u]; };
-    for (uint32_t s = 0; s < nspan; s++) {
-        uint32_t w_lo = s * kSpanWin > 0 ? s * kSpanWin - 1 : 0, w_hi = std::min(nwin, s * kSpanWin + kSpanWin);
-        for (uint32_t v = w_lo; v < w_hi; v++) {
-            span_cnt[s] += cnt[v];
-            for (uint32_t r = 0; r < cnt[v]; r++) {
-                uint32_t it = items[(size_t)v * kWindow + r];
-                uint32_t h = it >> 15, pl = it & kWindowMask, p = v * kWindow + pl;
-                uint32_t idx = r;
-                bool first = (r == offx(v, h));
-                for (uint32_t u = w_lo; u < w_hi; u++) {
-                    if (u < v) { idx += offx(u, h + 1); if (offx(u, h + 1) != offx(u, h)) first = false; }
-                    else if (u > v) idx += offx(u, h);
-                }
-                uint8_t b[7];
-                for (uint32_t k = 0; k < 7; k++) b[k] = p + k < n ? d[p + k] : 0;
-                uint32_t pos_in_span = p - s * kSpanWin * kWindow + kWindow;
-                M[(size_t)s * kSpanSlots + idx] = make_span_entry(pos_in_span, b, first);
-            }
-        }
-    }
-}
-
-constexpr uint32_t kModelChainChunk = 2048;   // entries per warp chunk
-constexpr uint32_t kModelChainCtx = 128;      // entries re-inserted in front of a chunk
-
-void match_all_chains(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<Entry>& M,
-                      const std::vector<uint32_t>& span_cnt, std::vector<uint32_t>& Mf) {
-    Mf.assign(n, 0);
-    HostBytes data{d};
-    const uint32_t c = prm.checks;
-    for (uint32_t s = 0; s < span_cnt.size(); s++) {
-        const Entry* E = &M[(size_t)s * kSpanSlots];
-        const uint32_t ne = span_cnt[s];
-        const uint32_t span_base = s * kSpanWin * kWindow;
-        for (uint32_t a = 0; a < ne; a += kModelChainChunk) {
-            const uint32_t ctx = a >= kModelChainCtx ? a - kModelChainCtx : 0;
-            const uint32_t b = std::min(ne, a + kModelChainChunk);
-            uint16_t head[kChainLevels][128];
-            uint8_t prevd[kChainLevels][256];
-            Entry ring[256];
-            memset(head, 0, sizeof(head));
-            memset(prevd, 0, sizeof(prevd));
-            uint32_t bstart = 256;                       // local index of the current bucket's first entry
-            for (uint32_t m = ctx; m < b; m++) {
-                const uint32_t i = m - ctx + 256;       // local index: never 0, so a zero head means "none"
-                const Entry me = E[m];
-                ring[i & 255] = me;
-                if (me.hi & kSpanFirstBit) bstart = i;
-                for (uint32_t lv = 0; lv < kChainLevels; lv++) {
-                    uint32_t sg = span_sig(me.lo, me.hi, lv) >> 1;   // 7-bit slot, as in the kernel
-                    uint32_t dl = i - head[lv][sg];
-                    prevd[lv][i & 255] = (uint8_t)(dl < 256 ? dl : 0);
-                    head[lv][sg] = (uint16_t)i;
-                }
-                const uint32_t pos = span_entry_pos(me.hi);
-                if (m < a || pos < kWindow) continue;   // context or history entry: not a target here
-                const uint32_t p = span_base + pos - kWindow;
-                const uint32_t maxl = std::min(kMaxMatch, n - p);
-                const uint32_t lb = std::max(bstart, i > c ? i - c : 0u);
-                uint32_t best_len = 1, best_q = 0, level = 0;
-                bool deep = false, done = false;
-                g_chain_stats[0]++;
-                while (level < kChainLevels && !done && !deep) {
-                    g_chain_stats[1]++;
-                    uint32_t j = i;
-                    bool found = false;
-                    Entry ce{0, 0};
-                    for (;;) {
-                        uint32_t dl = prevd[level][j & 255];
-                        if (dl == 0) break;
-                        j -= dl;
-                        if (j < lb) break;
-                        g_chain_stats[2]++;
-                        ce = ring[j & 255];
-                        if (span_key_equal(me, ce, level)) { found = true; break; }
-                        g_chain_stats[4]++;
-                    }
-                    if (!found) break;
-                    if (pos - span_entry_pos(ce.hi) > kWindow) break;      // matching.rs:102-106: beyond the window
-                    uint32_t l = span_entry_lcp(ce.lo ^ me.lo);
-                    uint32_t q = span_base + span_entry_pos(ce.hi) - kWindow;
-                    if (l >= maxl) { best_len = maxl; best_q = q; done = true; break; }
-                    if (l == kSpanEntryBytes) { deep = true; break; }
-                    best_len = l; best_q = q; level = l - 2;
-                }
-                if (deep) {
-                    // every candidate sharing 7+ bytes, nearest first: the reference's quick reject on the byte
-                    // that would extend the best match (matching.rs:141-143), then the real length
-                    g_chain_stats[7]++;
-                    uint32_t j = i;
-                    const uint32_t lv = kChainLevels - 1;
-                    for (;;) {
-                        uint32_t dl = prevd[lv][j & 255];
-                        if (dl == 0) break;
-                        j -= dl;
-                        if (j < lb) break;
-                        g_chain_stats[5]++;
-                        Entry ce = ring[j & 255];
-                        if (!span_key_equal(me, ce, lv)) { g_chain_stats[6]++; continue; }
-                        if (pos - span_entry_pos(ce.hi) > kWindow) break;
-                        uint32_t q = span_base + span_entry_pos(ce.hi) - kWindow;
-                        if (best_len >= kSpanEntryBytes && d[q + best_len] != d[p + best_len]) continue;
-                        g_chain_stats[3]++;
-                        uint32_t l = data.common_prefix(p, q, kSpanEntryBytes, maxl);
-                        if (l > best_len) { best_len = l; best_q = q; if (l == maxl) break; }
-                    }
-                }
-                Mf[p] = finalize_match(best_len, p - best_q);
-            }
-        }
-    }
-}
-
-int g_match_impl = 1;   // 0 = candidate walk (k_match), 1 = span chains (k_match_chains) when the options allow it
-bool use_chains(const Params& prm) { return g_match_impl == 1 && prm.checks <= kChainMaxChecks && !prm.need_quarter; }
-
-void find_matches(const uint8_t* in, uint32_t n, const Params& prm, std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
-    std::vector<uint32_t> cnt;
-    std::vector<uint16_t> off;
-    if (use_chains(prm)) {
-        std::vector<uint32_t> items, span_cnt;
-        std::vector<Entry> M;
-        window_sort_items(in, n, items, off, cnt);
-        span_scatter(in, n, items, off, cnt, M, span_cnt);
-        match_all_chains(in, n, prm, M, span_cnt, Mf);
-    } else {
-        std::vector<Entry> S;
-        window_sort(in, n, S, off, cnt);
-        match_all(in, n, prm, S, off, cnt, Mf, Mq);
-    }
+void find_matches(const uint8_t* in, uint32_t n, const Params& prm, std::vector<Entry>& S, std::vector<uint16_t>& off,
+                  std::vector<uint32_t>& cnt, std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
+    window_sort(in, n, S, off, cnt);
+    match_all(in, n, prm, S, off, cnt, Mf, Mq);
 }
 
 // ---- stage 3: speculative segment parse + hand-off verification + repair (k_parse*, k_verify)
@@ -288,20 +157,39 @@ struct SegRec {
     std::vector<uint32_t> toks;
 };
 
-int step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const std::vector<uint32_t>& Mf,
-         const std::vector<uint32_t>& Mq, uint32_t out[2]) {
+// What the match stage leaves for the parser: the records and the sorted lists they refer to.
+struct MatchData {
+    std::vector<Entry> K;
+    std::vector<uint16_t> off;
+    std::vector<uint32_t> cnt, Mf, Mq;
+};
+
+int step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const MatchData& md, uint32_t out[2]) {
     uint32_t p = st.pos;
-    uint32_t mf = (prm.mode != kRle && p + 2 < n && !Mf.empty()) ? Mf[p] : 0;
+    const bool has_m = prm.mode != kRle && p + 2 < n && !md.Mf.empty();
     if (prm.mode == kLazy) {
-        uint32_t mq = (prm.need_quarter && p + 2 < n) ? Mq[p] : 0;
-        return lazy_step(st, n, d, mf, mq, prm.lazy, out);
+        uint32_t m = 0;
+        if (has_m && !st.ign) {                       // the only case in which the reference searches (lz77.rs:347)
+            const bool quarter = st.prev_len >= 32u;  // lz77.rs:351-355
+            if (!quarter || prm.need_quarter) {
+                m = quarter ? md.Mq[p] : md.Mf[p];
+                if (rec_is_long(m))
+                    m = resolve_long(d, n, md.K, md.off, md.cnt, p, m, st.prev_len, quarter ? prm.checks_quarter : prm.checks,
+                                     prm.checks);
+            }
+        }
+        return lazy_step(st, n, d, m, m, prm.lazy, out);
     }
-    if (prm.mode == kGreedy) return greedy_step(st, n, d, mf, out);
+    if (prm.mode == kGreedy) {
+        uint32_t m = has_m ? md.Mf[p] : 0;
+        if (rec_is_long(m)) m = resolve_long(d, n, md.K, md.off, md.cnt, p, m, 0, prm.checks, prm.checks);
+        return greedy_step(st, n, d, m, out);
+    }
     return rle_step(st, n, d, out);
 }
 
-void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const std::vector<uint32_t>& Mf,
-                   const std::vector<uint32_t>& Mq, ParseState st, uint32_t a, uint32_t b, SegRec& r) {
+void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const MatchData& md, ParseState st, uint32_t a,
+                   uint32_t b, SegRec& r) {
     // runs from `st` until the first iteration position >= b (or the end of data)
     r.toks.clear();
     bool have_e = false;
@@ -309,7 +197,7 @@ void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const std::v
     while (st.pos < n) {
         if (!have_e && st.pos >= a) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); have_e = true; }
         if (st.pos >= b) break;
-        int ne = step(prm, st, n, d, Mf, Mq, out);
+        int ne = step(prm, st, n, d, md, out);
         for (int i = 0; i < ne; i++) r.toks.push_back(out[i]);
     }
     if (!have_e) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); }
@@ -323,8 +211,8 @@ ParseState state_from(uint32_t pos, uint32_t key) {
 
 uint32_t g_last_repairs = 0, g_last_seq_repairs = 0;
 
-void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, const std::vector<uint32_t>& Mf,
-               const std::vector<uint32_t>& Mq, std::vector<uint32_t>& tokens, uint32_t begin = 0) {
+void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, const MatchData& md,
+               std::vector<uint32_t>& tokens, uint32_t begin = 0) {
     tokens.clear();
     g_last_repairs = g_last_seq_repairs = 0;
     if (n <= begin) return;
@@ -333,7 +221,7 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
     for (uint32_t s = 0; s < nseg; s++) {
         uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
         uint32_t start = a - begin > cfg.warm ? a - cfg.warm : begin;
-        parse_segment(prm, d, n, Mf, Mq, parse_state_init(start), a, b, seg[s]);
+        parse_segment(prm, d, n, md, parse_state_init(start), a, b, seg[s]);
     }
     auto bad = [&](uint32_t s) {
         return s > 0 && (seg[s - 1].x_pos != seg[s].e_pos || seg[s - 1].x_key != seg[s].e_key);
@@ -347,7 +235,7 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
         for (size_t i = 0; i < list.size(); i++) {
             uint32_t s = list[i];
             uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
-            parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, fixed[i]);
+            parse_segment(prm, d, n, md, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, fixed[i]);
         }
         for (size_t i = 0; i < list.size(); i++) { seg[list[i]] = fixed[i]; g_last_repairs++; }
     }
@@ -355,7 +243,7 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
         if (bad(s)) {
             uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
             SegRec r;
-            parse_segment(prm, d, n, Mf, Mq, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, r);
+            parse_segment(prm, d, n, md, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, r);
             seg[s] = r; g_last_seq_repairs++;
         }
     }
@@ -474,9 +362,10 @@ int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy,
                   uint32_t warm, uint32_t rounds, uint8_t** out, size_t* out_len, uint32_t* stats /*[4]*/) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<uint32_t> Mf, Mq, tokens;
-    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
-    parse_all(prm, cfg, in, n, Mf, Mq, tokens);
+    std::vector<uint32_t> tokens;
+    MatchData md;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
+    parse_all(prm, cfg, in, n, md, tokens);
     std::vector<uint8_t> o;
     emit_blocks(in, n, tokens, o, 1);
     *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
@@ -491,9 +380,10 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
                 uint32_t warm, uint32_t rounds, uint32_t** toks, size_t* ntoks) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{pseg, warm, rounds};
-    std::vector<uint32_t> Mf, Mq, tokens;
-    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
-    parse_all(prm, cfg, in, n, Mf, Mq, tokens);
+    std::vector<uint32_t> tokens;
+    MatchData md;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
+    parse_all(prm, cfg, in, n, md, tokens);
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
     *ntoks = tokens.size();
@@ -505,9 +395,10 @@ int dflm_tokens_from(const uint8_t* in, uint32_t n, uint32_t begin, uint16_t che
                      uint32_t** toks, size_t* ntoks) {
     Params prm = make_params(checks, lazy, mtype);
     Cfg cfg{8192, 1024, 3};
-    std::vector<uint32_t> Mf, Mq, tokens;
-    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, Mf, Mq);
-    parse_all(prm, cfg, in, n, Mf, Mq, tokens, begin);
+    std::vector<uint32_t> tokens;
+    MatchData md;
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
+    parse_all(prm, cfg, in, n, md, tokens, begin);
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
     *ntoks = tokens.size();
@@ -522,8 +413,8 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 void dflm_free(void* p) { free(p); }
 uint32_t dflm_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return crc32_combine(c1, c2, len2); }
 uint32_t dflm_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
-void dflm_set_match_impl(int impl) { g_match_impl = impl; }
-void dflm_chain_stats(uint64_t* o /*[8]*/, int reset) {
-    for (int i = 0; i < 8; i++) { o[i] = g_chain_stats[i]; if (reset) g_chain_stats[i] = 0; }
+void dflm_resolve_stats(uint64_t* o /*[4]*/, int reset) {
+    for (int i = 0; i < 4; i++) { o[i] = g_resolve_stats[i]; if (reset) g_resolve_stats[i] = 0; }
 }
+
 }

@@ -29,27 +29,16 @@ def lib():
         L.dflm_crc32_combine.restype = ctypes.c_uint32
         L.dflm_adler32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
         L.dflm_adler32_combine.restype = ctypes.c_uint32
-        L.dflm_set_match_impl.argtypes = [ctypes.c_int]
-        L.dflm_chain_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
+        L.dflm_resolve_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
         _lib = L
     return _lib
 
 
-WALK, CHAINS = 0, 1
-
-
-def set_match_impl(impl):
-    """WALK: candidate walk (kernel k_match) for every option set.  CHAINS: span entries + multi-level
-    chains (k_span_scatter + k_match_chains) wherever the library would use them (checks <= 128, no
-    quarter-budget searches), the walk otherwise -- the library's own dispatch."""
-    lib().dflm_set_match_impl(impl)
-
-
-def chain_stats(reset=True):
-    st = (ctypes.c_uint64 * 8)()
-    lib().dflm_chain_stats(st, 1 if reset else 0)
-    return {"targets": st[0], "level_queries": st[1], "level_steps": st[2], "deep_compares": st[3],
-            "level_collisions": st[4], "deep_steps": st[5], "deep_collisions": st[6], "deep_targets": st[7]}
+def resolve_stats(reset=True):
+    """Counters of the long-match resolutions the parser asked for since the last reset."""
+    st = (ctypes.c_uint64 * 4)()
+    lib().dflm_resolve_stats(st, 1 if reset else 0)
+    return {"resolutions": st[0], "candidates": st[1], "bytes": st[2], "visits": st[3]}
 
 
 def compress(data, opts, pseg=8192, warm=1024, rounds=4):

@@ -309,17 +309,10 @@ def test_gz_encoder_writer(dfl, pg11):
     assert zlib.decompress(bytes(second), 31) == pg11[5000:12000] and b"two\0" in bytes(second[:20])
 
 
-# ---------------------------------------------------------------- the two match paths
-@pytest.fixture(params=["walk", "chains"])
-def match_path(request, dfl):
-    old = dfl.set_match_path(request.param)
-    yield request.param
-    dfl._native.lib().dfl_set_match_path(old)
-
-
-def test_both_match_paths_bit_exact(dfl, pg11, match_path):
-    """k_match (candidate walk) and k_span_scatter + k_match_chains (multi-level chains) are two
-    implementations of matching.rs:87-166 over the same sorted windows; both must equal the oracle."""
+# ---------------------------------------------------------------- match stage on every kind of input
+def test_match_stage_bit_exact_on_all_kinds(dfl, pg11):
+    """k_match (entry walk) + the parse stage's warp-cooperative resolution of long records implement
+    matching.rs:87-166 over the sorted windows; the result must equal the oracle on every kind of input."""
     import datagen
     inputs = _inputs(pg11)
     inputs["mix2m"] = datagen.silesia_mix(2 << 20)
@@ -332,15 +325,15 @@ def test_both_match_paths_bit_exact(dfl, pg11, match_path):
         opts = o.PRESETS[preset]()
         for name, data in inputs.items():
             got = dfl.deflate_bytes_conf(data, _copts(dfl, opts))
-            assert got == o.compress(data, opts, o.RAW), (match_path, name, preset)
+            assert got == o.compress(data, opts, o.RAW), (name, preset)
     for checks, lazy, mt in ((4, 8, 1), (16, 258, 1), (64, 4, 1), (7, 0, 0), (128, 33, 1), (129, 32, 1), (100, 20, 0)):
         opts = o.Options(checks, lazy, mt, 0)
         data = inputs["mix2m"][:600000]
-        assert dfl.deflate_bytes_conf(data, _copts(dfl, opts)) == o.compress(data, opts, o.RAW), (match_path, checks, lazy, mt)
+        assert dfl.deflate_bytes_conf(data, _copts(dfl, opts)) == o.compress(data, opts, o.RAW), (checks, lazy, mt)
 
 
-def test_both_match_paths_streaming_dictionary(dfl, pg11, match_path):
-    """Pieces encoded with the previous 32 KiB as dictionary (begin > 0) through either path."""
+def test_streaming_dictionary(dfl, pg11):
+    """Pieces encoded with the previous 32 KiB as dictionary (begin > 0)."""
     s = o.Stream(o.opts_default(), o.ZLIB)
     sink = bytearray()
     enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Default)
@@ -352,7 +345,7 @@ def test_both_match_paths_streaming_dictionary(dfl, pg11, match_path):
 
 
 # ---------------------------------------------------------------- pieces of one stream
-def test_pieces_concatenate_to_the_flushed_reference_stream(dfl, pg11, match_path):
+def test_pieces_concatenate_to_the_flushed_reference_stream(dfl, pg11):
     """dfl_compress_device_piece: pieces encoded independently (as the ranks of a multi-GPU job do),
     each with the 32 KiB in front of it as dictionary, concatenate into the stream the reference's
     writer produces with flush() at the piece boundaries."""
@@ -488,14 +481,6 @@ def test_full_size_default_raw_roundtrip(dfl):
     # 2 MiB prefix (minus its final block) is a prefix of the 1 GiB stream up to the last complete block
     ref = o.compress(data[:2 << 20], o.opts_default(), o.RAW)
     assert comp[:len(ref) * 9 // 10] == ref[:len(ref) * 9 // 10]
-    old = dfl.set_match_path("chains")
-    try:
-        out2, n2 = dfl.compress_device(src[:256 << 20], dfl.Compression.Default, dfl.RAW)
-        dfl.set_match_path("walk")
-        out3, n3 = dfl.compress_device(src[:256 << 20], dfl.Compression.Default, dfl.RAW)
-        assert n2 == n3 and torch.equal(out2[:n2], out3[:n3])
-    finally:
-        dfl._native.lib().dfl_set_match_path(old)
 
 
 def test_full_size_fast_zlib_roundtrip(dfl):

@@ -46,15 +46,8 @@ def _inputs(pg11):
     return d
 
 
-@pytest.fixture(params=[m.WALK, m.CHAINS], ids=["walk", "chains"])
-def match_impl(request):
-    m.set_match_impl(request.param)
-    yield request.param
-    m.set_match_impl(m.CHAINS)
-
-
 @pytest.mark.parametrize("preset", list(o.PRESETS))
-def test_model_is_bit_exact_with_oracle(preset, pg11, match_impl):
+def test_model_is_bit_exact_with_oracle(preset, pg11):
     opts = o.PRESETS[preset]()
     for name, data in _inputs(pg11).items():
         want = o.compress(data, opts, o.RAW)
@@ -72,7 +65,7 @@ def test_model_repairs_unsynchronised_segments():
     assert got == want and st["repairs"] + st["seq_repairs"] > 0
 
 
-def test_model_custom_options(pg11, match_impl):
+def test_model_custom_options(pg11):
     data = pg11[:120000]
     for checks, lazy, mt in ((4, 8, 1), (16, 258, 1), (3, 40, 1), (64, 4, 1), (7, 0, 0), (300, 64, 1), (1, 3, 1),
                              (128, 32, 1), (128, 33, 1), (129, 32, 1), (100, 20, 0)):

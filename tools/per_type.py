@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Diagnostic (GPU box): match-stage time per kind of synthetic data (64 MiB of each), both match paths."""
+"""Diagnostic (GPU box): stage times per kind of synthetic data (64 MiB of each)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,14 +21,12 @@ for kind, gen in kinds.items():
     data = gen()
     src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
     row = [kind]
-    for path in ("walk", "chains"):
-        dfl.set_match_path(path)
-        for _ in range(2):
-            dfl.compress_device(src, dfl.Compression.Default, dfl.RAW)
-        L.dfl_set_profiling(1)
-        out, n = dfl.compress_device(src, dfl.Compression.Default, dfl.RAW)
-        k = L.dfl_last_stage_times(names, ms, 32)
-        L.dfl_set_profiling(0)
-        st = {names[i].decode(): ms[i] for i in range(k)}
-        row.append(f"{path}: match {st['match']:.2f} ms sort {st['window_sort']:.2f} total {sum(st.values()):.2f} ratio {n/len(data):.3f}")
+    for _ in range(2):
+        dfl.compress_device(src, dfl.Compression.Default, dfl.RAW)
+    L.dfl_set_profiling(1)
+    out, n = dfl.compress_device(src, dfl.Compression.Default, dfl.RAW)
+    k = L.dfl_last_stage_times(names, ms, 32)
+    L.dfl_set_profiling(0)
+    st = {names[i].decode(): ms[i] for i in range(k)}
+    row.append(" ".join(f"{a} {b:.2f}" for a, b in st.items()) + f" | total {sum(st.values()):.2f} ms ratio {n/len(data):.3f}")
     print(" | ".join(row))
