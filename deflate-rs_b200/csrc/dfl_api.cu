@@ -546,11 +546,11 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
         CK(launch_crc32(d_in + begin, n - begin, b, st));
         tm.mark("crc32");
     }
-    if (need_lz && j.n_carry_tok)   // the lists the token array shares its memory with are dead by now
-        CK(cudaMemcpyAsync(b.tok, pin.h_carry_tok, (size_t)j.n_carry_tok * 4, cudaMemcpyHostToDevice, st));
     if (need_lz) {
         CK(launch_parse(j, b, st));
         tm.mark("parse");
+        if (j.n_carry_tok)   // the sorted lists the token array shares its memory with are dead only now (the parser resolves long matches on them)
+            CK(cudaMemcpyAsync(b.tok, pin.h_carry_tok, (size_t)j.n_carry_tok * 4, cudaMemcpyHostToDevice, st));
         CK(launch_token_layout(j, b, st));
         tm.mark("token_layout");
     }

@@ -351,6 +351,15 @@ __device__ __forceinline__ void walk_masks(uint32_t best_len, uint32_t& mlo, uin
     mhi = kEntryTagHi | (uint32_t)(m >> 32);
 }
 
+// The visit itself: ((v ^ me) & mask) == 0 over both words, one LOP3 per word (written as PTX so that the
+// compiler does not split the xor off for the rare path below and pay for it on every visit).
+__device__ __forceinline__ bool walk_test(const Walk& wk, uint2 v) {
+    uint32_t t1, t2;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t1) : "r"(v.x), "r"(wk.me_lo), "r"(wk.mlo));
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t2) : "r"(v.y), "r"(wk.me_hi), "r"(wk.mhi));
+    return (t1 | t2) == 0u;
+}
+
 // A candidate passed the masks: it shares more bytes with the target than the running best (unless the end
 // of the input clamps it).  kg = visit index, dist_base - position = distance.
 template <bool NEEDQ>
@@ -388,14 +397,12 @@ __device__ __forceinline__ void walk_segment(Walk& wk, const uint2* __restrict__
 DFL_PRAGMA(unroll DFL_WALK_UNROLL)
     for (; k < tmin; k++, ptr--) {
         const uint2 v = __ldg(ptr);
-        if ((((v.x ^ wk.me_lo) & wk.mlo) | ((v.y ^ wk.me_hi) & wk.mhi)) == 0u)
-            walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
+        if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
     }
     for (; k < tmax; k++, ptr--) {
         if (k < n_seg) {
             const uint2 v = __ldg(ptr);
-            if ((((v.x ^ wk.me_lo) & wk.mlo) | ((v.y ^ wk.me_hi) & wk.mhi)) == 0u)
-                walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
+            if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
         }
     }
 }
