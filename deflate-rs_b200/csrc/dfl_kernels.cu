@@ -338,18 +338,16 @@ struct Walk {
     uint32_t me_lo, me_hi;   // the target's entry; me_hi is poisoned once the walk has stopped so that nothing passes
     uint32_t mlo, mhi;       // entry_mask(best_len)
     uint32_t best_len;       // 1 = nothing yet
-    uint32_t best_dist, best_k;
+    uint32_t best_pos, best_k;
     uint32_t stop;
-    uint32_t q_len, q_dist, q_k, q_stop;   // state after checks_quarter visits (NEEDQ)
+    uint32_t q_len, q_pos, q_k;   // state after checks_quarter visits (NEEDQ)
 };
 
-__device__ __forceinline__ void walk_masks(uint32_t best_len, uint32_t& mlo, uint32_t& mhi) {
-    // bytes 3 .. best_len must agree: best_len - 2 of the five entry bytes (all five from best_len 7 on)
-    uint32_t nb = (best_len < 7u ? best_len : 7u) - 2u;
-    unsigned long long m = (1ull << (8u * nb)) - 1ull;
-    mlo = (uint32_t)m;
-    mhi = kEntryTagHi | (uint32_t)(m >> 32);
-}
+// entry_mask() by best length 3..8 (index 0..2 unused): what a candidate must share to be longer
+__constant__ uint2 c_walk_masks[9] = {
+    {0u, 0u}, {0u, 0u}, {0u, 0u},
+    {0x000000ffu, kEntryTagHi}, {0x0000ffffu, kEntryTagHi}, {0x00ffffffu, kEntryTagHi}, {0xffffffffu, kEntryTagHi},
+    {0xffffffffu, kEntryKeyHi}, {0xffffffffu, kEntryKeyHi}};
 
 // The visit itself: ((v ^ me) & mask) == 0 over both words, one LOP3 per word (written as PTX so that the
 // compiler does not split the xor off for the rare path below and pay for it on every visit).
@@ -361,48 +359,25 @@ __device__ __forceinline__ bool walk_test(const Walk& wk, uint2 v) {
 }
 
 // A candidate passed the masks: it shares more bytes with the target than the running best (unless the end
-// of the input clamps it).  kg = visit index, dist_base - position = distance.
+// of the input clamps it).  kg = visit index.
 template <bool NEEDQ>
-__device__ __forceinline__ void walk_improve(Walk& wk, uint2 v, uint32_t kg, uint32_t dist_base, uint32_t maxl, uint32_t qbudget) {
+__device__ __forceinline__ void walk_improve(Walk& wk, uint2 v, uint32_t kg, uint32_t maxl, uint32_t qbudget) {
     if (wk.stop) return;
     uint32_t l = entry_lcp(v.x ^ wk.me_lo, v.y ^ wk.me_hi);
     l = l < maxl ? l : maxl;
     if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
         wk.best_len = l;
-        wk.best_dist = dist_base - (v.y >> 17);
+        wk.best_pos = v.y >> 17;
         wk.best_k = kg;
-        const bool stop = (l >= kEntryBytes) || (l == maxl);
         if (NEEDQ) {
-            if (kg < qbudget) { wk.q_len = l; wk.q_dist = wk.best_dist; wk.q_k = kg; wk.q_stop = stop; }
+            if (kg < qbudget) { wk.q_len = l; wk.q_pos = wk.best_pos; wk.q_k = kg; }
         }
-        if (stop) {                             // matching.rs:152-156, or nothing longer can be proven from entries
+        const uint2 m = c_walk_masks[l];
+        wk.mlo = m.x; wk.mhi = m.y;
+        if (l >= kEntryBytes || l == maxl) {    // matching.rs:152-156, or nothing longer can be proven from entries
             wk.stop = 1;
             wk.mlo = 0xffffffffu; wk.mhi = kEntryKeyHi;
             wk.me_hi ^= 0x100u;                 // a flipped tag bit: (almost) nothing passes any more; the guard above catches the rest
-        } else {
-            walk_masks(l, wk.mlo, wk.mhi);
-        }
-    }
-}
-
-// One pass over the candidates Kseg[idx], Kseg[idx - 1], ... : lane-private count n_seg, of which the
-// first `tmin` visits are valid in every lane of the warp (no per-visit bounds test) and the rest up
-// to `tmax` are ragged.
-template <bool NEEDQ>
-__device__ __forceinline__ void walk_segment(Walk& wk, const uint2* __restrict__ Kseg, int idx, uint32_t n_seg, uint32_t tmin,
-                                             uint32_t tmax, uint32_t kbase, uint32_t dist_base, uint32_t maxl,
-                                             uint32_t qbudget) {
-    const uint2* ptr = Kseg + idx;
-    uint32_t k = 0;
-DFL_PRAGMA(unroll DFL_WALK_UNROLL)
-    for (; k < tmin; k++, ptr--) {
-        const uint2 v = __ldg(ptr);
-        if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
-    }
-    for (; k < tmax; k++, ptr--) {
-        if (k < n_seg) {
-            const uint2 v = __ldg(ptr);
-            if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, kbase + k, dist_base, maxl, qbudget);
         }
     }
 }
@@ -447,7 +422,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
         const uint32_t pl = entry_pos(wk.me_hi);
         const uint32_t p = base + pl;
         if (p < begin) act = false;
-        uint32_t n_own = 0, n_prev = 0, pe = 0;
+        uint32_t n_own = 0, n_tot = 0, pe = 0;
         uint32_t maxl = 0;
         if (act) {
             const uint32_t w0 = lds32(sw, pl);
@@ -455,6 +430,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
             maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
             const uint32_t s0 = ow[h];
             n_own = i - s0 < budget ? i - s0 : budget;
+            n_tot = n_own;
             if (w > 0 && n_own < budget) {
                 // previous window: entries [ps, pe) of the same bucket whose position is >= pl
                 // (distance <= 32768, matching.rs:102-106,127); they are position sorted.
@@ -469,17 +445,56 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                     uint32_t mid = (lo + hi) >> 1;
                     if (entry_pos(__ldg(&Kp[mid].y)) >= pl) hi = mid; else lo = mid + 1;
                 }
-                n_prev = pe - lo;
+                n_tot += pe - lo;
             }
         }
-        wk.best_len = 1; wk.best_dist = 0; wk.best_k = 0; wk.stop = 0; wk.mlo = 0; wk.mhi = kEntryTagHi;
-        wk.q_len = 1; wk.q_dist = 0; wk.q_k = 0; wk.q_stop = 0;
-        walk_segment<NEEDQ>(wk, Kw, (int)i - 1, n_own, warp_min(n_own), warp_max(n_own), 0u, pl, maxl, qbudget);
-        if (wk.stop) n_prev = 0;
-        walk_segment<NEEDQ>(wk, Kp, (int)pe - 1, n_prev, warp_min(n_prev), warp_max(n_prev), n_own, pl + kWindow, maxl, qbudget);
+        wk.best_len = 1; wk.best_pos = 0; wk.best_k = 0; wk.stop = 0; wk.mlo = 0; wk.mhi = kEntryTagHi;
+        wk.q_len = 1; wk.q_pos = 0; wk.q_k = 0;
+        // Visit k is Kw[i - 1 - k] while k < n_own and Kp[pe - 1 - (k - n_own)] after that: one index space, so
+        // that a warp whose lanes sit on both sides of a bucket boundary runs max(n_tot) steps, not the sum of
+        // the two maxima.  Steps below the warp minimum of n_own need no per-lane case distinction.
+        const uint32_t tA = warp_min(n_own), tB = warp_max(n_own), tmax = warp_max(n_tot);
+        uint32_t k = 0;
+        {   // every lane is inside its own window's list
+            const uint2* ptr = Kw + i - 1;
+            for (; k + 8u <= tA; k += 8u, ptr -= 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint2 v = __ldg(ptr - u);
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k + u, maxl, qbudget);
+                }
+                if (__all_sync(0xffffffffu, wk.stop != 0u)) { k = tmax; break; }
+            }
+        }
+        if (k < tB) {   // some lanes have crossed into the previous window's list, some have not
+            const uint32_t oa = i - 1u + kWindow, ob = pe - 1u + n_own;    // entry index relative to Kw - kWindow, minus k
+            const uint2* Kb = Kw - kWindow;
+#pragma unroll 2
+            for (; k < tB; k++) {
+                if (k < n_tot) {
+                    const uint2 v = __ldg(Kb + ((k < n_own ? oa : ob) - k));
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
+                }
+            }
+        }
+        if (k < tmax && !__all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) {   // only the previous window's list is left
+            const uint2* ptr = Kp + pe - 1 + n_own - k;
+#pragma unroll 2
+            for (; k < tmax; k++, ptr--) {
+                if (k < n_tot) {
+                    const uint2 v = __ldg(ptr);
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
+                }
+            }
+        }
         if (act) {
-            Mf[p] = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, wk.best_dist);
-            if (NEEDQ) Mq[p] = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, wk.q_dist);
+            // distance of visit k: own window pl - pos, previous window pl + 32768 - pos
+            const uint32_t d = (wk.best_k < n_own ? pl : pl + kWindow) - wk.best_pos;
+            Mf[p] = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            if (NEEDQ) {
+                const uint32_t dq = (wk.q_k < n_own ? pl : pl + kWindow) - wk.q_pos;
+                Mq[p] = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+            }
         }
     }
 }
@@ -526,22 +541,21 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* __restrict__ in
     return ((unsigned long long)hi << 32) | lo;
 }
 
-// What a parked lane asks for.  Filled by the lane itself (its loads overlap the other lanes' parsing).
+// What a parked lane asks for.  Filled by the lane itself; all parked lanes of a warp prepare at the same time.
 struct Resolve {
     uint32_t p;        // position
     uint32_t rank;     // index of the position in its window's sorted list
     uint32_t k0;       // first visit to look at (rec_k8)
-    uint32_t floor;    // prev_length: only a longer result is of use (matching.rs:161-165)
+    uint32_t start;    // max(prev_length, 7): only a longer result is of use (matching.rs:161-165)
+    uint32_t maxl;     // min(258, bytes left)
     uint32_t n_own;    // visits k < n_own are Kw[rank - 1 - k]
     uint32_t n_vis;    // visits allowed in total (chain budget; the previous window's share may end earlier)
     uint32_t pe;       // visit k >= n_own is Kp[pe - 1 - (k - n_own)]
     uint32_t me_lo, me_hi;
 };
 
-__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t p, uint32_t rec, uint32_t floor,
-                                                uint32_t budget) {
-    const uint32_t w = p >> 15, pl = p & kWindowMask;
-    r.p = p; r.rank = rec_rank(rec); r.k0 = rec_k8(rec); r.floor = floor;
+__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t budget) {
+    const uint32_t p = r.p, w = p >> 15;
     const uint2 me = __ldg(A.K + (size_t)w * kWindow + r.rank);
     r.me_lo = me.x; r.me_hi = me.y;
     const uint32_t h = hash3(A.in[p], A.in[p + 1], A.in[p + 2]);
@@ -556,72 +570,69 @@ __device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, 
         const uint32_t ps = __ldg(op + h);
         r.pe = (h + 1u < kWindow) ? (uint32_t)__ldg(op + h + 1u) : window_count(A.n, w - 1);
         const uint32_t rem = full - r.n_own;
-        n_tot += (r.pe - ps > rem) ? rem : r.pe - ps;   // entries with a position below pl are cut off during the rounds
+        n_tot += (r.pe - ps > rem) ? rem : r.pe - ps;   // entries with a position below pl are cut off during the scan
     }
     r.n_vis = n_tot < budget ? n_tot : budget;
-    (void)pl;
+    if (r.start >= r.maxl) r.n_vis = 0;                 // nothing can be longer than the floor (matching.rs:99-101)
 }
 
-// Served by the whole warp; every argument is warp-uniform.  Returns a finalize_match record (0 = nothing longer
-// than the floor).
-__device__ __forceinline__ uint32_t resolve_warp(const ParseArgs& A, const Resolve& r) {
-    const uint32_t lane = lane_id();
-    const uint32_t p = r.p, w = p >> 15, pl = p & kWindowMask;
-    const uint32_t maxl = (A.n - p) < kMaxMatch ? (A.n - p) : kMaxMatch;
-    const uint32_t start = r.floor > kEntryBytes - 1u ? r.floor : kEntryBytes - 1u;
-    uint32_t best = start, best_q = 0;
-    if (best >= maxl) return 0u;
+// Entry of visit k of a request (warp-uniform request, lane-private k).
+__device__ __forceinline__ const uint2* resolve_entry(const ParseArgs& A, uint32_t w, uint32_t rank, uint32_t n_own, uint32_t pe,
+                                                      uint32_t k) {
     const uint2* Kw = A.K + (size_t)w * kWindow;
-    const uint2* Kp = Kw - kWindow;
-    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + A.n - 1) & ~(uintptr_t)3);
-    for (uint32_t kb = r.k0; kb < r.n_vis; kb += 32) {
-        const uint32_t k = kb + lane;
-        bool eq = false, ended = false;
-        uint32_t q = 0;
-        if (k < r.n_vis) {
-            const bool own = k < r.n_own;
-            const uint2 e = __ldg(own ? Kw + (r.rank - 1u - k) : Kp + (r.pe - 1u - (k - r.n_own)));
-            const uint32_t ep = entry_pos(e.y);
-            if (!own && ep < pl) ended = true;              // beyond the window (matching.rs:102-106); so is everything older
-            else {
-                eq = (e.x == r.me_lo) && (((e.y ^ r.me_hi) & kEntryKeyHi) == 0u);
-                q = (own ? w : w - 1u) * kWindow + ep;
-            }
-        }
-        // the byte that would extend the running best (matching.rs:141-143)
-        if (eq) eq = A.in[q + best] == A.in[p + best];
-        if (__any_sync(0xffffffffu, eq)) {
-            uint32_t l = kEntryBytes, mine = 0;
-            bool alive = eq;
-            while (__any_sync(0xffffffffu, alive)) {         // lock step: l is the same in every lane that is alive
-                if (alive) {
-                    const unsigned long long x = ld8(A.in, last_word, p + l) ^ ld8(A.in, last_word, q + l);
-                    if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
-                    else if (l + 8u >= maxl) { mine = maxl; alive = false; }
-                }
-                l += 8u;
-            }
-            mine = mine < maxl ? mine : maxl;
-            const uint32_t key = (eq && mine > best) ? ((mine << 5) | (31u - lane)) : 0u;
-            const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
-            if (mx != 0u) {                                   // the longest of the round; the nearest among equals
-                best = mx >> 5;
-                best_q = __shfl_sync(0xffffffffu, q, 31u - (mx & 31u));
-                if (best >= maxl) break;                      // matching.rs:152-156
-            }
-        }
-        if (__any_sync(0xffffffffu, ended)) break;
-    }
-    return best > start ? finalize_match(best, p - best_q) : 0u;
+    return k < n_own ? Kw + (rank - 1u - k) : Kw - kWindow + (pe - 1u - (k - n_own));
 }
 
 #ifndef DFL_PARSE_KEEP
-#define DFL_PARSE_KEEP 12     // keep parsing while at least this many lanes of a warp are running
+#define DFL_PARSE_KEEP 6      // keep parsing while at least this many lanes of a warp are running
 #endif
+constexpr uint32_t kParseThreads = 128;
+constexpr uint32_t kParseWarps = kParseThreads / 32;
+constexpr uint32_t kCandCap = 256;       // candidates a warp collects before it compares them
+struct ParseShared {
+    uint32_t cand_q[kCandCap];           // absolute position of a candidate that shares the target's 8 entry bytes
+    uint32_t cand_meta[kCandCap];        // owner lane | visit index << 5
+    uint32_t res_key[32];                // per owner lane: best length << 16 | (0xffff - visit index)
+};
+
+// Compares the collected candidates of all owners, one candidate per lane and round: the byte that would extend
+// the owner's running best first (matching.rs:141-143), then a lock-step comparison 8 bytes at a time.  The
+// longest candidate wins, the nearest among equals (matching.rs:148-157): a max over length << 16 | ~visit.
+__device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared& S, uint32_t cnt, const Resolve& rq,
+                                                const uint32_t* last_word) {
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t c = base + lane;
+        const bool have = c < cnt;
+        const uint32_t meta = have ? S.cand_meta[c] : 0u;
+        const uint32_t q = have ? S.cand_q[c] : 0u;
+        const uint32_t owner = meta & 31u, k = meta >> 5;
+        const uint32_t po = __shfl_sync(0xffffffffu, rq.p, owner);
+        const uint32_t st = __shfl_sync(0xffffffffu, rq.start, owner);
+        const uint32_t ml = __shfl_sync(0xffffffffu, rq.maxl, owner);
+        const uint32_t cur = S.res_key[owner] >> 16;          // the owner's best from earlier rounds: all of them nearer
+        const uint32_t s0 = st > cur ? st : cur;
+        bool alive = have && s0 < ml;
+        if (alive) alive = A.in[q + s0] == A.in[po + s0];
+        const bool cand = alive;
+        uint32_t l = kEntryBytes, mine = 0;
+        while (__any_sync(0xffffffffu, alive)) {              // lock step: l is the same in every lane that is alive
+            if (alive) {
+                const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
+                if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
+                else if (l + 8u >= ml) { mine = ml; alive = false; }
+            }
+            l += 8u;
+        }
+        mine = mine < ml ? mine : ml;
+        if (cand && mine > s0) atomicMax(&S.res_key[owner], (mine << 16) | (0xffffu - k));
+        __syncwarp();
+    }
+}
 
 // Every lane of the calling warp enters (work == false: the lane only helps with resolutions).  A lane with work
 // runs the reference's token selection from `st` until the first iteration position >= b.
-__device__ void parse_lanes(const ParseArgs& A, bool work, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
+__device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
     uint32_t* tk = A.segtok + (size_t)s * A.tok_cap;
     uint32_t nt = 0;
     bool have_e = false;
@@ -630,10 +641,11 @@ __device__ void parse_lanes(const ParseArgs& A, bool work, uint32_t s, ParseStat
     const int mode = A.prm.mode;
     const bool has_m = (mode != kRle) && (A.prm.checks > 0);
     const uint32_t lane = lane_id();
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
     bool running = work, parked = false, have_m = false;
-    uint32_t m_ready = 0;
+    uint32_t m_ready = 0, rq_budget = 0;
     Resolve rq;
-    rq.p = rq.rank = rq.k0 = rq.floor = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = 0;
+    rq.p = rq.rank = rq.k0 = rq.start = rq.maxl = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = 0;
     for (;;) {
         // ---- parse: every running lane takes one step per iteration
         for (;;) {
@@ -653,20 +665,25 @@ __device__ void parse_lanes(const ParseArgs& A, bool work, uint32_t s, ParseStat
                     uint32_t m = 0;
                     if (have_m) { m = m_ready; have_m = false; }
                     else if (has_m && p + 2u < n) {
+                        uint32_t floor = 0;
+                        rq_budget = A.prm.checks;
                         if (mode == kLazy) {
                             if (!st.ign) {                                   // the only case in which the reference searches (lz77.rs:347)
                                 const bool quarter = st.prev_len >= 32u;     // lz77.rs:351-355
                                 if (!quarter || A.prm.need_quarter) {
                                     m = quarter ? A.Mq[p] : A.Mf[p];
-                                    if (rec_is_long(m)) {
-                                        resolve_prepare(A, rq, p, m, st.prev_len, quarter ? A.prm.checks_quarter : A.prm.checks);
-                                        parked = true;
-                                    }
+                                    floor = st.prev_len;
+                                    if (quarter) rq_budget = A.prm.checks_quarter;
                                 }
                             }
                         } else {
                             m = A.Mf[p];
-                            if (rec_is_long(m)) { resolve_prepare(A, rq, p, m, 0u, A.prm.checks); parked = true; }
+                        }
+                        if (rec_is_long(m)) {
+                            rq.p = p; rq.rank = rec_rank(m); rq.k0 = rec_k8(m);
+                            rq.start = floor > kEntryBytes - 1u ? floor : kEntryBytes - 1u;
+                            rq.maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                            parked = true;
                         }
                     }
                     if (!parked) {
@@ -687,34 +704,79 @@ __device__ void parse_lanes(const ParseArgs& A, bool work, uint32_t s, ParseStat
             if (going == 0u) break;
             if ((uint32_t)__popc(going) < DFL_PARSE_KEEP && __any_sync(0xffffffffu, parked)) break;
         }
-        // ---- resolve: the warp serves its parked lanes in turn
-        uint32_t waiting = __ballot_sync(0xffffffffu, parked);
+        // ---- resolve the parked lanes' long records together
+        const uint32_t waiting = __ballot_sync(0xffffffffu, parked);
         if (waiting == 0u) {
             if (!__any_sync(0xffffffffu, running)) break;
             continue;
         }
-        while (waiting) {
-            const int j = __ffs((int)waiting) - 1;
-            waiting &= waiting - 1u;
-            Resolve r;
-            r.p = __shfl_sync(0xffffffffu, rq.p, j);
-            r.rank = __shfl_sync(0xffffffffu, rq.rank, j);
-            r.k0 = __shfl_sync(0xffffffffu, rq.k0, j);
-            r.floor = __shfl_sync(0xffffffffu, rq.floor, j);
-            r.n_own = __shfl_sync(0xffffffffu, rq.n_own, j);
-            r.n_vis = __shfl_sync(0xffffffffu, rq.n_vis, j);
-            r.pe = __shfl_sync(0xffffffffu, rq.pe, j);
-            r.me_lo = __shfl_sync(0xffffffffu, rq.me_lo, j);
-            r.me_hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
-            const uint32_t res = resolve_warp(A, r);
-            if ((int)lane == j) { m_ready = res; have_m = true; parked = false; }
+        if (parked) resolve_prepare(A, rq, rq_budget);       // every parked lane at once: their loads overlap
+        S.res_key[lane] = 0u;
+        __syncwarp();
+        // scan: per owner, every candidate from visit k0 on whose 8 entry bytes equal the target's goes on the list
+        uint32_t cnt = 0;
+        for (uint32_t left = waiting; left;) {
+            const int j = __ffs((int)left) - 1;
+            left &= left - 1u;
+            const uint32_t o_p = __shfl_sync(0xffffffffu, rq.p, j), o_rank = __shfl_sync(0xffffffffu, rq.rank, j);
+            const uint32_t o_k0 = __shfl_sync(0xffffffffu, rq.k0, j), o_nown = __shfl_sync(0xffffffffu, rq.n_own, j);
+            const uint32_t o_nvis = __shfl_sync(0xffffffffu, rq.n_vis, j), o_pe = __shfl_sync(0xffffffffu, rq.pe, j);
+            const uint32_t o_lo = __shfl_sync(0xffffffffu, rq.me_lo, j), o_hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
+            const uint32_t w = o_p >> 15, pl = o_p & kWindowMask;
+            bool over = false;
+            for (uint32_t kb = o_k0; kb < o_nvis && !over; kb += 128u) {
+                uint2 e[4];
+#pragma unroll
+                for (uint32_t t = 0; t < 4; t++) {               // up to 128 entries in flight
+                    const uint32_t k = kb + t * 32u + lane;
+                    e[t] = make_uint2(0u, 0u);
+                    if (k < o_nvis) e[t] = __ldg(resolve_entry(A, w, o_rank, o_nown, o_pe, k));
+                }
+#pragma unroll
+                for (uint32_t t = 0; t < 4; t++) {
+                    const uint32_t k = kb + t * 32u + lane;
+                    const bool val = k < o_nvis, own = k < o_nown;
+                    const uint32_t ep = entry_pos(e[t].y);
+                    const bool ended = val && !own && ep < pl;   // beyond the window (matching.rs:102-106); so is everything older
+                    const bool eq = val && !ended && e[t].x == o_lo && (((e[t].y ^ o_hi) & kEntryKeyHi) == 0u);
+                    const uint32_t mk = __ballot_sync(0xffffffffu, eq);
+                    if (mk) {
+                        if (cnt + 32u > kCandCap) { __syncwarp(); resolve_compare(A, S, cnt, rq, last_word); cnt = 0; }
+                        if (eq) {
+                            const uint32_t at = cnt + __popc(mk & ((1u << lane) - 1u));
+                            S.cand_q[at] = (own ? w : w - 1u) * kWindow + ep;
+                            S.cand_meta[at] = (uint32_t)j | (k << 5);
+                        }
+                        cnt += __popc(mk);
+                    }
+                    if (__any_sync(0xffffffffu, ended)) { over = true; break; }
+                }
+            }
         }
+        __syncwarp();
+        resolve_compare(A, S, cnt, rq, last_word);
+        // every owner picks up its result; the distance comes from the winning visit's entry
+        if (parked) {
+            const uint32_t key = S.res_key[lane];
+            m_ready = 0u;
+            if (key != 0u) {
+                const uint32_t k = 0xffffu - (key & 0xffffu);
+                const uint32_t w = rq.p >> 15;
+                const uint2 e = __ldg(resolve_entry(A, w, rq.rank, rq.n_own, rq.pe, k));
+                const uint32_t q = (k < rq.n_own ? w : w - 1u) * kWindow + entry_pos(e.y);
+                m_ready = finalize_match(key >> 16, rq.p - q);
+            }
+            have_m = true;
+            parked = false;
+        }
+        __syncwarp();
     }
 }
 
-constexpr uint32_t kParseThreads = 128;
+
 
 __global__ void __launch_bounds__(kParseThreads) k_parse_spec(ParseArgs A) {
+    __shared__ ParseShared sh[kParseWarps];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool work = s < A.n_seg;
     uint32_t a = 0, b = 0;
@@ -725,7 +787,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse_spec(ParseArgs A) {
         const uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
         st = (s == 0) ? state_from_key(A.begin, A.init_key) : parse_state_init(start);
     }
-    parse_lanes(A, work, s, st, a, b);
+    parse_lanes(A, sh[warp_id()], work, s, st, a, b);
 }
 
 __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* start_pos,
@@ -747,6 +809,7 @@ __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad,
 
 __global__ void __launch_bounds__(kParseThreads) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
                                                                 const uint32_t* start_key, DevMeta* meta) {
+    __shared__ ParseShared sh[kParseWarps];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool work = s < A.n_seg && bad[s];
     if (!__any_sync(0xffffffffu, work)) return;
@@ -758,13 +821,14 @@ __global__ void __launch_bounds__(kParseThreads) k_parse_repair(ParseArgs A, con
         st = state_from_key(start_pos[s], start_key[s]);
         atomicAdd(&meta->n_repaired_par, 1u);
     }
-    parse_lanes(A, work, s, st, a, b);
+    parse_lanes(A, sh[warp_id()], work, s, st, a, b);
 }
 
 // Sequential fallback (one warp; lane 0 parses, the others help with resolutions): walks the segments in order
 // and re-parses every one whose entry does not continue its predecessor's exit.  Exact for any input; only slow
 // on inputs whose speculative parses never resynchronise (e.g. megabytes of a single repeated byte).
 __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
+    __shared__ ParseShared sh;
     if (meta->n_bad == 0) return;
     const uint32_t lane = lane_id();
     for (uint32_t s = 1; s < A.n_seg; s++) {
@@ -777,7 +841,7 @@ __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* m
         if (isbad) {
             const uint32_t a = A.begin + s * A.seg;
             const uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
-            parse_lanes(A, lane == 0, s, state_from_key(xp, xk), a, b);
+            parse_lanes(A, sh, lane == 0, s, state_from_key(xp, xk), a, b);
             if (lane == 0) meta->n_repaired_seq++;
             __threadfence();
             __syncwarp();
