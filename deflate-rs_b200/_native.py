@@ -14,6 +14,8 @@ RAW, ZLIB, GZIP = 0, 1, 2
 FLUSH_SYNC, FLUSH_FINISH = 1, 2
 OK, AGAIN = 0, 1
 E_OVERFLOW = -5
+E_NCCL = -10
+COMM_ID_BYTES = 128
 
 # every symbol include/deflate_b200.h declares
 EXPORTS = [
@@ -22,6 +24,8 @@ EXPORTS = [
     "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_set_piece_bytes", "dfl_encoder_take_output",
     "dfl_encoder_advance_output", "dfl_encoder_checksum", "dfl_encoder_reset", "dfl_encoder_free",
     "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens",
+    "dfl_comm_unique_id", "dfl_comm_init", "dfl_comm_free", "dfl_comm_world", "dfl_comm_rank", "dfl_comm_last_error",
+    "dfl_gather_device",
 ]
 
 
@@ -94,6 +98,15 @@ def lib():
     L.dfl_encode_tokens.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                     ctypes.c_size_t, szp]
     L.dfl_lz77_tokens.argtypes = [ctypes.c_void_p, ctypes.c_size_t, optp, ctypes.c_void_p, ctypes.c_size_t, szp]
+    L.dfl_comm_unique_id.argtypes = [ctypes.c_void_p]
+    L.dfl_comm_init.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.dfl_comm_free.argtypes = [ctypes.c_void_p]
+    L.dfl_comm_free.restype = None
+    L.dfl_comm_world.argtypes = [ctypes.c_void_p]
+    L.dfl_comm_rank.argtypes = [ctypes.c_void_p]
+    L.dfl_comm_last_error.restype = ctypes.c_char_p
+    L.dfl_gather_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, szp,
+                                    ctypes.c_int, ctypes.c_void_p]
     _lib = L
     return L
 

@@ -623,6 +623,7 @@ extern "C" const char* dfl_strerror(int status) {
         case DFL_E_STATE: return "encoder is in the wrong state for this call";
         case DFL_E_UNSUPPORTED: return "not supported";
         case DFL_E_INTERNAL: return "internal error";
+        case DFL_E_NCCL: return "NCCL unavailable or a collective failed";
         default: return "unknown status";
     }
 }

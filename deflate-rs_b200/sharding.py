@@ -13,9 +13,12 @@ layouts are supported:
                         piece boundaries (`piece_bounds`, `encode_piece_device`,
                         `combine_adler32`)
 
-The one exchange step is bringing the compressed pieces to rank 0: `gather_streams` (an all-gather
-of the sizes, then grouped point-to-point transfers -- NCCL has no gather-v; over `gloo` the same
-code runs on CPU tensors, which is how tests/test_sharding_cpu.py covers it without a GPU).
+The one exchange step is bringing the compressed pieces to rank 0: an all-gather of the sizes, then
+grouped point-to-point transfers (NCCL has no gather-v).  On GPUs that is the library's own
+`dfl_gather_device` over its own NCCL communicator (`Comm`: ncclAllGather + grouped
+ncclSend/ncclRecv on the caller's stream, csrc/dfl_comm.cu); `gather_streams` is the same exchange
+written with torch.distributed, which also runs over `gloo` on CPU tensors -- that is how
+tests/test_sharding_cpu.py covers the host-side logic without a GPU.
 """
 import ctypes
 
@@ -105,3 +108,50 @@ def gather_streams(local, n_bytes: int, dst: int = 0, group=None, recv_buf=None)
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local[:n_bytes], dst, group)]):
             w.wait()
     return None, offs
+
+
+class Comm:
+    """The library's NCCL communicator (dfl_comm_*), bootstrapped through an existing torch.distributed group:
+    rank 0 creates the NCCL unique id, a broadcast hands it to the others, every rank then joins.  One process
+    per GPU; the communicator is bound to the current CUDA device."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _native
+
+        self._L = _native.lib()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        idbuf = (ctypes.c_uint8 * _native.COMM_ID_BYTES)()
+        if self.rank == 0:
+            _native.check(self._L.dfl_comm_unique_id(idbuf), "dfl_comm_unique_id")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0, group=group)
+        idbuf = (ctypes.c_uint8 * _native.COMM_ID_BYTES)(*t.cpu().tolist())
+        h = ctypes.c_void_p()
+        rc = self._L.dfl_comm_init(ctypes.byref(h), self.world, self.rank, idbuf)
+        if rc != 0:
+            raise RuntimeError(f"dfl_comm_init: status {rc}: {self._L.dfl_comm_last_error().decode()}")
+        self._h = h
+
+    def gather(self, local, n_bytes: int, recv_buf=None, root: int = 0, stream=None):
+        """dfl_gather_device: rank r's first n_bytes of `local` arrive at recv_buf[offs[r]:offs[r+1]] on `root`.
+        Returns (sizes, recv_buf).  The payload is only queued on `stream` (default: torch's current stream)."""
+        import torch
+
+        sizes = (ctypes.c_size_t * self.world)()
+        st = ctypes.c_void_p(stream if stream is not None else torch.cuda.current_stream(local.device).cuda_stream)
+        dst = ctypes.c_void_p(recv_buf.data_ptr()) if recv_buf is not None else None
+        cap = recv_buf.numel() if recv_buf is not None else 0
+        rc = self._L.dfl_gather_device(self._h, ctypes.c_void_p(local.data_ptr()), n_bytes, dst, cap, sizes, root, st)
+        if rc != 0:
+            raise RuntimeError(f"dfl_gather_device: status {rc}: {self._L.dfl_comm_last_error().decode()}")
+        return [int(x) for x in sizes], recv_buf
+
+    def close(self):
+        if self._h:
+            self._L.dfl_comm_free(self._h)
+            self._h = None

@@ -71,7 +71,8 @@ enum dfl_status {
     DFL_E_OVERFLOW = -5,    /* out_cap too small; *out_len receives the size needed */
     DFL_E_STATE = -6,       /* e.g. write after finish */
     DFL_E_UNSUPPORTED = -7,
-    DFL_E_INTERNAL = -8
+    DFL_E_INTERNAL = -8,
+    DFL_E_NCCL = -10        /* NCCL missing or a collective failed (dfl_comm_last_error has the text) */
 };
 const char *dfl_strerror(int status);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
@@ -189,6 +190,31 @@ int dfl_encode_tokens(const uint8_t *in, size_t n, const uint32_t *tokens, size_
 /* Runs only the LZ77 stage and returns the token stream (host memory, same encoding). */
 int dfl_lz77_tokens(const uint8_t *in, size_t n, const dfl_options *opt, uint32_t *tokens,
                     size_t tokens_cap, size_t *n_tokens);
+
+/* ---- multi-GPU: bringing the compressed streams of all ranks to one rank ----------
+ * The reference is single-process; this is what replaces "append to the caller's Vec" (lib.rs:110-122)
+ * when independent inputs -- or the pieces of one stream, dfl_compress_device_piece -- are encoded on several
+ * GPUs, one process per GPU.  Encoding needs no collective; the one exchange step is a gather-v of byte
+ * streams over NCCL (NVLink / NVSwitch): ncclAllGather of the 8-byte sizes, then grouped ncclSend / ncclRecv
+ * at the prefix offsets, all on the caller's stream.  NCCL is loaded at run time; without it these calls
+ * return DFL_E_NCCL and everything else keeps working. */
+typedef struct dfl_comm dfl_comm;
+#define DFL_COMM_ID_BYTES 128
+/* Rank 0 creates the id and hands it to the other ranks out of band (MPI, torch.distributed, a file ...). */
+int dfl_comm_unique_id(uint8_t *id /* DFL_COMM_ID_BYTES */);
+/* Collective over all `world` ranks; binds the communicator to the current CUDA device. */
+int dfl_comm_init(dfl_comm **comm, int world, int rank, const uint8_t *id);
+void dfl_comm_free(dfl_comm *comm);
+int dfl_comm_world(const dfl_comm *comm);
+int dfl_comm_rank(const dfl_comm *comm);
+const char *dfl_comm_last_error(void);
+/* Collective.  Every rank contributes the first n bytes at d_src (device); on `root` they arrive back to back in
+ * rank order at d_dst (device, dst_cap bytes; ignored elsewhere).  sizes (host, world entries, may be NULL)
+ * receives every rank's n on every rank, so rank r's bytes are d_dst[sum(sizes[0..r)) ...).  The size exchange
+ * costs one short host wait; the payload is queued on `stream` (a cudaStream_t) and the call returns without
+ * waiting for it, so the transfer overlaps whatever the caller encodes next on another stream. */
+int dfl_gather_device(dfl_comm *comm, const void *d_src, size_t n, void *d_dst, size_t dst_cap, size_t *sizes,
+                      int root, void *stream);
 
 #ifdef __cplusplus
 }
