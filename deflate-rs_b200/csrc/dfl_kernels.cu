@@ -475,6 +475,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                     const uint2 v = __ldg(Kb + ((k < n_own ? oa : ob) - k));
                     if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
                 }
+                if ((k & 15u) == 15u && __all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) { k = tmax; break; }
             }
         }
         if (k < tmax && !__all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) {   // only the previous window's list is left
@@ -485,6 +486,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                     const uint2 v = __ldg(ptr);
                     if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
                 }
+                if ((k & 15u) == 15u && __all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) break;
             }
         }
         if (act) {
@@ -596,8 +598,9 @@ struct ParseShared {
 };
 
 // Compares the collected candidates of all owners, one candidate per lane and round: the byte that would extend
-// the owner's running best first (matching.rs:141-143), then a lock-step comparison 8 bytes at a time.  The
-// longest candidate wins, the nearest among equals (matching.rs:148-157): a max over length << 16 | ~visit.
+// the owner's running best (matching.rs:141-143) and the first 8 bytes behind the entry come in one round trip,
+// longer common prefixes continue in lock step 8 bytes at a time.  The longest candidate wins, the nearest
+// among equals (matching.rs:148-157): a max over length << 16 | ~visit.
 __device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared& S, uint32_t cnt, const Resolve& rq,
                                                 const uint32_t* last_word) {
     const uint32_t lane = lane_id();
@@ -613,9 +616,15 @@ __device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared&
         const uint32_t cur = S.res_key[owner] >> 16;          // the owner's best from earlier rounds: all of them nearer
         const uint32_t s0 = st > cur ? st : cur;
         bool alive = have && s0 < ml;
-        if (alive) alive = A.in[q + s0] == A.in[po + s0];
-        const bool cand = alive;
-        uint32_t l = kEntryBytes, mine = 0;
+        uint32_t mine = 0, l = kEntryBytes;
+        if (alive) {
+            const uint32_t bq = A.in[q + s0], bp = A.in[po + s0];
+            const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
+            if (bq != bp) alive = false;
+            else if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
+            else if (l + 8u >= ml) { mine = ml; alive = false; }
+        }
+        l += 8u;
         while (__any_sync(0xffffffffu, alive)) {              // lock step: l is the same in every lane that is alive
             if (alive) {
                 const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
@@ -625,8 +634,28 @@ __device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared&
             l += 8u;
         }
         mine = mine < ml ? mine : ml;
-        if (cand && mine > s0) atomicMax(&S.res_key[owner], (mine << 16) | (0xffffu - k));
+        if (mine > s0) atomicMax(&S.res_key[owner], (mine << 16) | (0xffffu - k));
         __syncwarp();
+    }
+}
+
+// One owner's request, broadcast to the warp.
+struct Owner { uint32_t p, rank, k0, n_own, n_vis, pe, lo, hi; };
+__device__ __forceinline__ Owner resolve_owner(const Resolve& rq, int j) {
+    Owner o;
+    o.p = __shfl_sync(0xffffffffu, rq.p, j); o.rank = __shfl_sync(0xffffffffu, rq.rank, j);
+    o.k0 = __shfl_sync(0xffffffffu, rq.k0, j); o.n_own = __shfl_sync(0xffffffffu, rq.n_own, j);
+    o.n_vis = __shfl_sync(0xffffffffu, rq.n_vis, j); o.pe = __shfl_sync(0xffffffffu, rq.pe, j);
+    o.lo = __shfl_sync(0xffffffffu, rq.me_lo, j); o.hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
+    return o;
+}
+// Entries of visits kb + 32 t + lane, t = 0..3 (up to 128 entries of one owner in flight).
+__device__ __forceinline__ void resolve_load4(const ParseArgs& A, const Owner& o, uint32_t kb, uint2 e[4]) {
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+        const uint32_t k = kb + t * 32u + lane_id();
+        e[t] = make_uint2(0u, 0u);
+        if (k < o.n_vis) e[t] = __ldg(resolve_entry(A, o.p >> 15, o.rank, o.n_own, o.pe, k));
     }
 }
 
@@ -713,32 +742,35 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
         if (parked) resolve_prepare(A, rq, rq_budget);       // every parked lane at once: their loads overlap
         S.res_key[lane] = 0u;
         __syncwarp();
-        // scan: per owner, every candidate from visit k0 on whose 8 entry bytes equal the target's goes on the list
+        // scan: per owner, every candidate from visit k0 on whose 8 entry bytes equal the target's goes on the list;
+        // the entries of the next owner are requested before the current one's are looked at
         uint32_t cnt = 0;
-        for (uint32_t left = waiting; left;) {
-            const int j = __ffs((int)left) - 1;
-            left &= left - 1u;
-            const uint32_t o_p = __shfl_sync(0xffffffffu, rq.p, j), o_rank = __shfl_sync(0xffffffffu, rq.rank, j);
-            const uint32_t o_k0 = __shfl_sync(0xffffffffu, rq.k0, j), o_nown = __shfl_sync(0xffffffffu, rq.n_own, j);
-            const uint32_t o_nvis = __shfl_sync(0xffffffffu, rq.n_vis, j), o_pe = __shfl_sync(0xffffffffu, rq.pe, j);
-            const uint32_t o_lo = __shfl_sync(0xffffffffu, rq.me_lo, j), o_hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
-            const uint32_t w = o_p >> 15, pl = o_p & kWindowMask;
+        uint32_t left = waiting;
+        int j = __ffs((int)left) - 1;
+        left &= left - 1u;
+        Owner o = resolve_owner(rq, j);
+        uint2 e[4];
+        resolve_load4(A, o, o.k0, e);
+        for (;;) {
+            const int jn = left ? __ffs((int)left) - 1 : -1;
+            Owner on = o;
+            uint2 en[4];
+            if (jn >= 0) {
+                left &= left - 1u;
+                on = resolve_owner(rq, jn);
+                resolve_load4(A, on, on.k0, en);
+            }
+            const uint32_t w = o.p >> 15, pl = o.p & kWindowMask;
             bool over = false;
-            for (uint32_t kb = o_k0; kb < o_nvis && !over; kb += 128u) {
-                uint2 e[4];
-#pragma unroll
-                for (uint32_t t = 0; t < 4; t++) {               // up to 128 entries in flight
-                    const uint32_t k = kb + t * 32u + lane;
-                    e[t] = make_uint2(0u, 0u);
-                    if (k < o_nvis) e[t] = __ldg(resolve_entry(A, w, o_rank, o_nown, o_pe, k));
-                }
+            for (uint32_t kb = o.k0; kb < o.n_vis && !over; kb += 128u) {
+                if (kb != o.k0) resolve_load4(A, o, kb, e);      // chain budgets above 128 only
 #pragma unroll
                 for (uint32_t t = 0; t < 4; t++) {
                     const uint32_t k = kb + t * 32u + lane;
-                    const bool val = k < o_nvis, own = k < o_nown;
+                    const bool val = k < o.n_vis, own = k < o.n_own;
                     const uint32_t ep = entry_pos(e[t].y);
                     const bool ended = val && !own && ep < pl;   // beyond the window (matching.rs:102-106); so is everything older
-                    const bool eq = val && !ended && e[t].x == o_lo && (((e[t].y ^ o_hi) & kEntryKeyHi) == 0u);
+                    const bool eq = val && !ended && e[t].x == o.lo && (((e[t].y ^ o.hi) & kEntryKeyHi) == 0u);
                     const uint32_t mk = __ballot_sync(0xffffffffu, eq);
                     if (mk) {
                         if (cnt + 32u > kCandCap) { __syncwarp(); resolve_compare(A, S, cnt, rq, last_word); cnt = 0; }
@@ -752,6 +784,10 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                     if (__any_sync(0xffffffffu, ended)) { over = true; break; }
                 }
             }
+            if (jn < 0) break;
+            j = jn; o = on;
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) e[t] = en[t];
         }
         __syncwarp();
         resolve_compare(A, S, cnt, rq, last_word);
@@ -777,7 +813,10 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
 
 __global__ void __launch_bounds__(kParseThreads) k_parse_spec(ParseArgs A) {
     __shared__ ParseShared sh[kParseWarps];
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    // The lanes of a warp take segments far apart (stride = number of warps in the grid): the cost of a segment
+    // depends on the kind of data, neighbouring segments are of one kind, and a warp is as slow as its slowest lane.
+    const uint32_t n_warps = gridDim.x * kParseWarps;
+    const uint32_t s = lane_id() * n_warps + blockIdx.x * kParseWarps + warp_id();
     const bool work = s < A.n_seg;
     uint32_t a = 0, b = 0;
     ParseState st = parse_state_init(0);

@@ -117,7 +117,7 @@ void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vecto
 // Every candidate from visit k8 on that shares the target's 8 entry bytes is compared on the data; the first
 // strictly longer one wins (matching.rs:148-157), starting from max(floor, 7): the caller only uses a result
 // longer than `floor` (= prev_length, matching.rs:161-165) and the record proves a length of at least 8.
-uint64_t g_resolve_stats[4] = {0, 0, 0, 0};   // resolutions, candidates compared, bytes compared, visits scanned
+uint64_t g_resolve_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // resolutions, candidates compared, bytes compared, visits scanned
 uint32_t resolve_long(const uint8_t* d, uint32_t n, const std::vector<Entry>& K, const std::vector<uint16_t>& off,
                       const std::vector<uint32_t>& cnt, uint32_t p, uint32_t rec, uint32_t floor, uint32_t budget,
                       uint32_t full_budget) {
@@ -140,6 +140,16 @@ uint32_t resolve_long(const uint8_t* d, uint32_t n, const std::vector<Entry>& K,
         while (l < maxl && d[p + l] == d[q + l]) l++;
         g_resolve_stats[2] += l - kEntryBytes;
         if (l > best) { best = l; best_q = q; if (l == maxl) break; }
+    }
+    {   // statistics: is the nearest candidate that shares the 8 entry bytes already the answer?
+        uint32_t k = rec_k8(rec);
+        Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+        uint32_t q = (k < c.n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
+        uint32_t l = 0; while (l < maxl && d[p + l] == d[q + l]) l++;
+        uint32_t want = best > std::max(floor, kEntryBytes - 1u) ? best : 0, got = l > std::max(floor, kEntryBytes - 1u) ? l : 0;
+        if (want == got) g_resolve_stats[4]++;
+        if (floor >= 8) g_resolve_stats[5]++;
+        if (want == 0) g_resolve_stats[6]++;
     }
     return best > std::max(floor, kEntryBytes - 1u) ? finalize_match(best, p - best_q) : 0u;
 }
@@ -413,8 +423,8 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 void dflm_free(void* p) { free(p); }
 uint32_t dflm_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return crc32_combine(c1, c2, len2); }
 uint32_t dflm_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
-void dflm_resolve_stats(uint64_t* o /*[4]*/, int reset) {
-    for (int i = 0; i < 4; i++) { o[i] = g_resolve_stats[i]; if (reset) g_resolve_stats[i] = 0; }
+void dflm_resolve_stats(uint64_t* o /*[8]*/, int reset) {
+    for (int i = 0; i < 8; i++) { o[i] = g_resolve_stats[i]; if (reset) g_resolve_stats[i] = 0; }
 }
 
 }

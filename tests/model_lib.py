@@ -36,9 +36,10 @@ def lib():
 
 def resolve_stats(reset=True):
     """Counters of the long-match resolutions the parser asked for since the last reset."""
-    st = (ctypes.c_uint64 * 4)()
+    st = (ctypes.c_uint64 * 8)()
     lib().dflm_resolve_stats(st, 1 if reset else 0)
-    return {"resolutions": st[0], "candidates": st[1], "bytes": st[2], "visits": st[3]}
+    return {"resolutions": st[0], "candidates": st[1], "bytes": st[2], "visits": st[3], "nearest_is_answer": st[4],
+            "floor_ge_8": st[5], "no_result": st[6]}
 
 
 def compress(data, opts, pseg=8192, warm=1024, rounds=4):
