@@ -43,6 +43,14 @@ CONFIGS = {
                opts="Compression::Default, one zlib stream per chunk, chunks dealt round-robin to the GPUs"),
     "c5": dict(gen="binary_like", seed=0xB1A2, size_mib=256, preset="high", wrap="raw",
                desc="synthetic binary", opts="CompressionOptions::high() (1768 checks, lazy<128), raw deflate"),
+    # not BASELINE configs: the input classes on which a stage could fall off a cliff (stored blocks, parses that
+    # never resynchronise), measured with the same machinery and kept under profiles/
+    "x_random": dict(gen="random_bytes", seed=7, size_mib=1024, preset="default", wrap="raw",
+                     desc="uniform random bytes (every block stored)", opts="Compression::Default, raw deflate"),
+    "x_zeros": dict(gen="zero_bytes", seed=0, size_mib=256, preset="default", wrap="raw",
+                    desc="zero bytes (258-byte matches at distance 1)", opts="Compression::Default, raw deflate"),
+    "x_issue44": dict(gen="issue44_like", seed=0, size_mib=256, preset="default", wrap="raw",
+                      desc="tests/fixtures/issue_44 (three byte values, long runs) repeated", opts="Compression::Default, raw deflate"),
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per input byte, from the ncu --set full
@@ -199,22 +207,36 @@ def run_chunks(args):
     srcs = [h.to(dev) for h in host]
     cap = L.dfl_bound(chunk, dfl.ZLIB) + 64
     outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in mine]
-    packed = torch.empty(len(mine) * cap, dtype=torch.uint8, device=dev)
-    gather_buf = None
-    sizes = []
+    # The exchange step (chunks -> rank 0) is the library's dfl_gather_device over its own NCCL communicator.  The
+    # chunks of a rank are encoded in groups; the gather of a group is queued on a side stream and travels while
+    # the next group is being encoded.
+    comm = sharding.Comm() if world > 1 else None
+    n_groups = max(1, min(4, len(mine)))
+    groups = [list(range(g, len(mine), n_groups)) for g in range(n_groups)]
+    packed = [torch.empty(len(g) * cap, dtype=torch.uint8, device=dev) for g in groups]
+    per_rank_max = -(-n_chunks // world)
+    recv = [torch.empty(world * (-(-per_rank_max // n_groups)) * cap, dtype=torch.uint8, device=dev) for _ in groups] \
+        if (world > 1 and rank == 0) else [None] * n_groups
+    side = torch.cuda.Stream(device=dev)
+    sizes = [0] * len(mine)
 
     def step():
-        nonlocal gather_buf, sizes
-        _, sizes = dfl.compress_device_batch(srcs, dfl.Compression.Default, dfl.ZLIB, outs)
-        off = 0
-        for o, s in zip(outs, sizes):
-            packed[off:off + s].copy_(o[:s])
-            off += s
-        if world > 1:
-            buf, _ = sharding.gather_streams(packed, off, dst=0, recv_buf=gather_buf)
-            if rank == 0:
-                gather_buf = buf
-        return off
+        cur = torch.cuda.current_stream(dev)
+        total = 0
+        for gi, g in enumerate(groups):
+            _, sz_g = dfl.compress_device_batch([srcs[i] for i in g], dfl.Compression.Default, dfl.ZLIB, [outs[i] for i in g])
+            off = 0
+            for i, s_ in zip(g, sz_g):
+                packed[gi][off:off + s_].copy_(outs[i][:s_])
+                sizes[i] = s_
+                off += s_
+            if comm is not None:
+                side.wait_stream(cur)
+                comm.gather(packed[gi], off, recv[gi], root=0, stream=side.cuda_stream)
+            total += off
+        if comm is not None:
+            cur.wait_stream(side)
+        return total
 
     def barrier():
         if world > 1:
@@ -239,6 +261,11 @@ def run_chunks(args):
     ev1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
+    mine_t = {"rank": rank, "ms_per_step": ev0.elapsed_time(ev1) / args.steps, "chunks": len(mine)}
+    per_rank = [mine_t]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_t)
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(csize)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -282,7 +309,9 @@ def run_chunks(args):
             "config": {"workload": f"{args.size_mib} MiB {cfg['desc']} (seed {cfg['seed']:#x}+i), {cfg['opts']}", "name": "c4",
                        "l2": "1 GiB of input per step, larger than L2", "compressed_bytes": int(tot.item()),
                        "ratio": float(tot.item()) / total_in, "verified": args.verify,
-                       "parallelism": f"{n_chunks} chunks over {world} GPU(s), NCCL gather to rank 0" if world > 1 else "single GPU"},
+                       "parallelism": f"{n_chunks} chunks over {world} GPU(s), dfl_gather_device (NCCL) to rank 0 per group of chunks, "
+                                      f"overlapping the next group's encode" if world > 1 else "single GPU"},
+            "per_rank": per_rank,
             "e2e": {"value": total_in / float(te.item()) / 2 ** 20, "unit": UNIT, "h2d_bytes_per_step": chunk * len(mine),
                     "d2h_bytes_per_step": int(csize)},
             "gpu_launches": None, "clocks": clk,
@@ -290,6 +319,8 @@ def run_chunks(args):
                              "sample": f"one chunk ({chunk >> 20} MiB), oracle/, {cpu_dt:.1f} s", "ratio": cpu_csize / min(chunk, args.cpu_sample_mib << 20)},
         }
         emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -327,19 +358,18 @@ def run_ours(args):
     sz = ctypes.c_size_t()
     stream = torch.cuda.current_stream(dev)
 
-    gather_buf = None
+    # the one real exchange step: compressed shards -> rank 0 through the library's own NCCL communicator
+    # (dfl_gather_device: ncclAllGather of the sizes, grouped ncclSend/ncclRecv, queued on this stream)
+    comm = sharding.Comm() if world > 1 else None
+    gather_buf = torch.empty(world * cap, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
 
     def step():
         rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), size, ctypes.byref(opts), wrap, None, 0,
                                    ctypes.c_void_p(out.data_ptr()), cap, ctypes.byref(sz), ctypes.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise dfl.DeflateB200Error(rc, "dfl_compress_device")
-        if world > 1:
-            # the one real exchange step: compressed shards -> rank 0 (sizes all-gather, then send/recv)
-            nonlocal gather_buf
-            buf, _ = sharding.gather_streams(out, sz.value, dst=0, recv_buf=gather_buf)
-            if rank == 0:
-                gather_buf = buf
+        if comm is not None:
+            comm.gather(out, sz.value, gather_buf, root=0, stream=stream.cuda_stream)
         return sz.value
 
     def barrier():
@@ -367,22 +397,34 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
     names = (ctypes.c_char_p * 32)()
     ms = (ctypes.c_float * 32)()
     cnt = (ctypes.c_uint64 * 8)()
+    # inputs larger than the 126 MB L2 need no flush; smaller ones get one (a 256 MiB write) before every timed step
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if size < (192 << 20) else None
+    elapsed_ms = 0.0
     for _ in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        ev0.record(stream)
         step()
+        ev1.record(stream)
+        ev1.synchronize()
+        elapsed_ms += ev0.elapsed_time(ev1)
         k = L.dfl_last_stage_times(names, ms, 32)
         for i in range(k):
             stage_tot[names[i].decode()] = stage_tot.get(names[i].decode(), 0.0) + ms[i]
         L.dfl_last_counters(cnt, 8)
         launches += int(cnt[5])
-    ev1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
     L.dfl_set_profiling(0)
-    elapsed_ms = ev0.elapsed_time(ev1)
+    # every rank's own clock and stage times travel to rank 0: a slow rank or stage must be visible in the line
+    mine = {"rank": rank, "ms_per_step": elapsed_ms / args.steps, "stage_ms": {k: v / args.steps for k, v in stage_tot.items()}}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -426,9 +468,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{args.size_mib} MiB {cfg['desc']} per GPU (seed {cfg['seed']:#x}+rank), {cfg['opts']}",
                        "name": args.config,
-                       "l2": "input (>= 1 GiB) larger than L2, no flush needed", "compressed_bytes": csize,
+                       "l2": (f"input ({args.size_mib} MiB) larger than the 126 MB L2, no flush needed" if flush is None
+                              else "L2 flushed (256 MiB write) before every timed step"), "compressed_bytes": csize,
                        "ratio": csize / size, "verified": args.verify,
-                       "parallelism": f"independent shards x{world}, NCCL gather to rank 0" if world > 1 else "single GPU"},
+                       "parallelism": f"independent shards x{world}, dfl_gather_device (NCCL) to rank 0" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": size, "d2h_bytes_per_step": int(n_out.value)},
             "gpu_launches": launches,
             "clocks": clk,
@@ -441,11 +484,14 @@ def run_ours(args):
                          "note": "algorithmic bytes = N read + C written over the dominant kernel's duration; the path "
                                  "is instruction/shared-memory bound (SURVEY 8(d)), not HBM bound"},
             "stage_ms": {k: v / args.steps for k, v in stage_tot.items()},
+            "per_rank": per_rank,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"first {cpu_sample >> 20} MiB of the same input, oracle/ (C port of the reference "
                                        f"algorithm), {cpu_dt:.1f} s", "ratio": cpu_csize / cpu_sample},
         }
         emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -1083,7 +1083,8 @@ __device__ __forceinline__ int choose_block_dev(const BlockCost& c, uint32_t pen
 
 __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCost* __restrict__ cost, int* blk_type,
                                                     unsigned long long* blk_bit, unsigned long long* blk_in,
-                                                    int sync_marker, uint32_t in_begin, uint32_t carry_bits_n) {
+                                                    int sync_marker, uint32_t in_begin, uint32_t carry_bits_n,
+                                                    uint32_t* out32, unsigned long long out_bit_base, unsigned long long out_cap) {
     __shared__ unsigned long long tot[256 * 8];   // bits consumed by a thread's run per entry alignment
     __shared__ unsigned long long inb[256];
     __shared__ unsigned long long entry_bit[256];
@@ -1129,6 +1130,13 @@ __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCo
         meta->stream_bytes = (bit + 7ull) >> 3;
     }
     __syncthreads();
+    // k_pack writes whole words; the words two blocks share (and what lies behind the last block: sync marker,
+    // padding) are combined with atomicOr and must start out as zero.  Nothing else is cleared.
+    const bool fits = out32 != nullptr && (out_bit_base >> 3) + meta->stream_bytes + 16ull <= out_cap;
+    if (fits && threadIdx.x == 0) {
+        const unsigned long long w0 = (out_bit_base + entry_bit[0]) >> 5;   // first word of the stream (may hold container bytes too)
+        out32[w0] = 0u;
+    }
     unsigned long long bit = entry_bit[threadIdx.x], in_off = inb[threadIdx.x];
     uint32_t n_st = 0, n_fx = 0;
     for (uint32_t b = lo; b < hi; b++) {
@@ -1142,43 +1150,38 @@ __global__ void __launch_bounds__(256) k_block_scan(DevMeta* meta, const BlockCo
         in_off += c.input_bytes;
         n_st += (t == kStored);
         n_fx += (t == kFixed);
+        if (fits) {
+            const unsigned long long w = (out_bit_base + bit) >> 5;       // the word this block shares with the next one
+            out32[w] = 0u;
+            if (b + 1 == nb) { out32[w + 1] = 0u; out32[w + 2] = 0u; }   // 3 header bits, padding and 00 00 of a sync marker
+        }
         if (b + 1 == nb) blk_bit[nb] = bit;
     }
     if (n_st) atomicAdd(&meta->n_stored, n_st);
     if (n_fx) atomicAdd(&meta->n_fixed, n_fx);
 }
 
-// Zero exactly the output words the stream will occupy (bits are ORed in by k_pack).
-__global__ void __launch_bounds__(256) k_zero_out(const DevMeta* meta, uint4* out, unsigned long long out_cap,
-                                                  uint32_t hdr_bytes) {
-    unsigned long long need = hdr_bytes + meta->stream_bytes + 16ull;
-    if (need > out_cap) need = out_cap;
-    unsigned long long n16 = (need + 15ull) >> 4;
-    if (n16 * 16ull > out_cap) n16 = out_cap >> 4;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        out[i] = make_uint4(0, 0, 0, 0);
-}
-
 // =====================================================================================
-// k_pack: one CTA per deflate block.  Output words are pre-zeroed; bits are ORed in.
+// k_pack: one CTA per deflate block.  The block's bits are assembled in shared memory, a tile of 1024 items
+// (header fields, tokens, end-of-block) at a time: per-item bit widths -> CTA prefix sum -> every item ORed into
+// a shared word buffer -> the completed words leave as coalesced 16-byte stores.  A block owns every output
+// word that lies completely inside its bit range; only the word it shares with the block in front of it and
+// the one it shares with the block behind it are combined with atomicOr (k_block_scan has zeroed those).
+// Stored blocks are a byte-shifted copy of the input, one output word per thread.
+// (encoder_state.rs:58-105, huffman_lengths.rs:290-369, bitstream.rs:76-106, stored_block.rs:13-40, compress.rs:59-77)
 // =====================================================================================
-__device__ __forceinline__ void put_bits(uint32_t* out32, unsigned long long bitpos, unsigned long long v, uint32_t nbits) {
-    if (nbits == 0) return;
-    unsigned long long w = bitpos >> 5;
-    uint32_t s = (uint32_t)(bitpos & 31ull);
-    unsigned long long lo = v << s;
-    uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)(lo >> 32);
-    uint32_t x2 = s ? (uint32_t)(v >> (64u - s)) : 0u;
-    if (x0) atomicOr(&out32[w], x0);
-    if (x1) atomicOr(&out32[w + 1], x1);
-    if (x2) atomicOr(&out32[w + 2], x2);
-}
-__device__ __forceinline__ void put_byte(uint32_t* out32, unsigned long long byte_idx, uint32_t v) {
-    if (v) atomicOr(&out32[byte_idx >> 2], v << ((uint32_t)(byte_idx & 3ull) * 8u));
-}
-
 constexpr uint32_t kPackThreads = 256;
+constexpr uint32_t kPackItems = 4;                                // consecutive items per thread and tile
+constexpr uint32_t kPackTile = kPackThreads * kPackItems;
+constexpr uint32_t kPackWords = kPackTile * 48u / 32u + 8u;       // an item is at most 48 bits
+
+// word `g` of the output: plain store if the block owns it, atomicOr if a neighbouring block writes into it too
+__device__ __forceinline__ void pack_store_word(uint32_t* out32, unsigned long long g, uint32_t v, unsigned long long bs,
+                                                unsigned long long be) {
+    const bool shared = (g == (bs >> 5) && (bs & 31ull)) || (g == (be >> 5) && (be & 31ull));
+    if (shared) { if (v) atomicOr(&out32[g], v); }
+    else out32[g] = v;
+}
 
 __global__ void __launch_bounds__(kPackThreads)
 k_pack(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, DevMeta* meta, const BlockCost* __restrict__ cost,
@@ -1187,7 +1190,9 @@ k_pack(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, DevMeta
        uint32_t* __restrict__ out32, unsigned long long out_bit_base, int final_block, unsigned long long out_cap) {
     __shared__ uint32_t ll_cl[288];   // code | len << 16
     __shared__ uint32_t d_cl[32];
+    __shared__ uint32_t c_cl[19];
     __shared__ uint32_t ws[33];
+    __shared__ uint32_t sw[kPackWords];
     const uint32_t b = blockIdx.x;
     const uint32_t nb = meta->n_blocks;
     if (b >= nb) return;
@@ -1200,29 +1205,35 @@ k_pack(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, DevMeta
     const uint32_t ntok = (uint32_t)((T - t0) < kBlockTokens ? (T - t0) : kBlockTokens);
     const int type = blk_type[b];
     const int last = (b + 1 == nb) && final_block;
-    unsigned long long bp = blk_bit[b] + out_bit_base;
+    const unsigned long long bs = blk_bit[b] + out_bit_base, be = blk_bit[b + 1] + out_bit_base;
 
     if (type == kStored) {
-        unsigned long long pos = blk_in[b], left = cost[b].input_bytes;
-        while (left > 0) {
-            uint32_t chunk = left < kMaxStored ? (uint32_t)left : kMaxStored;
-            int lastchunk = (left == chunk);
-            if (threadIdx.x == 0 && last && lastchunk) put_bits(out32, bp, 1ull, 3);
-            bp += 3ull;
-            bp = (bp + 7ull) & ~7ull;
-            unsigned long long byte0 = bp >> 3;
-            if (threadIdx.x == 0) {
-                put_byte(out32, byte0, chunk & 0xffu);
-                put_byte(out32, byte0 + 1, chunk >> 8);
-                put_byte(out32, byte0 + 2, (~chunk) & 0xffu);
-                put_byte(out32, byte0 + 3, ((~chunk) >> 8) & 0xffu);
+        // bytes of the block: [B0] the 3 header bits (BFINAL only ever sets one of them) and padding, then per chunk
+        // LEN, ~LEN, data; every chunk after the first is preceded by its own header byte (stored_block.rs:13-40)
+        const unsigned long long pos0 = blk_in[b], nbytes = cost[b].input_bytes;
+        const unsigned long long k = (nbytes - 1ull) / kMaxStored + 1ull;           // chunks (nbytes > 0 for a stored block)
+        const unsigned long long B0 = bs >> 3, D0 = (bs + 3ull + 7ull) >> 3, Bend = be >> 3;
+        const uint32_t stride = kMaxStored + 5u;
+        for (unsigned long long g = (bs >> 5) + threadIdx.x; g <= ((be - 1ull) >> 5); g += blockDim.x) {
+            uint32_t word = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                const unsigned long long jb = g * 4ull + i;
+                uint32_t v = 0;
+                if (jb >= D0 && jb < Bend) {
+                    const unsigned long long rel = jb - D0, c = rel / stride;
+                    const uint32_t r = (uint32_t)(rel - c * stride);
+                    const uint32_t len_c = c + 1ull < k ? kMaxStored : (uint32_t)(nbytes - c * kMaxStored);
+                    if (r < 4u) { const uint32_t lv = r < 2u ? len_c : ~len_c; v = (lv >> (8u * (r & 1u))) & 0xffu; }
+                    else if (r < 4u + len_c) v = in[pos0 + c * kMaxStored + (r - 4u)];
+                    else v = (last && c + 2ull == k) ? 1u : 0u;                      // header byte of chunk c + 1
+                } else if (jb == B0 && jb < D0) {
+                    v = (last && k == 1ull) ? (1u << (uint32_t)(bs & 7ull)) : 0u;
+                }
+                word |= v << (8u * i);
             }
-            for (uint32_t i = threadIdx.x; i < chunk; i += blockDim.x) put_byte(out32, byte0 + 4 + i, in[pos + i]);
-            bp += 32ull + 8ull * chunk;
-            pos += chunk;
-            left -= chunk;
+            pack_store_word(out32, g, word, bs, be);
         }
-        if (threadIdx.x == 0 && bp != blk_bit[b + 1] + out_bit_base) meta->err = 2;
         return;
     }
 
@@ -1238,66 +1249,122 @@ k_pack(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, DevMeta
     } else {
         for (uint32_t s = threadIdx.x; s < 288; s += blockDim.x) ll_cl[s] = tb.ll_code[s] | ((uint32_t)tb.ll_len[s] << 16);
         if (threadIdx.x < 32) d_cl[threadIdx.x] = tb.d_code[threadIdx.x] | ((uint32_t)tb.d_len[threadIdx.x] << 16);
+        if (threadIdx.x < 19) c_cl[threadIdx.x] = tb.cl_code[threadIdx.x] | ((uint32_t)tb.cl_len[threadIdx.x] << 16);
     }
+    // items of the block: header fields (encoder_state.rs:85-99, huffman_lengths.rs:290-369), tokens, end-of-block
+    const uint32_t hclens = type == kDynamic ? tb.used_hclens : 0u;
+    const uint32_t n_hsym = type == kDynamic ? tb.n_hdr_sym : 0u;
+    const uint32_t n_hdr = type == kDynamic ? 4u + hclens + n_hsym : 1u;
+    const uint32_t n_items = n_hdr + ntok + 1u;
+    if (threadIdx.x == 0) sw[0] = 0u;
     __syncthreads();
 
-    unsigned long long body = bp + 3ull;
-    if (type == kDynamic) body += cost[b].hdr_bits;
-    if (threadIdx.x == 0) {
-        // encoder_state.rs:85-99 block marker, then huffman_lengths.rs:290-369 header
-        if (type == kFixed) put_bits(out32, bp, last ? 3ull : 2ull, 3);
-        else {
-            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-            unsigned long long q = bp;
-            put_bits(out32, q, last ? 5ull : 4ull, 3); q += 3;
-            put_bits(out32, q, tb.hlit - 257u, 5); q += 5;
-            put_bits(out32, q, tb.hdist - 1u, 5); q += 5;
-            put_bits(out32, q, tb.used_hclens - 4u, 4); q += 4;
-            for (uint32_t i = 0; i < tb.used_hclens; i++) { put_bits(out32, q, tb.cl_len[order[i]], 3); q += 3; }
-            for (uint32_t i = 0; i < tb.n_hdr_sym; i++) {
-                uint32_t sym = tb.hdr_sym[i] & 31u, rep = tb.hdr_sym[i] >> 8;
-                put_bits(out32, q, tb.cl_code[sym], tb.cl_len[sym]); q += tb.cl_len[sym];
-                if (sym == 16u) { put_bits(out32, q, rep - 3u, 2); q += 2; }
-                else if (sym == 17u) { put_bits(out32, q, rep - 3u, 3); q += 3; }
-                else if (sym == 18u) { put_bits(out32, q, rep - 11u, 7); q += 7; }
+    unsigned long long bitpos = bs;
+    for (uint32_t base = 0; base < n_items; base += kPackTile) {
+        unsigned long long v[kPackItems];
+        uint32_t nbv[kPackItems];
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < kPackItems; q++) {
+            const uint32_t i = base + threadIdx.x * kPackItems + q;
+            unsigned long long x = 0;
+            uint32_t nbits = 0;
+            if (i < n_hdr) {
+                if (type == kFixed) { x = last ? 3ull : 2ull; nbits = 3; }
+                else if (i == 0u) { x = last ? 5ull : 4ull; nbits = 3; }
+                else if (i == 1u) { x = tb.hlit - 257u; nbits = 5; }
+                else if (i == 2u) { x = tb.hdist - 1u; nbits = 5; }
+                else if (i == 3u) { x = hclens - 4u; nbits = 4; }
+                else if (i < 4u + hclens) {
+                    const uint32_t order = 0u;   // 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, 5 bits each, packed below
+                    (void)order;
+                    const unsigned long long ord_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) |
+                                                      (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+                    const unsigned long long ord_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+                    const uint32_t oi = i - 4u;
+                    const uint32_t sym = (uint32_t)((oi < 12u ? ord_lo >> (5u * oi) : ord_hi >> (5u * (oi - 12u))) & 31ull);
+                    x = c_cl[sym] >> 16; nbits = 3;
+                } else {
+                    const uint32_t hs = tb.hdr_sym[i - 4u - hclens];
+                    const uint32_t sym = hs & 31u, rep = hs >> 8;
+                    const uint32_t cl = c_cl[sym];
+                    x = cl & 0xffffu; nbits = cl >> 16;
+                    if (sym == 16u) { x |= (unsigned long long)(rep - 3u) << nbits; nbits += 2; }
+                    else if (sym == 17u) { x |= (unsigned long long)(rep - 3u) << nbits; nbits += 3; }
+                    else if (sym == 18u) { x |= (unsigned long long)(rep - 11u) << nbits; nbits += 7; }
+                }
+            } else if (i < n_hdr + ntok) {
+                const uint32_t t = tok[t0 + (i - n_hdr)];
+                const uint32_t d = tok_dist(t);
+                if (d) {
+                    uint32_t c, ne, ev;
+                    length_symbol(tok_lo(t), c, ne, ev);
+                    uint32_t cl = ll_cl[c];
+                    x = cl & 0xffffu; nbits = cl >> 16;
+                    x |= (unsigned long long)ev << nbits; nbits += ne;
+                    dist_symbol(d, c, ne, ev);
+                    cl = d_cl[c];
+                    x |= (unsigned long long)(cl & 0xffffu) << nbits; nbits += cl >> 16;
+                    x |= (unsigned long long)ev << nbits; nbits += ne;
+                } else {
+                    const uint32_t cl = ll_cl[tok_lo(t)];
+                    x = cl & 0xffffu; nbits = cl >> 16;
+                }
+            } else if (i == n_hdr + ntok) {
+                const uint32_t cl = ll_cl[kEob];
+                x = cl & 0xffffu; nbits = cl >> 16;
             }
-            if (q != body) meta->err = 3;
-        }
-    }
-
-    unsigned long long running = body;
-    for (uint32_t base = 0; base < ntok; base += blockDim.x) {
-        uint32_t i = base + threadIdx.x;
-        unsigned long long v = 0;
-        uint32_t nbits = 0;
-        if (i < ntok) {
-            uint32_t t = tok[t0 + i];
-            uint32_t d = tok_dist(t);
-            if (d) {
-                uint32_t c, ne, ev;
-                length_symbol(tok_lo(t), c, ne, ev);
-                uint32_t cl = ll_cl[c];
-                v = cl & 0xffffu; nbits = cl >> 16;
-                v |= (unsigned long long)ev << nbits; nbits += ne;
-                dist_symbol(d, c, ne, ev);
-                cl = d_cl[c];
-                v |= (unsigned long long)(cl & 0xffffu) << nbits; nbits += cl >> 16;
-                v |= (unsigned long long)ev << nbits; nbits += ne;
-            } else {
-                uint32_t cl = ll_cl[tok_lo(t)];
-                v = cl & 0xffffu; nbits = cl >> 16;
-            }
+            v[q] = x; nbv[q] = nbits; sum += nbits;
         }
         uint32_t total;
-        uint32_t ex = block_excl_scan(nbits, ws, total);
-        put_bits(out32, running + ex, v, nbits);
-        running += total;
+        const uint32_t ex = block_excl_scan(sum, ws, total);
+        const unsigned long long wbase = bitpos >> 5, end = bitpos + total;
+        const uint32_t n_words = (uint32_t)(((end + 31ull) >> 5) - wbase);
+        for (uint32_t i = threadIdx.x + 1u; i <= n_words; i += blockDim.x) sw[i] = 0u;   // word 0 carries the previous tile's tail
+        __syncthreads();
+        uint32_t off = (uint32_t)(bitpos & 31ull) + ex;
+#pragma unroll
+        for (uint32_t q = 0; q < kPackItems; q++) {
+            if (nbv[q]) {
+                const uint32_t wi = off >> 5, sh = off & 31u;
+                const unsigned long long lo = v[q] << sh;
+                const uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)(lo >> 32), x2 = sh ? (uint32_t)(v[q] >> (64u - sh)) : 0u;
+                if (x0) atomicOr(&sw[wi], x0);
+                if (x1) atomicOr(&sw[wi + 1], x1);
+                if (x2) atomicOr(&sw[wi + 2], x2);
+                off += nbv[q];
+            }
+        }
+        __syncthreads();
+        // completed words leave; 16 bytes at a time where the output address allows it
+        const uint32_t n_done = (uint32_t)((end >> 5) - wbase);
+        {
+            const uint32_t head0 = (uint32_t)((4ull - (wbase & 3ull)) & 3ull);
+            const uint32_t head = head0 < n_done ? head0 : n_done;
+            const uint32_t n_vec = (n_done - head) >> 2, tail = head + 4u * n_vec;
+            if (threadIdx.x < head) pack_store_word(out32, wbase + threadIdx.x, sw[threadIdx.x], bs, be);
+            if (threadIdx.x >= 32u && threadIdx.x - 32u < n_done - tail)
+                pack_store_word(out32, wbase + tail + (threadIdx.x - 32u), sw[tail + (threadIdx.x - 32u)], bs, be);
+            uint4* out4 = reinterpret_cast<uint4*>(out32 + wbase + head);
+            for (uint32_t vi = threadIdx.x; vi < n_vec; vi += blockDim.x) {
+                const uint32_t i0 = head + 4u * vi;
+                const unsigned long long g = wbase + i0;
+                if (g == (bs >> 5) && (bs & 31ull)) {          // the block's first word sits at a 16-byte boundary and is shared
+                    pack_store_word(out32, g, sw[i0], bs, be);
+                    out32[g + 1] = sw[i0 + 1]; out32[g + 2] = sw[i0 + 2]; out32[g + 3] = sw[i0 + 3];
+                } else {
+                    out4[vi] = make_uint4(sw[i0], sw[i0 + 1], sw[i0 + 2], sw[i0 + 3]);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sw[0] = (end & 31ull) ? sw[n_done] : 0u;
+        __syncthreads();
+        bitpos = end;
     }
     if (threadIdx.x == 0) {
-        uint32_t cl = ll_cl[kEob];
-        put_bits(out32, running, cl & 0xffffu, cl >> 16);
-        running += cl >> 16;
-        if (running != blk_bit[b + 1] + out_bit_base) meta->err = 4;
+        if (bitpos != be) meta->err = 4;                        // the scan and the packer must agree
+        else if (bitpos & 31ull) pack_store_word(out32, bitpos >> 5, sw[0], bs, be);
     }
 }
 
@@ -1611,15 +1678,14 @@ cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st) 
 
 cudaError_t launch_block_scan(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     k_block_scan<<<1, 256, 0, st>>>(b.meta, b.cost, b.blk_type, b.blk_bit, b.blk_in, j.sync_marker,
-                                    j.n_carry_tok ? j.carry_in_pos : j.begin, j.carry_bits_n);
+                                    j.n_carry_tok ? j.carry_in_pos : j.begin, j.carry_bits_n, reinterpret_cast<uint32_t*>(j.d_out),
+                                    (unsigned long long)j.hdr_bytes * 8ull, (unsigned long long)j.out_cap);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
 cudaError_t launch_pack(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     const uint32_t* tok = j.d_tokens_override ? j.d_tokens_override : b.tok;
-    k_zero_out<<<148 * 8, 256, 0, st>>>(b.meta, reinterpret_cast<uint4*>(j.d_out), (unsigned long long)j.out_cap, j.hdr_bytes);
-    DFL_LAUNCH_CHECK();
     k_pack<<<max_blocks_for(j.n - j.begin + j.n_carry_tok), kPackThreads, 0, st>>>(j.d_in, tok, b.meta, b.cost, b.tables, b.blk_type, b.blk_bit,
                                                                     b.blk_in, reinterpret_cast<uint32_t*>(j.d_out),
                                                                     (unsigned long long)j.hdr_bytes * 8ull, j.final_block,

@@ -162,3 +162,21 @@ def binary_like(size: int, seed: int = 0xB1A2) -> bytes:
         parts.append(blk)
         total += len(blk)
     return b"".join(parts)[:size]
+
+
+def random_bytes(size: int, seed: int = 7) -> bytes:
+    """Incompressible input: every block ends up stored (stored_block.rs:13-40)."""
+    return _random(np.random.default_rng(seed), size)
+
+
+def zero_bytes(size: int, seed: int = 0) -> bytes:
+    """One repeated byte: 258-byte matches at distance 1 end to end; speculative parses never resynchronise."""
+    return bytes(size)
+
+
+def issue44_like(size: int, seed: int = 0) -> bytes:
+    """tests/fixtures/issue_44.zlib inflated (25 MiB over three byte values, long runs) and repeated."""
+    import zlib
+    raw = zlib.decompress(open(os.path.join(_FIX, "issue_44.zlib"), "rb").read())
+    reps = -(-size // len(raw))
+    return (raw * reps)[:size]
