@@ -305,7 +305,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.off); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Lf); dev_free(b.Lq); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -349,6 +349,8 @@ struct Context {
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
+        if ((rc = dev_alloc(b.Lf, cap + 512))) return rc;
+        if (quarter && (rc = dev_alloc(b.Lq, cap + 512))) return rc;
         if ((rc = dev_alloc(b.segtok, parse_buffer_words(cap)))) return rc;
         if ((rc = dev_alloc(b.seg_e_pos, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_e_key, n_seg))) return rc;
@@ -507,7 +509,16 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     if (rc) return rc;
     Buffers& b = c.buf;
     CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
-    const bool need_lz = (d_tokens_override == nullptr);
+    const bool seq_lz = (d_tokens_override == nullptr) && use_seq_lz77(j.prm, j.begin, j.open_piece, j.init_key, j.n_carry_tok) &&
+                        j.parse_end == j.n;
+    if (seq_lz) {
+        if (!b.seq_tab) { int arc = dev_alloc(b.seq_tab, 3 * kWindow); if (arc) return arc; }
+        if (arrival)
+            for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
+        CK(launch_lz77_seq(j, b, st));
+        tm.mark("lz77_sequential");
+    }
+    const bool need_lz = (d_tokens_override == nullptr) && !seq_lz;
     const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
     if (need_match) {
         const uint32_t w_end = n_windows(j), w_sort0 = first_sort_window(j), w_match0 = first_match_window(j);
@@ -535,7 +546,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
             CK(launch_match(j, b, st, w_match0, w_end));
             tm.mark("match");
         }
-    } else if (arrival) {
+    } else if (arrival && !seq_lz) {
         for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
     }
     if (wrap == DFL_ZLIB && final_block && !stop_after_tokens) {

@@ -139,6 +139,7 @@ DFL_HD void ewalk_visit(EntryWalk& s, Entry me, Entry ce, uint32_t k, uint32_t m
 // of the position in its window's sorted list, bits 15..30 = visit index of the nearest candidate that shares
 // 8 bytes (every nearer one shares fewer, so a resolution starts there).
 constexpr uint32_t kRecLong = 0x80000000u;
+constexpr uint32_t kLenLong = 0xffu;     // length code (one byte per position beside the record): the record is long
 DFL_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 9); }
 DFL_HD uint32_t match_len(uint32_t m) { return m & 0x1ffu; }
 DFL_HD uint32_t match_dist(uint32_t m) { return ((m >> 9) & 0x7fffu) + 1u; }
@@ -153,6 +154,8 @@ DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
     if (len == kMinMatch && dist > kTooFar) return 0u;
     return pack_match(len, dist);
 }
+// Length code of a record: what the parser needs in order to decide (the distance only matters once a token is written).
+DFL_HD uint32_t rec_len_code(uint32_t rec) { return rec_is_long(rec) ? kLenLong : match_len(rec); }
 // Record of a finished entry walk.  `rank` = index of the target in its window's sorted list, `dist` = distance
 // of the best candidate.
 DFL_HD uint32_t ewalk_record(const EntryWalk& s, uint32_t rank, uint32_t dist, uint32_t maxl) {
@@ -223,87 +226,202 @@ DFL_HD uint32_t reverse_bits(uint32_t v, uint32_t nbits) {
 // State of the reference's parsers *between* loop iterations, in absolute positions.
 // (lz77.rs:162-173 ChunkState + the locals prev_length/prev_distance/ignore_next of
 // process_chunk_lazy, lz77.rs:305-486.)  `pos` is the position the next iteration examines.
+// The pending match is (prev_len, reference to its distance): the parser's decisions only depend on lengths,
+// so a caller may hand in matches whose distance it has not looked up yet (kRefFull / kRefQuarter: prev_ref is
+// the position whose full- / quarter-budget match record holds it) and resolve them when the token is written.
+enum RefKind : uint32_t { kRefDist = 0, kRefFull = 1, kRefQuarter = 2 };
 struct ParseState {
     uint32_t pos;
     uint32_t prev_len;   // pending match found at pos-1 (0 = none)
-    uint32_t prev_dist;
+    uint32_t prev_ref;   // its distance (kRefDist) or the position of its record
+    uint32_t prev_kind;  // RefKind
     uint32_t add;        // byte pos-1 is still to be emitted as a literal
     uint32_t ign;        // ignore_next
 };
 DFL_HD ParseState parse_state_init(uint32_t pos) {
-    ParseState s; s.pos = pos; s.prev_len = 0; s.prev_dist = 0; s.add = 0; s.ign = 0; return s;
+    ParseState s; s.pos = pos; s.prev_len = 0; s.prev_ref = 0; s.prev_kind = kRefDist; s.add = 0; s.ign = 0; return s;
 }
-DFL_HD uint32_t parse_state_key(const ParseState& s) {
-    return s.prev_len | (s.prev_dist << 9) | (s.add << 25) | (s.ign << 26);   // prev_dist <= 32768: 16 bits
+// Hand-off key of a state whose pending distance is known (prev_dist <= 32768: 16 bits).
+DFL_HD uint32_t parse_state_key(const ParseState& s, uint32_t prev_dist) {
+    return s.prev_len | (prev_dist << 9) | (s.add << 25) | (s.ign << 26);
+}
+DFL_HD ParseState parse_state_from_key(uint32_t pos, uint32_t key) {
+    ParseState s;
+    s.pos = pos; s.prev_len = key & 0x1ffu; s.prev_ref = (key >> 9) & 0xffffu; s.prev_kind = kRefDist;
+    s.add = (key >> 25) & 1u; s.ign = (key >> 26) & 1u;
+    return s;
 }
 
-// One iteration of process_chunk_lazy (lz77.rs:340-480) over precomputed per-position matches.
-// mf/mq: finalize_match() records of this position for the full / quarter chain budget
-// (matching.rs:87-166 returns the longest among the first `checks` chain candidates, nearest on
-// ties, and only if it is longer than prev_length).  Emits 0..2 tokens through out[]; returns count.
-DFL_HD int lazy_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t mf, uint32_t mq,
-                     uint32_t lazy, uint32_t out[2]) {
+// One iteration of process_chunk_lazy (lz77.rs:340-480).  (m_len, m_ref, m_kind): the longest match among the
+// candidates the reference would visit at this position (matching.rs:87-166; 0 = none), whatever the floor --
+// the step applies "only if longer than prev_length" itself (matching.rs:161-165).  Only looked at when the
+// reference searches (p + 2 < n and !ign).  Tokens go to `out`: out.literal(position), out.match(len, ref, kind).
+template <class Sink>
+DFL_HD void lazy_step(ParseState& s, uint32_t n, uint32_t m_len, uint32_t m_ref, uint32_t m_kind, uint32_t lazy, Sink& out) {
     const uint32_t p = s.pos;
-    int ne = 0;
     if (p + 2u < n) {                                   // hash_it.next() is Some
-        uint32_t cur_len = 0, cur_dist = 0;
+        uint32_t cur_len = 0;
         if (!s.ign) {
-            uint32_t m = (s.prev_len >= 32u) ? mq : mf; // lz77.rs:351-355
-            uint32_t floor_len = s.prev_len > 1u ? s.prev_len : 1u;
-            if (match_len(m) > floor_len) { cur_len = match_len(m); cur_dist = match_dist(m); }
+            const uint32_t floor_len = s.prev_len > 1u ? s.prev_len : 1u;
+            if (m_len > floor_len) cur_len = m_len;
             if (cur_len >= lazy) s.ign = 1;             // lz77.rs:374-377
         } else {
             s.ign = 0;                                  // lz77.rs:380-386
         }
         if (s.prev_len >= cur_len && s.prev_len >= kMinMatch) {   // lz77.rs:388-426
-            out[ne++] = tok_match(s.prev_len, s.prev_dist);
+            out.match(s.prev_len, s.prev_ref, s.prev_kind);
             s.pos = p - 1u + s.prev_len;
-            s.add = 0; s.prev_len = 0; s.prev_dist = 0; s.ign = 0;
+            s.add = 0; s.prev_len = 0; s.prev_ref = 0; s.prev_kind = kRefDist; s.ign = 0;
         } else {
-            if (s.add) out[ne++] = tok_literal(data[p - 1u]);     // lz77.rs:427-431
+            if (s.add) out.literal(p - 1u);                       // lz77.rs:427-431
             else s.add = 1;                                        // lz77.rs:432-434
-            s.prev_len = cur_len; s.prev_dist = cur_dist;
+            s.prev_len = cur_len; s.prev_ref = m_ref; s.prev_kind = m_kind;
             s.pos = p + 1u;
         }
     } else {                                            // last two bytes, lz77.rs:440-482
         if (s.prev_len >= kMinMatch) {
-            out[ne++] = tok_match(s.prev_len, s.prev_dist);
-            s.pos = n; s.add = 0; s.prev_len = 0; s.prev_dist = 0;
+            out.match(s.prev_len, s.prev_ref, s.prev_kind);
+            s.pos = n; s.add = 0; s.prev_len = 0; s.prev_ref = 0; s.prev_kind = kRefDist;
         } else {
-            if (s.add) { s.add = 0; out[ne++] = tok_literal(data[p - 1u]); }
-            out[ne++] = tok_literal(data[p]);
+            if (s.add) { s.add = 0; out.literal(p - 1u); }
+            out.literal(p);
             s.pos = p + 1u;
         }
     }
-    return ne;
 }
 
 // One iteration of process_chunk_greedy (lz77.rs:502-544).
-DFL_HD int greedy_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t mf, uint32_t out[2]) {
+template <class Sink>
+DFL_HD void greedy_step(ParseState& s, uint32_t n, uint32_t m_len, uint32_t m_ref, uint32_t m_kind, Sink& out) {
     const uint32_t p = s.pos;
-    if (p + 2u < n && match_len(mf) >= kMinMatch) {
-        out[0] = tok_match(match_len(mf), match_dist(mf));
-        s.pos = p + match_len(mf);
+    if (p + 2u < n && m_len >= kMinMatch) {
+        out.match(m_len, m_ref, m_kind);
+        s.pos = p + m_len;
     } else {
-        out[0] = tok_literal(data[p]);
+        out.literal(p);
         s.pos = p + 1u;
     }
-    return 1;
 }
 
 // One iteration of process_chunk_greedy_rle (rle.rs:23-71): distance-1 runs only.
-DFL_HD int rle_step(ParseState& s, uint32_t n, const uint8_t* data, uint32_t out[2]) {
+template <class Sink>
+DFL_HD void rle_step(ParseState& s, uint32_t n, const uint8_t* data, Sink& out) {
     const uint32_t p = s.pos;
-    if (p == 0u) { out[0] = tok_literal(data[0]); s.pos = 1; return 1; }
+    if (p == 0u) { out.literal(0u); s.pos = 1; return; }
     const uint8_t prev = data[p - 1u];
     uint32_t len = 0;
     if (data[p] == prev) {
         uint32_t maxl = n - p < kMaxMatch ? n - p : kMaxMatch;
         while (len < maxl && data[p + len] == prev) len++;
     }
-    if (len >= kMinMatch) { out[0] = tok_match(len, 1u); s.pos = p + len; }
-    else { out[0] = tok_literal(data[p]); s.pos = p + 1u; }
-    return 1;
+    if (len >= kMinMatch) { out.match(len, 1u, kRefDist); s.pos = p + len; }
+    else { out.literal(p); s.pos = p + 1u; }
+}
+
+// ---------------------------------------------------------------- the reference's loop, sequentially
+// process_chunk_lazy (lz77.rs:305-486) over the reference's own head/prev chains (chained_hash_table.rs), for
+// MatchingType::Lazy with lazy_if_less_than < 3 -- the option values for which two things become observable
+// that the parallel pipeline leaves out (kernel k_lz77_seq has the full story): length-2 results from spurious
+// chain entries, and ignore_next being re-derived at the start of every process_chunk_lazy call.
+// Chains in absolute positions: head[hash] = last inserted position (kSeqNone = still its own index);
+// prev_val/prev_org[pos & 0x7fff] = what head[hash] held when pos was inserted: an absolute position (prev_org ==
+// kSeqNone; stale once below the buffer origin of the window being processed, where `slide` would have reset it to
+// the slot's own index, chained_hash_table.rs:197-219), or the hash itself (prev_org = buffer origin at insertion:
+// head still held its own index; valid as buffer-relative position until the next slide).
+// The caller initialises all three tables (32768 entries each) to kSeqNone.  Returns the number of tokens.
+constexpr uint32_t kSeqNone = 0xffffffffu;
+DFL_HD uint32_t seq_origin(uint32_t pos) {          // buffer origin while pos's window is processed: windows 0 and 1
+    const uint32_t w = pos >> 15;                   // share the unslid buffer (lz77.rs:650-667,745-756)
+    return w <= 1u ? 0u : (w - 1u) << 15;
+}
+DFL_HD void seq_insert_upto(const uint8_t* in, uint32_t n, uint32_t& next_insert, uint32_t upto, uint32_t* head,
+                            uint32_t* prev_val, uint32_t* prev_org) {
+    for (; next_insert < upto; next_insert++) {     // chained_hash_table.rs:148-158, every position once, in order
+        const uint32_t q = next_insert;
+        if (q + 2u >= n) continue;                  // hash_it.next() is None: not inserted
+        const uint32_t h = hash3(in[q], in[q + 1], in[q + 2]);
+        const uint32_t hv = head[h];
+        const uint32_t qorg = seq_origin(q);
+        if (hv == kSeqNone || hv < qorg) { prev_val[q & kWindowMask] = h; prev_org[q & kWindowMask] = qorg; }
+        else { prev_val[q & kWindowMask] = hv; prev_org[q & kWindowMask] = kSeqNone; }
+        head[h] = q;
+    }
+}
+DFL_HD unsigned long long lz77_sequential(const uint8_t* in, uint32_t n, const Params& prm, uint32_t* head, uint32_t* prev_val,
+                                          uint32_t* prev_org, uint32_t* tok) {
+    const uint32_t lazy = prm.lazy, checks = prm.checks;
+    unsigned long long nt = 0;
+    uint32_t prev_len = 0, prev_dist = 0, add = 0, ign = 0;
+    uint32_t cur_w = kSeqNone, org = 0, next_insert = 0;
+    bool chunk_start = true;
+    uint32_t p = 0;
+    while (p < n) {
+        const uint32_t w = p >> 15;
+        if (w != cur_w) { cur_w = w; org = seq_origin(p); chunk_start = true; }       // a new process_chunk_lazy call
+        if (chunk_start) { ign = prev_len >= lazy ? 1u : 0u; chunk_start = false; }   // lz77.rs:331
+        if (p + 2u < n) {
+            seq_insert_upto(in, n, next_insert, p + 1u, head, prev_val, prev_org);
+            uint32_t cur_len = 0, cur_dist = 0;
+            if (!ign) {
+                const uint32_t budget = prev_len >= 32u ? checks >> 2 : checks;       // lz77.rs:351-355
+                if (!(prev_len >= kMaxMatch || p + prev_len >= n)) {                  // longest_match, matching.rs:87-166
+                    const uint32_t pos_rel = p - org;
+                    const uint32_t limit = pos_rel > kWindow ? pos_rel - kWindow : 0u;
+                    const uint32_t floor_len = prev_len > 1u ? prev_len : 1u;
+                    const uint32_t max_len = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                    uint32_t best = floor_len, best_dist = 0, cur = pos_rel;
+                    for (uint32_t c = 0; c < budget; c++) {
+                        const uint32_t prev_head = cur;
+                        const uint32_t slot = cur & kWindowMask;
+                        const uint32_t v = prev_val[slot], vo = prev_org[slot];
+                        if (vo == kSeqNone) {                         // an absolute position
+                            if (v == kSeqNone || v < org) break;      // its own index by now: the chain ends (matching.rs:127-132)
+                            cur = v - org;
+                        } else {                                      // the hash itself, until the next slide
+                            if (vo != org) break;
+                            cur = v;
+                        }
+                        if (cur >= prev_head || cur < limit) break;
+                        const uint32_t ca = org + cur;
+                        if (in[p + best - 1u] == in[ca + best - 1u] && in[p + best] == in[ca + best]) {
+                            uint32_t l = 0;
+                            while (l < max_len && in[p + l] == in[ca + l]) l++;
+                            if (l > best) { best = l; best_dist = p - ca; if (l == max_len) break; }
+                        }
+                    }
+                    if (best > floor_len) { cur_len = best; cur_dist = best_dist; }
+                }
+                if (cur_len == kMinMatch && cur_dist > kTooFar) cur_len = 0;          // lz77.rs:274-278
+                if (cur_len >= lazy) ign = 1;                                         // lz77.rs:374-377
+            } else {
+                ign = 0;
+            }
+            if (prev_len >= cur_len && prev_len >= kMinMatch) {
+                tok[nt++] = tok_match(prev_len, prev_dist);
+                const uint32_t np = p - 1u + prev_len;
+                seq_insert_upto(in, n, next_insert, np < n ? np : n, head, prev_val, prev_org);
+                add = 0; prev_len = 0; prev_dist = 0;
+                if (nt % kBlockTokens == 0ull) chunk_start = true; else ign = 0;      // BufferFull returns before `ignore_next = false`
+                p = np;
+                continue;
+            }
+            if (add) {
+                tok[nt++] = tok_literal(in[p - 1u]);
+                if (nt % kBlockTokens == 0ull) chunk_start = true;                    // BufferFull: the next call re-derives ignore_next
+            } else add = 1;
+            prev_len = cur_len; prev_dist = cur_dist;
+            p++;
+        } else {                                                                     // last two bytes, lz77.rs:440-482
+            if (prev_len >= kMinMatch) {
+                tok[nt++] = tok_match(prev_len, prev_dist);
+                break;
+            }
+            if (add) { add = 0; tok[nt++] = tok_literal(in[p - 1u]); }
+            tok[nt++] = tok_literal(in[p]);
+            p++;
+        }
+    }
+    return nt;
 }
 
 // ---------------------------------------------------------------- Huffman code construction

@@ -43,7 +43,7 @@ inline size_t parse_buffer_words(size_t cap) {
         }
     return best;
 }
-constexpr uint32_t kRepairRounds = 3;    // parallel repair rounds before the sequential fallback
+constexpr uint32_t kRepairRounds = 6;    // parallel repair rounds before the sequential fallback (the second predicts chain phases)
 
 // Device-resident bookkeeping of one encode call (one instance per context).
 struct DevMeta {
@@ -92,6 +92,8 @@ struct Buffers {   // device scratch of one context, grown on demand
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
+    uint8_t* Lf = nullptr;          // per-position length code of Mf (dfl_core.h rec_len_code): what the parser reads at every step
+    uint8_t* Lq = nullptr;          // ... of Mq
     uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * parse_tok_cap
     uint32_t* seg_e_pos = nullptr;  // hand-off records (SoA), n_pseg each
     uint32_t* seg_e_key = nullptr;
@@ -104,6 +106,7 @@ struct Buffers {   // device scratch of one context, grown on demand
     uint8_t* seg_bad = nullptr;
     uint32_t* seg_cnt = nullptr;    // valid tokens per segment
     unsigned long long* seg_off = nullptr;   // exclusive prefix of seg_cnt
+    uint32_t* seq_tab = nullptr;    // head / prev chains of the sequential lazy < 3 path (3 x 32768 words), on first use
     uint32_t* tok = nullptr;        // compacted token stream
     uint32_t* hist = nullptr;       // per block 320 counters (286 ll + 30 dist + pad)
     BlockCost* cost = nullptr;
@@ -116,6 +119,12 @@ struct Buffers {   // device scratch of one context, grown on demand
     size_t cap_n = 0;               // input size the buffers were sized for
     bool cap_quarter = false;
 };
+
+// MatchingType::Lazy with lazy_if_less_than < 3 on a one-shot stream takes the sequential kernel (k_lz77_seq):
+// only there can the reference's length-2 results and its per-call ignore_next be observed.
+inline bool use_seq_lz77(const Params& p, uint32_t begin, int open_piece, uint32_t init_key, uint32_t n_carry_tok) {
+    return p.mode == kLazy && p.lazy < 3u && begin == 0 && !open_piece && init_key == 0 && n_carry_tok == 0;
+}
 
 struct EncodeJob {
     const uint8_t* d_in;     // device input (history + payload)
@@ -151,6 +160,7 @@ uint32_t first_sort_window(const EncodeJob& j);
 cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
 cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
 cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st);
+cudaError_t launch_lz77_seq(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_block_stats(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_block_codes(const EncodeJob& j, Buffers& b, cudaStream_t st);

@@ -392,7 +392,7 @@ template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
 k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
         const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
-        uint32_t* __restrict__ Mq) {
+        uint32_t* __restrict__ Mq, uint8_t* __restrict__ Lf, uint8_t* __restrict__ Lq) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
     const uint32_t w = w_first + blockIdx.x;
@@ -492,10 +492,14 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
         if (act) {
             // distance of visit k: own window pl - pos, previous window pl + 32768 - pos
             const uint32_t d = (wk.best_k < n_own ? pl : pl + kWindow) - wk.best_pos;
-            Mf[p] = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            const uint32_t rec = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            Mf[p] = rec;
+            Lf[p] = (uint8_t)rec_len_code(rec);
             if (NEEDQ) {
                 const uint32_t dq = (wk.q_k < n_own ? pl : pl + kWindow) - wk.q_pos;
-                Mq[p] = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+                const uint32_t rq = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+                Mq[p] = rq;
+                Lq[p] = (uint8_t)rec_len_code(rq);
             }
         }
     }
@@ -512,15 +516,12 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
 //   (matching.rs:148-157).  Only positions the reference's parser searches are ever resolved: everything
 //   inside an emitted match is skipped (lz77.rs:398-405), which is 70-85 % of all positions on text.
 // =====================================================================================
-__device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key) {
-    ParseState s;
-    s.pos = pos; s.prev_len = key & 0x1ffu; s.prev_dist = (key >> 9) & 0xffffu; s.add = (key >> 25) & 1u; s.ign = (key >> 26) & 1u;
-    return s;
-}
+__device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key) { return parse_state_from_key(pos, key); }
 
 struct ParseArgs {
     const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
     const uint32_t* Mf; const uint32_t* Mq;
+    const uint8_t* Lf; const uint8_t* Lq;  // one byte per position: 0 = no match, 3..8 = length of the final record, kLenLong
     const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window (long records refer to them)
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
@@ -556,8 +557,10 @@ struct Resolve {
     uint32_t me_lo, me_hi;
 };
 
-__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t budget) {
+__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t budget, bool quarter) {
     const uint32_t p = r.p, w = p >> 15;
+    const uint32_t rec = quarter ? A.Mq[p] : A.Mf[p];   // a long record: rank of p in its window's list, first visit to look at
+    r.rank = rec_rank(rec); r.k0 = rec_k8(rec);
     const uint2 me = __ldg(A.K + (size_t)w * kWindow + r.rank);
     r.me_lo = me.x; r.me_hi = me.y;
     const uint32_t h = hash3(A.in[p], A.in[p + 1], A.in[p + 2]);
@@ -591,10 +594,32 @@ __device__ __forceinline__ const uint2* resolve_entry(const ParseArgs& A, uint32
 constexpr uint32_t kParseThreads = 128;
 constexpr uint32_t kParseWarps = kParseThreads / 32;
 constexpr uint32_t kCandCap = 256;       // candidates a warp collects before it compares them
+constexpr uint32_t kLcBytes = 256;       // length codes a lane keeps in shared memory: the 128-byte line it is in and the next
+constexpr uint32_t kLcWords = kLcBytes / 4;
 struct ParseShared {
     uint32_t cand_q[kCandCap];           // absolute position of a candidate that shares the target's 8 entry bytes
     uint32_t cand_meta[kCandCap];        // owner lane | visit index << 5
     uint32_t res_key[32];                // per owner lane: best length << 16 | (0xffff - visit index)
+    uint32_t lc[32 * (kLcWords + 1)];    // per lane kLcWords words of length codes (+1: rows fall on different banks)
+};
+
+// Tokens as the parser writes them into its segment buffer.  What the parser does not need in order to decide --
+// the byte of a literal, the distance of a match whose record is final -- is not loaded by it (a dependent load
+// per step is what bounds a sequential parser on a GPU): such tokens name a position instead and k_compact,
+// fully parallel, fills them in.  Positions are relative to (segment start - origin_back).
+constexpr uint32_t kTokLitAt = 0x80000000u;       // | relative position
+constexpr uint32_t kTokMatchAt = 0x40000000u;     // | quarter-budget record << 29 | length << 14 | relative position
+constexpr uint32_t kTokQuarter = 0x20000000u;
+constexpr uint32_t kTokRelMask = 0x3fffu;
+__host__ __device__ inline uint32_t parse_origin_back(uint32_t warm) { return warm + 300u; }
+struct DeferSink {
+    uint32_t* tk; uint32_t nt, cap; long long origin;
+    __device__ __forceinline__ void put(uint32_t t) { if (nt < cap) tk[nt] = t; nt++; }
+    __device__ __forceinline__ void literal(uint32_t pos) { put(kTokLitAt | (uint32_t)((long long)pos - origin)); }
+    __device__ __forceinline__ void match(uint32_t len, uint32_t ref, uint32_t kind) {
+        if (kind == kRefDist) put(tok_match(len, ref));
+        else put(kTokMatchAt | (kind == kRefQuarter ? kTokQuarter : 0u) | (len << 14) | (uint32_t)((long long)ref - origin));
+    }
 };
 
 // Compares the collected candidates of all owners, one candidate per lane and round: the byte that would extend
@@ -662,8 +687,9 @@ __device__ __forceinline__ void resolve_load4(const ParseArgs& A, const Owner& o
 // Every lane of the calling warp enters (work == false: the lane only helps with resolutions).  A lane with work
 // runs the reference's token selection from `st` until the first iteration position >= b.
 __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
-    uint32_t* tk = A.segtok + (size_t)s * A.tok_cap;
-    uint32_t nt = 0;
+    DeferSink out;
+    out.tk = A.segtok + (size_t)s * A.tok_cap; out.nt = 0; out.cap = A.tok_cap;
+    out.origin = (long long)A.begin + (long long)s * A.seg - (long long)parse_origin_back(A.warm);
     bool have_e = false;
     uint32_t epos = 0, ekey = 0, etok = 0;
     const uint32_t n = A.n;
@@ -671,63 +697,85 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
     const bool has_m = (mode != kRle) && (A.prm.checks > 0);
     const uint32_t lane = lane_id();
     const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
-    bool running = work, parked = false, have_m = false;
+    const uint32_t* L32 = reinterpret_cast<const uint32_t*>(A.Lf);
+    uint32_t* lc = S.lc + lane * (kLcWords + 1u);
+    uint32_t cb = 0xffffff00u;                       // position of the first cached length code (a multiple of 128); nothing yet
+    bool running = work, parked = false, have_m = false, rq_quarter = false;
     uint32_t m_ready = 0, rq_budget = 0;
     Resolve rq;
     rq.p = rq.rank = rq.k0 = rq.start = rq.maxl = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = 0;
+    // the hand-off key carries the pending match's distance: looked up here, once per segment boundary
+    auto state_key = [&](const ParseState& x) -> uint32_t {
+        uint32_t d = 0;
+        if (x.prev_len) d = x.prev_kind == kRefDist ? x.prev_ref : match_dist((x.prev_kind == kRefQuarter ? A.Mq : A.Mf)[x.prev_ref]);
+        return parse_state_key(x, d);
+    };
     for (;;) {
         // ---- parse: every running lane takes one step per iteration
         for (;;) {
+            bool miss = false;
             if (running && !parked) {
                 bool stop_here = st.pos >= n;
                 if (!stop_here) {
-                    if (!have_e && st.pos >= a) { epos = st.pos; ekey = parse_state_key(st); etok = nt; have_e = true; }
+                    if (!have_e && st.pos >= a) { epos = st.pos; ekey = state_key(st); etok = out.nt; have_e = true; }
                     stop_here = st.pos >= b;
                 }
                 if (stop_here) {
-                    if (!have_e) { epos = st.pos; ekey = parse_state_key(st); etok = nt; }
+                    if (!have_e) { epos = st.pos; ekey = state_key(st); etok = out.nt; }
                     A.e_pos[s] = epos; A.e_key[s] = ekey; A.e_tok[s] = etok;
-                    A.x_pos[s] = st.pos; A.x_key[s] = parse_state_key(st); A.x_tok[s] = nt;
+                    A.x_pos[s] = st.pos; A.x_key[s] = state_key(st); A.x_tok[s] = out.nt;
                     running = false;
                 } else {
                     const uint32_t p = st.pos;
-                    uint32_t m = 0;
-                    if (have_m) { m = m_ready; have_m = false; }
-                    else if (has_m && p + 2u < n) {
-                        uint32_t floor = 0;
-                        rq_budget = A.prm.checks;
-                        if (mode == kLazy) {
-                            if (!st.ign) {                                   // the only case in which the reference searches (lz77.rs:347)
-                                const bool quarter = st.prev_len >= 32u;     // lz77.rs:351-355
-                                if (!quarter || A.prm.need_quarter) {
-                                    m = quarter ? A.Mq[p] : A.Mf[p];
-                                    floor = st.prev_len;
-                                    if (quarter) rq_budget = A.prm.checks_quarter;
-                                }
+                    uint32_t m_len = 0, m_ref = 0, m_kind = kRefDist;
+                    if (have_m) {                                            // the answer to this lane's request
+                        m_len = match_len(m_ready); m_ref = m_len ? match_dist(m_ready) : 0u; have_m = false;
+                    } else if (has_m && p + 2u < n && (mode != kLazy || !st.ign)) {   // the reference searches here (lz77.rs:347,505)
+                        const bool quarter = mode == kLazy && st.prev_len >= 32u;        // lz77.rs:351-355
+                        if (!quarter || A.prm.need_quarter) {
+                            uint32_t code;
+                            if (quarter) code = A.Lq[p];
+                            else if (p - cb < kLcBytes) code = (lc[(p - cb) >> 2] >> (8u * (p & 3u))) & 0xffu;
+                            else { code = 0; miss = true; }
+                            if (code == kLenLong) {
+                                rq.p = p;
+                                const uint32_t floor = mode == kLazy ? st.prev_len : 0u;
+                                rq.start = floor > kEntryBytes - 1u ? floor : kEntryBytes - 1u;
+                                rq.maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                                rq_budget = quarter ? A.prm.checks_quarter : A.prm.checks;
+                                rq_quarter = quarter;
+                                parked = true;
+                            } else {
+                                m_len = code; m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
                             }
-                        } else {
-                            m = A.Mf[p];
-                        }
-                        if (rec_is_long(m)) {
-                            rq.p = p; rq.rank = rec_rank(m); rq.k0 = rec_k8(m);
-                            rq.start = floor > kEntryBytes - 1u ? floor : kEntryBytes - 1u;
-                            rq.maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
-                            parked = true;
                         }
                     }
-                    if (!parked) {
-                        uint32_t out[2];
-                        int ne;
-                        if (mode == kLazy) ne = lazy_step(st, n, A.in, m, m, A.prm.lazy, out);
-                        else if (mode == kGreedy) ne = greedy_step(st, n, A.in, m, out);
-                        else ne = rle_step(st, n, A.in, out);   // rle.rs runs over the buffer from its first byte
-                        if (nt + (uint32_t)ne <= A.tok_cap) {
-                            if (ne > 0) tk[nt] = out[0];
-                            if (ne > 1) tk[nt + 1] = out[1];
-                        }
-                        nt += (uint32_t)ne;
+                    if (!parked && !miss) {
+                        if (mode == kLazy) lazy_step(st, n, m_len, m_ref, m_kind, A.prm.lazy, out);
+                        else if (mode == kGreedy) greedy_step(st, n, m_len, m_ref, m_kind, out);
+                        else rle_step(st, n, A.in, out);       // rle.rs runs over the buffer from its first byte
                     }
                 }
+            }
+            // length codes: a lane that ran out of its cached 256 bytes gets the line it is in and the next one; lanes
+            // that have left their first line are refreshed in the same round, so that round trips are shared
+            uint32_t want = __ballot_sync(0xffffffffu, miss);
+            if (want) {
+                want |= __ballot_sync(0xffffffffu, running && !parked && has_m && st.pos - cb >= 128u);
+                const uint32_t mine = st.pos & ~127u;
+                for (uint32_t left = want; left;) {
+                    const int j = __ffs((int)left) - 1;
+                    left &= left - 1u;
+                    const uint32_t base = __shfl_sync(0xffffffffu, mine, j);
+                    uint32_t* row = S.lc + (uint32_t)j * (kLcWords + 1u);
+#pragma unroll
+                    for (uint32_t t = 0; t < kLcWords / 32u; t++) {
+                        const uint32_t wi = t * 32u + lane;
+                        row[wi] = (base + 4u * wi < n) ? __ldg(L32 + (base >> 2) + wi) : 0u;
+                    }
+                }
+                if ((want >> lane) & 1u) cb = mine;
+                __syncwarp();
             }
             const uint32_t going = __ballot_sync(0xffffffffu, running && !parked);
             if (going == 0u) break;
@@ -739,7 +787,7 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
             if (!__any_sync(0xffffffffu, running)) break;
             continue;
         }
-        if (parked) resolve_prepare(A, rq, rq_budget);       // every parked lane at once: their loads overlap
+        if (parked) resolve_prepare(A, rq, rq_budget, rq_quarter);   // every parked lane at once: their loads overlap
         S.res_key[lane] = 0u;
         __syncwarp();
         // scan: per owner, every candidate from visit k0 on whose 8 entry bytes equal the target's goes on the list;
@@ -891,6 +939,77 @@ __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* m
 
 __global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; }
 
+// Repair start states for chains of bad segments.  A speculative parse resynchronises with the true one at the
+// end of a match -- except inside a chain of maximum-length matches (runs of one byte, short periods): every
+// match is cut at 258 bytes (huffman_table.rs:21), so where a match ends depends on where the chain began, and
+// the hand-off check fails for every segment of the run.  But then the true parser is in a blank state every 258
+// bytes, so the entry of *every* segment of the chain follows from the exit of the last good segment in front of
+// it: the first blank position at or after the segment start with the same phase.  This kernel rewrites the
+// repair start of every bad segment whose predecessor is bad too; the next verify checks the prediction like
+// any other hand-off (a wrong guess stays bad and is repaired the ordinary way).  One CTA.
+__global__ void __launch_bounds__(1024) k_chain_predict(ParseArgs A, const uint8_t* bad, uint32_t* start_pos, uint32_t* start_key) {
+    __shared__ int carry[1024];
+    const uint32_t per = (A.n_seg + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per < A.n_seg ? threadIdx.x * per : A.n_seg;
+    const uint32_t hi = lo + per < A.n_seg ? lo + per : A.n_seg;
+    int last = -1;
+    for (uint32_t i = lo; i < hi; i++) if (!bad[i]) last = (int)i;
+    carry[threadIdx.x] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = -1;
+        for (uint32_t t = 0; t < blockDim.x; t++) { const int v = carry[t]; carry[t] = run; if (v >= 0) run = v; }
+    }
+    __syncthreads();
+    int g = carry[threadIdx.x];                      // last good segment in front of this thread's range
+    for (uint32_t i = lo; i < hi; i++) {
+        if (!bad[i]) { g = (int)i; continue; }
+        if (i == 0 || !bad[i - 1] || g < 0) continue;   // the head of a chain starts from its good predecessor's exit
+        if (A.x_key[g] != 0u) continue;              // only a blank state repeats with the stride of the length cap
+        const uint32_t xg = A.x_pos[g], a = A.begin + i * A.seg;
+        const uint32_t steps = a > xg ? (a - xg + kMaxMatch - 1u) / kMaxMatch : 0u;
+        start_pos[i] = xg + steps * kMaxMatch;
+        start_key[i] = 0u;
+    }
+}
+
+// =====================================================================================
+// k_lz77_seq: MatchingType::Lazy with lazy_if_less_than < 3 (compression_options.rs:93 documents 0 as "never lazy
+// match"; 1 and 2 are legal too).  For these values the reference's output depends on things the parallel
+// pipeline deliberately leaves out because no other option set can observe them:
+//   * longest_match may return length 2 (matching.rs:161-165) -- only through a *spurious* candidate, a chain
+//     entry that still holds its initial / slid-out self index (chained_hash_table.rs:34-51,197-219): two
+//     positions with equal 3-byte hash and two equal bytes have the third byte equal as well.  A length-2 result
+//     is never emitted, but it satisfies `match_len >= lazy_if_less_than` (lz77.rs:374-377) and becomes the floor
+//     of the next search;
+//   * ignore_next is re-derived as prev_length >= lazy_if_less_than at the start of every process_chunk_lazy call
+//     (lz77.rs:331), i.e. at every 32 KiB window and after every full token buffer; with 0 that is always true.
+// So this kernel is the reference's own loop, one thread, with the head/prev chains of chained_hash_table.rs
+// kept in global memory in absolute positions.  A chain value is either an absolute position (stale once it
+// lies below the buffer origin of the window being processed: `slide` would have turned it into the slot's own
+// index) or "the hash itself" -- what `prev[pos] = head[hash]` copies while head[hash] still holds its own
+// index -- valid as buffer-relative position `hash` until the next slide.  Slow by construction (about the speed
+// of one CPU core); it exists so that every legal CompressionOptions value gives the reference's bytes.
+// One-shot streams only (begin == 0, closed piece).
+// =====================================================================================
+struct SeqTables { uint32_t* head; uint32_t* prev_val; uint32_t* prev_org; };   // 32768 entries each
+
+__global__ void __launch_bounds__(32) k_lz77_seq_init(SeqTables t) {
+    for (uint32_t i = threadIdx.x + blockIdx.x * blockDim.x; i < kWindow; i += blockDim.x * gridDim.x) {
+        t.head[i] = kSeqNone; t.prev_val[i] = kSeqNone; t.prev_org[i] = kSeqNone;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_lz77_seq(const uint8_t* __restrict__ in, uint32_t n, Params prm, SeqTables t,
+                                                uint32_t* __restrict__ tok, DevMeta* meta) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long nt = lz77_sequential(in, n, prm, t.head, t.prev_val, t.prev_org, tok);   // dfl_core.h
+    meta->n_tokens = nt;
+    meta->n_blocks = (uint32_t)(nt / kBlockTokens) + 1u;
+    meta->end_pos = n;
+    meta->end_key = 0;
+}
+
 // =====================================================================================
 // token layout: exclusive scan of per-segment token counts (single CTA), then compaction
 // =====================================================================================
@@ -923,16 +1042,27 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_
     for (uint32_t i = lo; i < hi; i++) { seg_off[i] = run; run += seg_cnt[i]; }
 }
 
-__global__ void __launch_bounds__(128) k_compact(const uint32_t* __restrict__ segtok, const uint32_t* __restrict__ e_tok,
-                                                 const uint32_t* __restrict__ seg_cnt,
+// Copies every segment's tokens to their place in the stream and fills in what the parser left open: the byte of a
+// literal (kTokLitAt) and the distance of a match whose record is final (kTokMatchAt).
+__global__ void __launch_bounds__(128) k_compact(ParseArgs A, const uint32_t* __restrict__ seg_cnt,
                                                  const unsigned long long* __restrict__ seg_off, uint32_t* __restrict__ tok,
-                                                 DevMeta* meta, uint32_t tok_cap) {
-    uint32_t s = blockIdx.x;
-    uint32_t c = seg_cnt[s];
-    if (e_tok[s] + c > tok_cap) { if (threadIdx.x == 0) meta->err = 1; return; }
-    const uint32_t* src = segtok + (size_t)s * tok_cap + e_tok[s];
+                                                 DevMeta* meta) {
+    const uint32_t s = blockIdx.x;
+    const uint32_t c = seg_cnt[s], e0 = A.e_tok[s];
+    if (e0 + c > A.tok_cap) { if (threadIdx.x == 0) meta->err = 1; return; }
+    const uint32_t* src = A.segtok + (size_t)s * A.tok_cap + e0;
     uint32_t* dst = tok + seg_off[s];
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+    const long long origin = (long long)A.begin + (long long)s * A.seg - (long long)parse_origin_back(A.warm);
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        uint32_t t = src[i];
+        if (t & kTokLitAt) t = tok_literal(A.in[origin + (long long)(t & kTokRelMask)]);
+        else if (t & kTokMatchAt) {
+            const long long q = origin + (long long)(t & kTokRelMask);
+            const uint32_t rec = (t & kTokQuarter) ? A.Mq[q] : A.Mf[q];
+            t = tok_match((t >> 14) & 0x1ffu, match_dist(rec));
+        }
+        dst[i] = t;
+    }
 }
 
 __global__ void k_set_tokens(DevMeta* meta, unsigned long long n_tokens) {
@@ -1558,7 +1688,7 @@ uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 
 static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     ParseArgs A;
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
-    A.K = b.K; A.off = b.off;
+    A.K = b.K; A.off = b.off; A.Lf = b.Lf; A.Lq = b.Lq;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
@@ -1614,9 +1744,9 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
     parts = parts > 16u ? 16u : (parts < 1u ? 1u : parts);
     const dim3 grid(n_w, parts);
     if (j.prm.need_quarter)
-        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq, b.Lf, b.Lq);
     else
-        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
+        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq, b.Lf, b.Lq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1633,6 +1763,10 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
         DFL_LAUNCH_CHECK();
         k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
+        if (r & 1u) {   // the round before has given every chain of bad segments a true head; now the rest of each chain
+            k_chain_predict<<<1, 1024, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key);
+            DFL_LAUNCH_CHECK();
+        }
         k_parse_repair<<<grid, kParseThreads, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
     }
@@ -1645,6 +1779,15 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     return cudaSuccess;
 }
 
+cudaError_t launch_lz77_seq(const EncodeJob& j, Buffers& b, cudaStream_t st) {
+    SeqTables t{b.seq_tab, b.seq_tab + kWindow, b.seq_tab + 2 * kWindow};
+    k_lz77_seq_init<<<32, 32, 0, st>>>(t);
+    DFL_LAUNCH_CHECK();
+    k_lz77_seq<<<1, 32, 0, st>>>(j.d_in, j.n, j.prm, t, b.tok, b.meta);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
     uint32_t n_seg = j.parse_end > j.begin ? (uint32_t)parse_n_seg(j.parse_end - j.begin, g) : 0u;
@@ -1652,7 +1795,8 @@ cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st)
                                    b.seg_x_pos, b.seg_x_key, j.begin, j.init_key);
     DFL_LAUNCH_CHECK();
     if (n_seg > 0) {
-        k_compact<<<n_seg, 128, 0, st>>>(b.segtok, b.seg_e_tok, b.seg_cnt, b.seg_off, b.tok, b.meta, parse_tok_cap(g));
+        ParseArgs A = make_parse_args(j, b);
+        k_compact<<<n_seg, 128, 0, st>>>(A, b.seg_cnt, b.seg_off, b.tok, b.meta);
         DFL_LAUNCH_CHECK();
     }
     return cudaSuccess;

@@ -174,28 +174,41 @@ struct MatchData {
     std::vector<uint32_t> cnt, Mf, Mq;
 };
 
-int step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const MatchData& md, uint32_t out[2]) {
+// Token sink of the model: distances and literal bytes are looked up as the token is written (the kernels defer
+// exactly these two look-ups to k_compact).
+struct ModelSink {
+    const uint8_t* d; const MatchData* md; std::vector<uint32_t>* toks;
+    uint32_t dist_of(uint32_t ref, uint32_t kind) const {
+        return kind == kRefDist ? ref : match_dist((kind == kRefQuarter ? md->Mq : md->Mf)[ref]);
+    }
+    void literal(uint32_t pos) { toks->push_back(tok_literal(d[pos])); }
+    void match(uint32_t len, uint32_t ref, uint32_t kind) { toks->push_back(tok_match(len, dist_of(ref, kind))); }
+};
+
+void step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const MatchData& md, ModelSink& out) {
     uint32_t p = st.pos;
     const bool has_m = prm.mode != kRle && p + 2 < n && !md.Mf.empty();
+    uint32_t m_len = 0, m_ref = 0, m_kind = kRefDist;
+    auto take = [&](uint32_t rec, bool quarter, uint32_t floor) {
+        if (rec_is_long(rec)) {      // resolved now: the distance is known
+            uint32_t m = resolve_long(d, n, md.K, md.off, md.cnt, p, rec, floor, quarter ? prm.checks_quarter : prm.checks, prm.checks);
+            m_len = match_len(m); m_ref = m_len ? match_dist(m) : 0; m_kind = kRefDist;
+        } else {                     // final record: only its length is needed to decide; the distance stays behind `p`
+            m_len = match_len(rec); m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
+        }
+    };
     if (prm.mode == kLazy) {
-        uint32_t m = 0;
         if (has_m && !st.ign) {                       // the only case in which the reference searches (lz77.rs:347)
             const bool quarter = st.prev_len >= 32u;  // lz77.rs:351-355
-            if (!quarter || prm.need_quarter) {
-                m = quarter ? md.Mq[p] : md.Mf[p];
-                if (rec_is_long(m))
-                    m = resolve_long(d, n, md.K, md.off, md.cnt, p, m, st.prev_len, quarter ? prm.checks_quarter : prm.checks,
-                                     prm.checks);
-            }
+            if (!quarter || prm.need_quarter) take(quarter ? md.Mq[p] : md.Mf[p], quarter, st.prev_len);
         }
-        return lazy_step(st, n, d, m, m, prm.lazy, out);
+        lazy_step(st, n, m_len, m_ref, m_kind, prm.lazy, out);
+    } else if (prm.mode == kGreedy) {
+        if (has_m) take(md.Mf[p], false, 0);
+        greedy_step(st, n, m_len, m_ref, m_kind, out);
+    } else {
+        rle_step(st, n, d, out);
     }
-    if (prm.mode == kGreedy) {
-        uint32_t m = has_m ? md.Mf[p] : 0;
-        if (rec_is_long(m)) m = resolve_long(d, n, md.K, md.off, md.cnt, p, m, 0, prm.checks, prm.checks);
-        return greedy_step(st, n, d, m, out);
-    }
-    return rle_step(st, n, d, out);
 }
 
 void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const MatchData& md, ParseState st, uint32_t a,
@@ -203,21 +216,18 @@ void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const MatchD
     // runs from `st` until the first iteration position >= b (or the end of data)
     r.toks.clear();
     bool have_e = false;
-    uint32_t out[2];
+    ModelSink out{d, &md, &r.toks};
+    auto key = [&](const ParseState& s) { return parse_state_key(s, s.prev_len ? out.dist_of(s.prev_ref, s.prev_kind) : 0u); };
     while (st.pos < n) {
-        if (!have_e && st.pos >= a) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); have_e = true; }
+        if (!have_e && st.pos >= a) { r.e_pos = st.pos; r.e_key = key(st); r.e_tok = (uint32_t)r.toks.size(); have_e = true; }
         if (st.pos >= b) break;
-        int ne = step(prm, st, n, d, md, out);
-        for (int i = 0; i < ne; i++) r.toks.push_back(out[i]);
+        step(prm, st, n, d, md, out);
     }
-    if (!have_e) { r.e_pos = st.pos; r.e_key = parse_state_key(st); r.e_tok = (uint32_t)r.toks.size(); }
-    r.x_pos = st.pos; r.x_key = parse_state_key(st); r.x_tok = (uint32_t)r.toks.size();
+    if (!have_e) { r.e_pos = st.pos; r.e_key = key(st); r.e_tok = (uint32_t)r.toks.size(); }
+    r.x_pos = st.pos; r.x_key = key(st); r.x_tok = (uint32_t)r.toks.size();
 }
 
-ParseState state_from(uint32_t pos, uint32_t key) {
-    ParseState s; s.pos = pos; s.prev_len = key & 0x1ff; s.prev_dist = (key >> 9) & 0xffff; s.add = (key >> 25) & 1; s.ign = (key >> 26) & 1;
-    return s;
-}
+ParseState state_from(uint32_t pos, uint32_t key) { return parse_state_from_key(pos, key); }
 
 uint32_t g_last_repairs = 0, g_last_seq_repairs = 0;
 
@@ -242,10 +252,24 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
         if (list.empty()) break;
         // all repairs of one round read the *previous* round's exits, like a parallel kernel would
         std::vector<SegRec> fixed(list.size());
+        std::vector<uint8_t> isbad(nseg, 0);
+        for (uint32_t s : list) isbad[s] = 1;
         for (size_t i = 0; i < list.size(); i++) {
             uint32_t s = list[i];
             uint32_t a = begin + s * cfg.pseg, b = std::min(n, a + cfg.pseg);
-            parse_segment(prm, d, n, md, state_from(seg[s - 1].x_pos, seg[s - 1].x_key), a, b, fixed[i]);
+            ParseState st = state_from(seg[s - 1].x_pos, seg[s - 1].x_key);
+            if ((round & 1u) && isbad[s - 1]) {
+                // kernel k_chain_predict: inside a chain of maximum-length matches the parser is blank every 258
+                // bytes, so the entry follows from the exit of the last good segment in front of the chain
+                int g = (int)s - 1;
+                while (g >= 0 && isbad[g]) g--;
+                if (g >= 0 && seg[g].x_key == 0) {
+                    uint32_t xg = seg[g].x_pos;
+                    uint32_t steps = a > xg ? (a - xg + kMaxMatch - 1) / kMaxMatch : 0;
+                    st = state_from(xg + steps * kMaxMatch, 0);
+                }
+            }
+            parse_segment(prm, d, n, md, st, a, b, fixed[i]);
         }
         for (size_t i = 0; i < list.size(); i++) { seg[list[i]] = fixed[i]; g_last_repairs++; }
     }
@@ -259,6 +283,13 @@ void parse_all(const Params& prm, const Cfg& cfg, const uint8_t* d, uint32_t n, 
     }
     for (uint32_t s = 0; s < nseg; s++)
         tokens.insert(tokens.end(), seg[s].toks.begin() + seg[s].e_tok, seg[s].toks.begin() + seg[s].x_tok);
+}
+
+// ---- Lazy with lazy_if_less_than < 3: the reference's loop itself (kernel k_lz77_seq, dfl_core.h lz77_sequential)
+void sequential_tokens(const uint8_t* in, uint32_t n, const Params& prm, std::vector<uint32_t>& tokens) {
+    std::vector<uint32_t> head(kWindow, kSeqNone), pv(kWindow, kSeqNone), po(kWindow, kSeqNone);
+    tokens.assign((size_t)n + 4, 0);
+    tokens.resize((size_t)lz77_sequential(in, n, prm, head.data(), pv.data(), po.data(), tokens.data()));
 }
 
 // ---- stage 4..7: blocks
@@ -374,8 +405,12 @@ int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy,
     Cfg cfg{pseg, warm, rounds};
     std::vector<uint32_t> tokens;
     MatchData md;
-    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
-    parse_all(prm, cfg, in, n, md, tokens);
+    if (prm.mode == kLazy && prm.lazy < 3) {          // the library's dispatch: k_lz77_seq
+        sequential_tokens(in, n, prm, tokens);
+    } else {
+        if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
+        parse_all(prm, cfg, in, n, md, tokens);
+    }
     std::vector<uint8_t> o;
     emit_blocks(in, n, tokens, o, 1);
     *out = (uint8_t*)malloc(o.size() ? o.size() : 1);
@@ -392,8 +427,12 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
     Cfg cfg{pseg, warm, rounds};
     std::vector<uint32_t> tokens;
     MatchData md;
-    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
-    parse_all(prm, cfg, in, n, md, tokens);
+    if (prm.mode == kLazy && prm.lazy < 3) {          // the library's dispatch: k_lz77_seq
+        sequential_tokens(in, n, prm, tokens);
+    } else {
+        if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
+        parse_all(prm, cfg, in, n, md, tokens);
+    }
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
     *ntoks = tokens.size();

@@ -138,6 +138,30 @@ def test_custom_options_bit_exact(dfl, pg11):
         assert got == o.compress(data, opts, o.RAW), (checks, lazy, mt)
 
 
+def test_lazy_below_three_bit_exact(dfl, pg11):
+    """MatchingType::Lazy with lazy_if_less_than in {0, 1, 2} (0 is documented, compression_options.rs:93): the
+    reference's length-2 results from spurious chain entries (matching.rs:161-165, chained_hash_table.rs:34-51)
+    and its per-call re-derivation of ignore_next (lz77.rs:331) become visible in the output.  These option sets
+    run the reference's loop itself on the device (k_lz77_seq), one-shot in every container and through a writer
+    that is finished without intermediate flushes."""
+    rng = np.random.default_rng(1)
+    inputs = {"pg11": pg11, "issue_18": fixture_bytes("issue_18_201911.bin"),
+              "random4": rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+              "random16": rng.integers(0, 16, 200000, dtype=np.uint8).tobytes(), "zeros": bytes(100000), "empty": b"",
+              "pg70000": pg11[:70000]}
+    for checks, lazy, mt in ((128, 0, 1), (128, 1, 1), (128, 2, 1), (1, 0, 1), (4, 2, 1), (1768, 2, 1)):
+        opts = o.Options(checks, lazy, mt, 0)
+        for name, data in inputs.items():
+            want = o.compress(data, opts, o.RAW)
+            assert dfl.deflate_bytes_conf(data, _copts(dfl, opts)) == want, (checks, lazy, name)
+    opts = o.Options(128, 0, 1, 0)
+    assert dfl.deflate_bytes_zlib_conf(pg11, _copts(dfl, opts)) == o.compress(pg11, opts, o.ZLIB)
+    enc = dfl.write.DeflateEncoder(bytearray(), _copts(dfl, opts))
+    for i in range(0, len(pg11), 50000):
+        enc.write_all(pg11[i:i + 50000])
+    assert bytes(enc.finish()) == o.compress(pg11, opts, o.RAW)
+
+
 def test_device_api_and_overflow(dfl, pg11):
     import torch
     src = torch.frombuffer(bytearray(pg11), dtype=torch.uint8).cuda()

@@ -74,6 +74,22 @@ def test_model_custom_options(pg11):
         assert got == o.compress(data, opts, o.RAW), (checks, lazy, mt)
 
 
+def test_model_lazy_below_three(pg11):
+    """Lazy matching with lazy_if_less_than in {0, 1, 2}: length-2 results from spurious chain entries and the
+    per-call re-derivation of ignore_next matter (lz77.rs:331,374-377; matching.rs:161-165); dfl_core.h
+    lz77_sequential -- the code kernel k_lz77_seq runs -- must reproduce the oracle."""
+    rng = np.random.default_rng(1)
+    inputs = {"pg11": pg11, "issue_18": fixture_bytes("issue_18_201911.bin"),
+              "random4": rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+              "random16": rng.integers(0, 16, 200000, dtype=np.uint8).tobytes(), "zeros": bytes(100000), "empty": b"",
+              "one": b"\x01", "short": fixture_bytes("short.bin"), "pg65537": pg11[:65537]}
+    for checks, lazy, mt in ((128, 0, 1), (128, 1, 1), (128, 2, 1), (1, 0, 1), (4, 2, 1), (1768, 2, 1)):
+        opts = o.Options(checks, lazy, mt, 0)
+        for name, data in inputs.items():
+            got, _ = m.compress(data, opts, 4096, 256, 3)
+            assert got == o.compress(data, opts, o.RAW), (checks, lazy, name)
+
+
 def test_checksum_combine_arithmetic():
     """dfl_core.h crc32_combine / adler32_combine (used by the kernels' tree reductions and by the
     streaming handle) against CPython zlib on random splits, incl. empty and > 4 GiB-style lengths."""
