@@ -305,7 +305,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Lf); dev_free(b.Lq); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -349,8 +349,6 @@ struct Context {
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
-        if ((rc = dev_alloc(b.Lf, cap + 512))) return rc;
-        if (quarter && (rc = dev_alloc(b.Lq, cap + 512))) return rc;
         if ((rc = dev_alloc(b.segtok, parse_buffer_words(cap)))) return rc;
         if ((rc = dev_alloc(b.seg_e_pos, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_e_key, n_seg))) return rc;

@@ -43,7 +43,10 @@ inline size_t parse_buffer_words(size_t cap) {
         }
     return best;
 }
-constexpr uint32_t kRepairRounds = 6;    // parallel repair rounds before the sequential fallback (the second predicts chain phases)
+// Parallel repair rounds before the sequential fallback; every second one predicts the phase of chains of
+// maximum-length matches (k_chain_predict).  A round is three small launches; short inputs, where launch latency
+// is what counts, get fewer.
+inline uint32_t repair_rounds(size_t payload) { return payload <= (4u << 20) ? 4u : 12u; }
 
 // Device-resident bookkeeping of one encode call (one instance per context).
 struct DevMeta {
@@ -92,8 +95,6 @@ struct Buffers {   // device scratch of one context, grown on demand
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
-    uint8_t* Lf = nullptr;          // per-position length code of Mf (dfl_core.h rec_len_code): what the parser reads at every step
-    uint8_t* Lq = nullptr;          // ... of Mq
     uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * parse_tok_cap
     uint32_t* seg_e_pos = nullptr;  // hand-off records (SoA), n_pseg each
     uint32_t* seg_e_key = nullptr;

@@ -329,6 +329,19 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
 //   searches there.  No data is touched here beyond the three bytes that give a target its bucket.
 //   shared: the window's bytes (+16)
 // =====================================================================================
+// 8 bytes at in[idx ..] (idx < n), little endian; bytes past the last word of the input read as 0 (callers clamp
+// the lengths they derive to the bytes that exist).  Works for any alignment of `in`.
+__device__ __forceinline__ unsigned long long ld8(const uint8_t* __restrict__ in, const uint32_t* last_word, uint32_t idx) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t x0 = __ldg(w);
+    const uint32_t x1 = (w + 1 <= last_word) ? __ldg(w + 1) : 0u;
+    const uint32_t x2 = (w + 2 <= last_word) ? __ldg(w + 2) : 0u;
+    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 constexpr uint32_t kMatchThreads = 512;
 constexpr uint32_t kMatchStage = kWindow + 16;        // multiple of 16
 constexpr uint32_t kMatchSmem = kMatchStage + 16;
@@ -392,7 +405,7 @@ template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
 k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
         const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
-        uint32_t* __restrict__ Mq, uint8_t* __restrict__ Lf, uint8_t* __restrict__ Lq) {
+        uint32_t* __restrict__ Mq) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
     const uint32_t w = w_first + blockIdx.x;
@@ -408,6 +421,7 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
     const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
     const uint32_t budget = prm.checks;
     const uint32_t qbudget = prm.checks_quarter;
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
 
     // gridDim.y CTAs share one window when the input is small (the stage's latency is one CTA's run through
     // 32768 entries otherwise): each takes a contiguous, 32-aligned slice of the sorted entries
@@ -492,14 +506,24 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
         if (act) {
             // distance of visit k: own window pl - pos, previous window pl + 32768 - pos
             const uint32_t d = (wk.best_k < n_own ? pl : pl + kWindow) - wk.best_pos;
-            const uint32_t rec = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            uint32_t rec = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            if (rec_is_long(rec) && n_tot == 1u) {
+                // a single candidate (always so at Compression::Fast, max_hash_checks = 1): nothing to choose from, so the
+                // length is settled here instead of by the parser (the bytes are in L2: this CTA has just staged them)
+                uint32_t l = kEntryBytes;
+                while (l < maxl) {
+                    const unsigned long long x = ld8(in, last_word, p + l) ^ ld8(in, last_word, p - d + l);
+                    if (x != 0ull) { l += (uint32_t)(__ffsll((long long)x) - 1) >> 3; break; }
+                    l += 8u;
+                }
+                rec = finalize_match(l < maxl ? l : maxl, d);
+            }
             Mf[p] = rec;
-            Lf[p] = (uint8_t)rec_len_code(rec);
             if (NEEDQ) {
                 const uint32_t dq = (wk.q_k < n_own ? pl : pl + kWindow) - wk.q_pos;
-                const uint32_t rq = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+                uint32_t rq = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+                if (rec_is_long(rq) && n_tot == 1u) rq = rec;      // the one candidate there is: settled above
                 Mq[p] = rq;
-                Lq[p] = (uint8_t)rec_len_code(rq);
             }
         }
     }
@@ -521,7 +545,6 @@ __device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key)
 struct ParseArgs {
     const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
     const uint32_t* Mf; const uint32_t* Mq;
-    const uint8_t* Lf; const uint8_t* Lq;  // one byte per position: 0 = no match, 3..8 = length of the final record, kLenLong
     const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window (long records refer to them)
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
@@ -530,19 +553,6 @@ struct ParseArgs {
     uint32_t end;                  // parse bound (EncodeJob::parse_end)
     uint32_t init_key;             // state at `begin`
 };
-
-// 8 bytes at in[idx ..] (idx < n), little endian; bytes past the last word of the input read as 0 (callers clamp
-// the lengths they derive to the bytes that exist).  Works for any alignment of `in`.
-__device__ __forceinline__ unsigned long long ld8(const uint8_t* __restrict__ in, const uint32_t* last_word, uint32_t idx) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-    const uint32_t x0 = __ldg(w);
-    const uint32_t x1 = (w + 1 <= last_word) ? __ldg(w + 1) : 0u;
-    const uint32_t x2 = (w + 2 <= last_word) ? __ldg(w + 2) : 0u;
-    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
-    return ((unsigned long long)hi << 32) | lo;
-}
 
 // What a parked lane asks for.  Filled by the lane itself; all parked lanes of a warp prepare at the same time.
 struct Resolve {
@@ -588,14 +598,18 @@ __device__ __forceinline__ const uint2* resolve_entry(const ParseArgs& A, uint32
     return k < n_own ? Kw + (rank - 1u - k) : Kw - kWindow + (pe - 1u - (k - n_own));
 }
 
+#ifndef DFL_PARSE_CTAS
+#define DFL_PARSE_CTAS 7      // CTAs of 128 threads per SM the parse kernels are compiled for (72 registers)
+#endif
 #ifndef DFL_PARSE_KEEP
 #define DFL_PARSE_KEEP 6      // keep parsing while at least this many lanes of a warp are running
 #endif
 constexpr uint32_t kParseThreads = 128;
 constexpr uint32_t kParseWarps = kParseThreads / 32;
 constexpr uint32_t kCandCap = 256;       // candidates a warp collects before it compares them
-constexpr uint32_t kLcBytes = 256;       // length codes a lane keeps in shared memory: the 128-byte line it is in and the next
+constexpr uint32_t kLcBytes = 128;       // length codes (dfl_core.h rec_len_code, one byte per position) a lane keeps in shared memory
 constexpr uint32_t kLcWords = kLcBytes / 4;
+constexpr uint32_t kLcHalf = kLcBytes / 2;
 struct ParseShared {
     uint32_t cand_q[kCandCap];           // absolute position of a candidate that shares the target's 8 entry bytes
     uint32_t cand_meta[kCandCap];        // owner lane | visit index << 5
@@ -697,9 +711,8 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
     const bool has_m = (mode != kRle) && (A.prm.checks > 0);
     const uint32_t lane = lane_id();
     const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
-    const uint32_t* L32 = reinterpret_cast<const uint32_t*>(A.Lf);
     uint32_t* lc = S.lc + lane * (kLcWords + 1u);
-    uint32_t cb = 0xffffff00u;                       // position of the first cached length code (a multiple of 128); nothing yet
+    uint32_t cb = 0xffffff00u;                       // position of the first cached length code (a multiple of kLcHalf); nothing yet
     bool running = work, parked = false, have_m = false, rq_quarter = false;
     uint32_t m_ready = 0, rq_budget = 0;
     Resolve rq;
@@ -734,8 +747,8 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                         const bool quarter = mode == kLazy && st.prev_len >= 32u;        // lz77.rs:351-355
                         if (!quarter || A.prm.need_quarter) {
                             uint32_t code;
-                            if (quarter) code = A.Lq[p];
-                            else if (p - cb < kLcBytes) code = (lc[(p - cb) >> 2] >> (8u * (p & 3u))) & 0xffu;
+                            if (quarter) code = rec_len_code(A.Mq[p]);
+                            else if (p - cb < kLcBytes) code = (lc[(p - cb) >> 2] >> (8u * (p & 3u))) & 0xffu;   // cb is a multiple of 4
                             else { code = 0; miss = true; }
                             if (code == kLenLong) {
                                 rq.p = p;
@@ -757,22 +770,27 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                     }
                 }
             }
-            // length codes: a lane that ran out of its cached 256 bytes gets the line it is in and the next one; lanes
-            // that have left their first line are refreshed in the same round, so that round trips are shared
+            // Length codes: the match records of the next kLcBytes positions of a lane, one byte each, fetched by the
+            // whole warp (coalesced 16-byte loads, four records per lane and load) when the lane runs out; lanes that
+            // are past the middle of what they hold are refreshed in the same round, so that round trips are shared.
             uint32_t want = __ballot_sync(0xffffffffu, miss);
             if (want) {
-                want |= __ballot_sync(0xffffffffu, running && !parked && has_m && st.pos - cb >= 128u);
-                const uint32_t mine = st.pos & ~127u;
+                want |= __ballot_sync(0xffffffffu, running && !parked && has_m && st.pos - cb >= kLcHalf);
+                const uint32_t mine = st.pos & ~(kLcHalf - 1u);
                 for (uint32_t left = want; left;) {
                     const int j = __ffs((int)left) - 1;
                     left &= left - 1u;
                     const uint32_t base = __shfl_sync(0xffffffffu, mine, j);
-                    uint32_t* row = S.lc + (uint32_t)j * (kLcWords + 1u);
+                    const uint32_t q = base + 4u * lane;                      // this lane converts records q .. q + 3
+                    uint32_t codes = 0;
+                    if (q + 4u <= n && ((reinterpret_cast<uintptr_t>(A.Mf + q) & 15u) == 0)) {
+                        const uint4 r = __ldg(reinterpret_cast<const uint4*>(A.Mf + q));
+                        codes = rec_len_code(r.x) | (rec_len_code(r.y) << 8) | (rec_len_code(r.z) << 16) | (rec_len_code(r.w) << 24);
+                    } else {
 #pragma unroll
-                    for (uint32_t t = 0; t < kLcWords / 32u; t++) {
-                        const uint32_t wi = t * 32u + lane;
-                        row[wi] = (base + 4u * wi < n) ? __ldg(L32 + (base >> 2) + wi) : 0u;
+                        for (uint32_t t = 0; t < 4; t++) if (q + t < n) codes |= rec_len_code(A.Mf[q + t]) << (8u * t);
                     }
+                    S.lc[(uint32_t)j * (kLcWords + 1u) + lane] = codes;
                 }
                 if ((want >> lane) & 1u) cb = mine;
                 __syncwarp();
@@ -859,7 +877,7 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
 
 
 
-__global__ void __launch_bounds__(kParseThreads) k_parse_spec(ParseArgs A) {
+__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_spec(ParseArgs A) {
     __shared__ ParseShared sh[kParseWarps];
     // The lanes of a warp take segments far apart (stride = number of warps in the grid): the cost of a segment
     // depends on the kind of data, neighbouring segments are of one kind, and a warp is as slow as its slowest lane.
@@ -894,7 +912,7 @@ __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad,
     bad[s] = is_bad;
 }
 
-__global__ void __launch_bounds__(kParseThreads) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
+__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
                                                                 const uint32_t* start_key, DevMeta* meta) {
     __shared__ ParseShared sh[kParseWarps];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1688,7 +1706,7 @@ uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 
 static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     ParseArgs A;
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
-    A.K = b.K; A.off = b.off; A.Lf = b.Lf; A.Lq = b.Lq;
+    A.K = b.K; A.off = b.off;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
@@ -1744,9 +1762,9 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
     parts = parts > 16u ? 16u : (parts < 1u ? 1u : parts);
     const dim3 grid(n_w, parts);
     if (j.prm.need_quarter)
-        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq, b.Lf, b.Lq);
+        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     else
-        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq, b.Lf, b.Lq);
+        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1758,7 +1776,7 @@ cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     k_parse_spec<<<grid, kParseThreads, 0, st>>>(A);
     DFL_LAUNCH_CHECK();
     if (A.n_seg == 1) return cudaSuccess;
-    for (uint32_t r = 0; r < kRepairRounds; r++) {
+    for (uint32_t r = 0, nr = repair_rounds(j.n - j.begin); r < nr; r++) {
         k_reset_bad<<<1, 1, 0, st>>>(b.meta);
         DFL_LAUNCH_CHECK();
         k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);

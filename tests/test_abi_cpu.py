@@ -123,3 +123,52 @@ def test_c_caller_output_equals_the_oracle(tmp_path):
             got = out.read_bytes()
             assert zlib.decompress(got, wbits) == data
             assert got == o.compress(data, opts, owrap), (level, wrap)
+
+
+def _build_cpp_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "deflate_file_cpp")
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "deflate_file.cpp"), "-o", exe, "-L", lib_dir, "-ldeflate_b200",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def test_cpp_header_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """include/deflate_b200.hpp (the C++ mirror of the crate API, SURVEY 8(b) "who calls it") must compile with
+    -Wall -Werror against the C header as shipped, and on a box without a GPU stop with the library's message."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU variant")
+    exe = _build_cpp_example(tmp_path)
+    out = tmp_path / "out.zlib"
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "fixtures", "pg11.txt"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    assert not out.exists()
+
+
+@pytest.mark.gpu
+def test_cpp_caller_output_equals_the_oracle(tmp_path):
+    import subprocess
+    import oracle_lib as o
+    exe = _build_cpp_example(tmp_path)
+    src = os.path.join(ROOT, "tests", "fixtures", "pg11.txt")
+    out = tmp_path / "out.zlib"
+    subprocess.check_call([exe, src, str(out)])   # the example itself checks one-shot == streamed
+    assert out.read_bytes() == o.compress(open(src, "rb").read(), o.opts_default(), o.ZLIB)
+
+
+def test_rust_shim_binds_only_symbols_the_library_exports():
+    """rust-shim/src/lib.rs cannot be compiled here (no rustc); at least every `pub fn dfl_*` it declares must be
+    a symbol include/deflate_b200.h declares and the built library exports."""
+    import re
+    src = open(os.path.join(ROOT, "rust-shim", "src", "lib.rs")).read()
+    names = set(re.findall(r"pub fn (dfl_[a-z0-9_]+)\(", src))
+    assert len(names) >= 20
+    hdr = open(os.path.join(ROOT, "include", "deflate_b200.h")).read()
+    L = _native.lib()
+    for nm in sorted(names):
+        assert re.search(r"\b" + nm + r"\(", hdr), nm
+        assert hasattr(L, nm), nm
