@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -53,6 +54,24 @@ int device_count_cached() {
     });
     return count;
 }
+
+// Streams, scratch and kernel attributes belong to one CUDA device: everything that caches them is keyed by it.
+int current_device() {
+    int dev = 0;
+    if (device_count_cached() <= 0 || cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return dev;
+}
+// Makes `dev` current for the lifetime of the guard (an encoder handle stays on the device it was created on,
+// whatever device the calling thread has selected since).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0 || device_count_cached() <= 0) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 template <typename T>
 int dev_alloc(T*& p, size_t count) {
@@ -154,6 +173,16 @@ inline bool host_pointer_is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// Copy jobs hold pointers into the caller's buffer, the slot rings and the completion flags of the call that
+// submitted them: whichever way that call returns -- also with a CUDA error half way -- it first waits for every
+// job it has submitted.
+struct JobDrain {
+    CopyPool& pool;
+    std::atomic<int>* done;
+    size_t submitted = 0;
+    ~JobDrain() { for (size_t i = 0; i < submitted; i++) pool.wait(&done[i]); }
+};
+
 struct Stager {   // one per Context, allocated on first use
     uint8_t* ring[2] = {nullptr, nullptr};   // [0] host-to-device, [1] device-to-host
     cudaEvent_t ev[2][kStageSlots] = {};
@@ -180,6 +209,7 @@ struct Stager {   // one per Context, allocated on first use
         const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
         std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_chunks]);
         for (size_t i = 0; i < n_chunks; i++) done[i].store(0, std::memory_order_relaxed);
+        JobDrain drain{pool, done.get()};
         size_t enq = 0;   // chunks whose DMA has been queued (in order)
         auto chunk_len = [&](size_t i) { return (i + 1 == n_chunks) ? len - i * kStageSlot : kStageSlot; };
         auto queue_dma = [&](size_t i) -> int {
@@ -195,6 +225,7 @@ struct Stager {   // one per Context, allocated on first use
             const size_t slot = (size_t)((seq + i) % kStageSlots);
             CK(cudaEventSynchronize(ev[0][slot]));   // the DMA that last read this slot (this call or an earlier one)
             pool.submit(ring[0] + slot * kStageSlot, h_src + i * kStageSlot, chunk_len(i), &done[i]);
+            drain.submitted = i + 1;
         }
         while (enq < n_chunks) { pool.wait(&done[enq]); if ((rc = queue_dma(enq))) return rc; enq++; }
         seq += n_chunks;
@@ -225,6 +256,7 @@ struct Stager {   // one per Context, allocated on first use
         const size_t n_chunks = (len + kStageSlot - 1) / kStageSlot;
         std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_chunks]);
         for (size_t i = 0; i < n_chunks; i++) done[i].store(0, std::memory_order_relaxed);
+        JobDrain drain{pool, done.get()};
         auto chunk_len = [&](size_t i) { return (i + 1 == n_chunks) ? len - i * kStageSlot : kStageSlot; };
         for (size_t i = 0; i < n_chunks + kStageAhead; i++) {
             if (i < n_chunks) {
@@ -237,6 +269,7 @@ struct Stager {   // one per Context, allocated on first use
                 const size_t j = i - kStageAhead, slot = j % kStageSlots;
                 CK(cudaEventSynchronize(ev[1][slot]));
                 pool.submit(h_dst + j * kStageSlot, ring[1] + slot * kStageSlot, chunk_len(j), &done[j]);
+                drain.submitted = j + 1;
             }
         }
         for (size_t i = 0; i < n_chunks; i++) pool.wait(&done[i]);
@@ -408,8 +441,9 @@ struct InputArrival {
     }
 };
 
-Context& tls_context() {
-    thread_local std::unique_ptr<Context> ctx;
+Context& tls_context() {   // one per calling thread and device
+    thread_local std::map<int, std::unique_ptr<Context>> ctxs;
+    std::unique_ptr<Context>& ctx = ctxs[current_device()];
     if (!ctx) ctx.reset(new Context());
     return *ctx;
 }
@@ -933,7 +967,8 @@ extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, 
                                          int* status) {
     if (!opt || !valid_wrap(wrap) || (count && (!d_in || !n || !d_out || !out_cap || !out_len))) return DFL_E_ARG;
     constexpr size_t kBatchLanes = 16;
-    thread_local std::vector<std::unique_ptr<Context>> pool;
+    thread_local std::map<int, std::vector<std::unique_ptr<Context>>> pools;   // per device
+    std::vector<std::unique_ptr<Context>>& pool = pools[current_device()];
     const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
     while (pool.size() < lanes) pool.emplace_back(new Context());
     int first_err = DFL_OK;
@@ -973,7 +1008,8 @@ extern "C" int dfl_compress_batch(size_t count, const uint8_t* const* in, const 
                                   uint8_t* const* out, const size_t* out_cap, size_t* out_len, int* status) {
     if (!opt || !valid_wrap(wrap) || (count && (!in || !n || !out || !out_cap || !out_len))) return DFL_E_ARG;
     constexpr size_t kBatchLanes = 16;
-    thread_local std::vector<std::unique_ptr<Context>> pool;
+    thread_local std::map<int, std::vector<std::unique_ptr<Context>>> pools;   // per device
+    std::vector<std::unique_ptr<Context>>& pool = pools[current_device()];
     const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
     while (pool.size() < lanes) pool.emplace_back(new Context());
     std::vector<size_t> member(lanes, SIZE_MAX);   // the member in flight on each lane
@@ -1557,6 +1593,7 @@ static size_t piece_target(const dfl_encoder* e) {
 }
 
 extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, size_t* consumed) {
+    DeviceGuard on_device(e ? e->device : -1);   // the handle's streams and buffers live on the device it was created on
     if (!e || (!buf && n)) return DFL_E_ARG;
     if (e->finished) return DFL_E_STATE;
     int rc = DFL_OK;
@@ -1596,12 +1633,14 @@ extern "C" int dfl_encoder_write(dfl_encoder* e, const uint8_t* buf, size_t n, s
 }
 
 extern "C" int dfl_encoder_flush(dfl_encoder* e, int mode) {
+    DeviceGuard on_device(e ? e->device : -1);   // the handle's streams and buffers live on the device it was created on
     if (!e || (mode != DFL_FLUSH_SYNC && mode != DFL_FLUSH_FINISH)) return DFL_E_ARG;
     if (e->finished) return mode == DFL_FLUSH_FINISH ? DFL_OK : DFL_E_STATE;
     return encoder_emit(e, mode);
 }
 
 extern "C" int dfl_encoder_take_output(dfl_encoder* e, const uint8_t** p, size_t* len) {
+    DeviceGuard on_device(e ? e->device : -1);   // the handle's streams and buffers live on the device it was created on
     if (!e || !p || !len) return DFL_E_ARG;
     // bytes of a piece still running become visible once it is settled; do that here if it costs no wait
     if (e->busy && cudaStreamQuery(e->ctx->stream) == cudaSuccess) {
@@ -1630,6 +1669,7 @@ extern "C" int dfl_encoder_set_piece_bytes(dfl_encoder* e, size_t bytes) {
 }
 
 extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
+    DeviceGuard on_device(e ? e->device : -1);   // the handle's streams and buffers live on the device it was created on
     if (!e || e->wrap == DFL_RAW) return 1;   // NoChecksum::current_hash (checksum.rs:26-28)
     if (encoder_init(e) != DFL_OK || encoder_settle(e, kPieceOpen) != DFL_OK || encoder_fetch_bulk(e) != DFL_OK ||
         encoder_push_pending(e) != DFL_OK)
@@ -1640,6 +1680,7 @@ extern "C" uint32_t dfl_encoder_checksum(dfl_encoder* e) {
 }
 
 extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t gz_hdr_len) {
+    DeviceGuard on_device(e ? e->device : -1);   // the handle's streams and buffers live on the device it was created on
     if (!e || gz_hdr_len > 0xffffu) return DFL_E_ARG;
     if (!e->finished) {
         int rc = encoder_emit(e, DFL_FLUSH_FINISH);   // output_all() (writer.rs:112-115,218-223)
@@ -1674,4 +1715,8 @@ extern "C" int dfl_encoder_reset(dfl_encoder* e, const uint8_t* gz_hdr, size_t g
     return DFL_OK;
 }
 
-extern "C" void dfl_encoder_free(dfl_encoder* e) { delete e; }
+extern "C" void dfl_encoder_free(dfl_encoder* e) {
+    if (!e) return;
+    DeviceGuard on_device(e->device);
+    delete e;
+}

@@ -154,8 +154,15 @@ DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
     if (len == kMinMatch && dist > kTooFar) return 0u;
     return pack_match(len, dist);
 }
-// Length code of a record: what the parser needs in order to decide (the distance only matters once a token is written).
-DFL_HD uint32_t rec_len_code(uint32_t rec) { return rec_is_long(rec) ? kLenLong : match_len(rec); }
+// Length code of a record, one byte: what the parser needs in order to decide (the distance only matters once a
+// token is written).  0 = no match, 1..253 = length - 2, kLenSeeRecord = a final length of 256..258 (read it from
+// the record), kLenLong = the record is long.
+constexpr uint32_t kLenSeeRecord = 0xfeu;
+DFL_HD uint32_t rec_len_code(uint32_t rec) {
+    if (rec_is_long(rec)) return kLenLong;
+    const uint32_t l = match_len(rec);
+    return l == 0u ? 0u : (l <= 255u ? l - 2u : kLenSeeRecord);
+}
 // Record of a finished entry walk.  `rank` = index of the target in its window's sorted list, `dist` = distance
 // of the best candidate.
 DFL_HD uint32_t ewalk_record(const EntryWalk& s, uint32_t rank, uint32_t dist, uint32_t maxl) {

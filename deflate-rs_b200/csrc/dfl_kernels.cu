@@ -759,7 +759,8 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                                 rq_quarter = quarter;
                                 parked = true;
                             } else {
-                                m_len = code; m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
+                                m_len = code == 0u ? 0u : (code == kLenSeeRecord ? match_len(quarter ? A.Mq[p] : A.Mf[p]) : code + 2u);
+                                m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
                             }
                         }
                     }
@@ -1673,7 +1674,9 @@ __global__ void k_finalize(DevMeta* meta, uint8_t* out, unsigned long long out_c
                            int sync_marker, int write_trailer, uint32_t isize, uint32_t carry_bits_n, uint32_t carry_bits_v) {
     unsigned long long end = hdr_bytes + meta->stream_bytes;
     const unsigned long long trailer = write_trailer ? (wrap == 1 ? 4ull : (wrap == 2 ? 8ull : 0ull)) : 0ull;
-    if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = end + trailer; return; }
+    // the packer writes whole 16-byte units: the buffer must hold the container rounded up plus one unit of slack;
+    // on overflow that is the size reported, so that a caller who retries with exactly it succeeds
+    if (end + 16ull > out_cap) { meta->err = 100; meta->out_bytes = ((end + trailer + 16ull) + 15ull) & ~15ull; return; }
     if (carry_bits_n) out[hdr_bytes] |= (uint8_t)carry_bits_v;   // the bits the previous piece left in its last byte
     if (sync_marker && end >= 4 && end <= out_cap) {
         out[end - 2] = 0xff;

@@ -68,7 +68,7 @@ enum dfl_status {
     DFL_E_NOMEM = -2,
     DFL_E_CUDA = -3,
     DFL_E_NODEVICE = -4,    /* no CUDA device / extension unusable: there is no CPU fallback */
-    DFL_E_OVERFLOW = -5,    /* out_cap too small; *out_len receives the size needed */
+    DFL_E_OVERFLOW = -5,    /* out_cap too small; *out_len receives a capacity that suffices (see dfl_bound) */
     DFL_E_STATE = -6,       /* e.g. write after finish */
     DFL_E_UNSUPPORTED = -7,
     DFL_E_INTERNAL = -8,
@@ -81,7 +81,10 @@ int dfl_version(void);
 /* Number of usable CUDA devices (0 on a CPU-only box; never an error). */
 int dfl_device_count(void);
 
-/* Upper bound of the output size for n input bytes (any options, any wrapper). */
+/* Upper bound of the output size for n input bytes (any options, any wrapper with its default header; a caller
+ * that passes its own gzip header adds gz_hdr_len).  Device output buffers must be 16-byte aligned and the kernels
+ * write whole 16-byte units: a capacity of dfl_bound() is always enough; when a smaller one turns out too small the
+ * call returns DFL_E_OVERFLOW and *out_len holds a capacity that is enough for this input. */
 size_t dfl_bound(size_t n, int wrap);
 
 /* ---- one-shot, host buffers: deflate_bytes_conf / _zlib_conf / _gzip_conf -------------------

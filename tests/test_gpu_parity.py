@@ -172,6 +172,17 @@ def test_device_api_and_overflow(dfl, pg11):
     with pytest.raises(dfl.DeflateB200Error) as ei:
         dfl.compress_device(src, dfl.Compression.Default, dfl.RAW, out=small)
     assert ei.value.status == -5   # DFL_E_OVERFLOW, nothing written past the buffer
+    # the size reported with DFL_E_OVERFLOW is a capacity that suffices: retrying with exactly it succeeds
+    L = dfl._native.lib()
+    opts = dfl.CompressionOptions.default()._c()
+    need = ctypes.c_size_t()
+    rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), src.numel(), ctypes.byref(opts), dfl.RAW, None, 0,
+                               ctypes.c_void_p(small.data_ptr()), small.numel(), ctypes.byref(need), None)
+    assert rc == -5 and need.value > small.numel()
+    exact = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    rc = L.dfl_compress_device(ctypes.c_void_p(src.data_ptr()), src.numel(), ctypes.byref(opts), dfl.RAW, None, 0,
+                               ctypes.c_void_p(exact.data_ptr()), exact.numel(), ctypes.byref(need), None)
+    assert rc == 0 and bytes(exact[:need.value].cpu().numpy()) == o.compress(pg11, o.opts_default(), o.RAW)
 
 
 def test_large_synthetic_roundtrip_and_ratio(dfl):
