@@ -338,7 +338,7 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.K2); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
         dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
@@ -379,6 +379,7 @@ struct Context {
         size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
         int rc = 0;
         if ((rc = dev_alloc(b.K, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.K2, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.Mf, cap))) return rc;
         if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;

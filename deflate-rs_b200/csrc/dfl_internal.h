@@ -92,6 +92,7 @@ struct BlockTables {
 
 struct Buffers {   // device scratch of one context, grown on demand
     uint2* K = nullptr;             // candidate entries in bucket order (dfl_core.h Entry), n_windows * 32768
+    uint2* K2 = nullptr;            // bytes 8..15 of every entry of K, same order (the parse stage settles common prefixes below 16 from it)
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
     uint32_t* Mf = nullptr;         // per-position match (full chain budget)
     uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed

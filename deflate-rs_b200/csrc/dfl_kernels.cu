@@ -129,14 +129,14 @@ constexpr uint32_t kSortCntWords = 32 * (kSortThreads / 2);      // 32 digits x 
 constexpr uint32_t kSortBufWords = kWindow + kWindow / 32;       // +1 pad word per 32 (conflict-free blocked reads)
 constexpr uint32_t kSortSmem = (kSortCntWords + kSortBufWords) * 4 + 256;
 static_assert(kSortItems == 32, "one item per bit of the digit/prefix packing below");
-static_assert(kWindow + 16 <= kSortCntWords * 4, "byte staging must fit in the counter area");
+static_assert(kWindow + 32 <= kSortCntWords * 4, "byte staging must fit in the counter area");
 
 // word w of a counter row is stored at slot_of(w): its 32-word group rotated by the group number
 __device__ __forceinline__ uint32_t sort_slot_of(uint32_t w) { return (w & ~31u) | ((w + (w >> 5)) & 31u); }
 
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
-                                                                 uint16_t* __restrict__ off) {
+                                                                 uint2* __restrict__ K2, uint16_t* __restrict__ off) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* cntw = reinterpret_cast<uint32_t*>(smem);                        // kSortCntWords
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem);
@@ -246,10 +246,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
 
     // ---- output: entries in bucket order
     {
-    stage_bytes(smem, in, (long long)base, kWindow + 16, n);   // counters are dead; bytes again
+    stage_bytes(smem, in, (long long)base, kWindow + 32, n);   // counters are dead; bytes again
     __syncthreads();
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
     uint2* Kw = K + (size_t)w * kWindow;
+    uint2* K2w = K2 + (size_t)w * kWindow;
     for (uint32_t r = t; r < kWindow; r += kSortThreads) {
         uint2 e = make_uint2(0u, 0xfffe0000u);               // filler beyond cnt; never read as a candidate
         if (r < cnt) {
@@ -261,6 +262,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
             uint32_t v1 = __funnelshift_r(w1, w2, sh);       // bytes 4..7
             e.x = (v0 >> 24) | (v1 << 8);                    // bytes 3..6
             e.y = (v1 >> 24) | (tag9(v0 & 0xffu, (v0 >> 8) & 0xffu) << 8) | (pos << 17);
+            // bytes 8..15, for the parse stage: what decides between candidates that share the 8 entry bytes
+            const uint32_t w3 = sw[a + 3], w4 = sw[a + 4];
+            K2w[r] = make_uint2(__funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
         }
         Kw[r] = e;
     }
@@ -546,6 +550,7 @@ struct ParseArgs {
     const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
     const uint32_t* Mf; const uint32_t* Mq;
     const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window (long records refer to them)
+    const uint2* K2;                       // bytes 8..15 of every sorted entry
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
     uint32_t n_seg;
@@ -565,6 +570,7 @@ struct Resolve {
     uint32_t n_vis;    // visits allowed in total (chain budget; the previous window's share may end earlier)
     uint32_t pe;       // visit k >= n_own is Kp[pe - 1 - (k - n_own)]
     uint32_t me_lo, me_hi;
+    uint32_t b8_lo, b8_hi;   // bytes 8..15 of the target
 };
 
 __device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t budget, bool quarter) {
@@ -572,7 +578,8 @@ __device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, 
     const uint32_t rec = quarter ? A.Mq[p] : A.Mf[p];   // a long record: rank of p in its window's list, first visit to look at
     r.rank = rec_rank(rec); r.k0 = rec_k8(rec);
     const uint2 me = __ldg(A.K + (size_t)w * kWindow + r.rank);
-    r.me_lo = me.x; r.me_hi = me.y;
+    const uint2 b8 = __ldg(A.K2 + (size_t)w * kWindow + r.rank);
+    r.me_lo = me.x; r.me_hi = me.y; r.b8_lo = b8.x; r.b8_hi = b8.y;
     const uint32_t h = hash3(A.in[p], A.in[p + 1], A.in[p + 2]);
     const uint16_t* ow = A.off + (size_t)w * kWindow;
     const uint32_t full = A.prm.checks;
@@ -606,13 +613,17 @@ __device__ __forceinline__ const uint2* resolve_entry(const ParseArgs& A, uint32
 #endif
 constexpr uint32_t kParseThreads = 128;
 constexpr uint32_t kParseWarps = kParseThreads / 32;
-constexpr uint32_t kCandCap = 256;       // candidates a warp collects before it compares them
-constexpr uint32_t kLcBytes = 128;       // length codes (dfl_core.h rec_len_code, one byte per position) a lane keeps in shared memory
+constexpr uint32_t kCandCap = 128;       // candidates a warp collects before it compares them
+#ifndef DFL_LC_BYTES
+#define DFL_LC_BYTES 128
+#endif
+constexpr uint32_t kLcBytes = DFL_LC_BYTES;   // length codes (dfl_core.h rec_len_code, one byte per position) a lane keeps in shared memory
 constexpr uint32_t kLcWords = kLcBytes / 4;
 constexpr uint32_t kLcHalf = kLcBytes / 2;
 struct ParseShared {
     uint32_t cand_q[kCandCap];           // absolute position of a candidate that shares the target's 8 entry bytes
     uint32_t cand_meta[kCandCap];        // owner lane | visit index << 5
+    uint2 cand_b8[kCandCap];             // the candidate's bytes 8..15
     uint32_t res_key[32];                // per owner lane: best length << 16 | (0xffff - visit index)
     uint32_t lc[32 * (kLcWords + 1)];    // per lane kLcWords words of length codes (+1: rows fall on different banks)
 };
@@ -636,9 +647,10 @@ struct DeferSink {
     }
 };
 
-// Compares the collected candidates of all owners, one candidate per lane and round: the byte that would extend
-// the owner's running best (matching.rs:141-143) and the first 8 bytes behind the entry come in one round trip,
-// longer common prefixes continue in lock step 8 bytes at a time.  The longest candidate wins, the nearest
+// Compares the collected candidates of all owners, one candidate per lane and round.  Bytes 8..15 of target and
+// candidate are at hand (K2), so a common prefix below 16 bytes is settled without touching the input; only a
+// candidate that shares all 16 goes on: the byte that would extend the owner's running best
+// (matching.rs:141-143), then a lock-step comparison 8 bytes at a time.  The longest candidate wins, the nearest
 // among equals (matching.rs:148-157): a max over length << 16 | ~visit.
 __device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared& S, uint32_t cnt, const Resolve& rq,
                                                 const uint32_t* last_word) {
@@ -648,22 +660,24 @@ __device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared&
         const bool have = c < cnt;
         const uint32_t meta = have ? S.cand_meta[c] : 0u;
         const uint32_t q = have ? S.cand_q[c] : 0u;
+        const uint2 cb8 = have ? S.cand_b8[c] : make_uint2(0u, 0u);
         const uint32_t owner = meta & 31u, k = meta >> 5;
         const uint32_t po = __shfl_sync(0xffffffffu, rq.p, owner);
         const uint32_t st = __shfl_sync(0xffffffffu, rq.start, owner);
         const uint32_t ml = __shfl_sync(0xffffffffu, rq.maxl, owner);
+        const uint32_t tlo = __shfl_sync(0xffffffffu, rq.b8_lo, owner), thi = __shfl_sync(0xffffffffu, rq.b8_hi, owner);
         const uint32_t cur = S.res_key[owner] >> 16;          // the owner's best from earlier rounds: all of them nearer
         const uint32_t s0 = st > cur ? st : cur;
-        bool alive = have && s0 < ml;
-        uint32_t mine = 0, l = kEntryBytes;
-        if (alive) {
-            const uint32_t bq = A.in[q + s0], bp = A.in[po + s0];
-            const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
-            if (bq != bp) alive = false;
-            else if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
-            else if (l + 8u >= ml) { mine = ml; alive = false; }
+        uint32_t mine = 0;
+        bool alive = false;
+        if (have && s0 < ml) {
+            const uint32_t xlo = cb8.x ^ tlo, xhi = cb8.y ^ thi;
+            if (xlo) mine = kEntryBytes + ((uint32_t)(__ffs((int)xlo) - 1) >> 3);
+            else if (xhi) mine = kEntryBytes + 4u + ((uint32_t)(__ffs((int)xhi) - 1) >> 3);
+            else if (ml <= 2u * kEntryBytes) mine = ml;
+            else alive = (s0 < 2u * kEntryBytes) || (A.in[q + s0] == A.in[po + s0]);
         }
-        l += 8u;
+        uint32_t l = 2u * kEntryBytes;
         while (__any_sync(0xffffffffu, alive)) {              // lock step: l is the same in every lane that is alive
             if (alive) {
                 const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
@@ -688,13 +702,17 @@ __device__ __forceinline__ Owner resolve_owner(const Resolve& rq, int j) {
     o.lo = __shfl_sync(0xffffffffu, rq.me_lo, j); o.hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
     return o;
 }
-// Entries of visits kb + 32 t + lane, t = 0..3 (up to 128 entries of one owner in flight).
+// Entries of visits kb + 32 t + lane, t = 0..3 (up to 128 entries of one owner in flight); slots past the owner's
+// last visit are not touched.
 __device__ __forceinline__ void resolve_load4(const ParseArgs& A, const Owner& o, uint32_t kb, uint2 e[4]) {
+    const uint2* Kw = A.K + (size_t)(o.p >> 15) * kWindow;
+    const uint2* pa = Kw + (o.rank - 1u);                 // visit k of the own window: pa - k
+    const uint2* pb = Kw - kWindow + (o.pe - 1u + o.n_own);   // visit k of the previous window: pb - k
 #pragma unroll
     for (uint32_t t = 0; t < 4; t++) {
         const uint32_t k = kb + t * 32u + lane_id();
         e[t] = make_uint2(0u, 0u);
-        if (k < o.n_vis) e[t] = __ldg(resolve_entry(A, o.p >> 15, o.rank, o.n_own, o.pe, k));
+        if (k < o.n_vis) e[t] = __ldg((k < o.n_own ? pa : pb) - k);
     }
 }
 
@@ -716,7 +734,7 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
     bool running = work, parked = false, have_m = false, rq_quarter = false;
     uint32_t m_ready = 0, rq_budget = 0;
     Resolve rq;
-    rq.p = rq.rank = rq.k0 = rq.start = rq.maxl = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = 0;
+    rq.p = rq.rank = rq.k0 = rq.start = rq.maxl = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = rq.b8_lo = rq.b8_hi = 0;
     // the hand-off key carries the pending match's distance: looked up here, once per segment boundary
     auto state_key = [&](const ParseState& x) -> uint32_t {
         uint32_t d = 0;
@@ -782,16 +800,19 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                     const int j = __ffs((int)left) - 1;
                     left &= left - 1u;
                     const uint32_t base = __shfl_sync(0xffffffffu, mine, j);
-                    const uint32_t q = base + 4u * lane;                      // this lane converts records q .. q + 3
-                    uint32_t codes = 0;
-                    if (q + 4u <= n && ((reinterpret_cast<uintptr_t>(A.Mf + q) & 15u) == 0)) {
-                        const uint4 r = __ldg(reinterpret_cast<const uint4*>(A.Mf + q));
-                        codes = rec_len_code(r.x) | (rec_len_code(r.y) << 8) | (rec_len_code(r.z) << 16) | (rec_len_code(r.w) << 24);
-                    } else {
 #pragma unroll
-                        for (uint32_t t = 0; t < 4; t++) if (q + t < n) codes |= rec_len_code(A.Mf[q + t]) << (8u * t);
+                    for (uint32_t u = 0; u < kLcWords / 32u; u++) {
+                        const uint32_t q = base + 4u * (u * 32u + lane);      // this lane converts records q .. q + 3
+                        uint32_t codes = 0;
+                        if (q + 4u <= n && ((reinterpret_cast<uintptr_t>(A.Mf + q) & 15u) == 0)) {
+                            const uint4 r = __ldg(reinterpret_cast<const uint4*>(A.Mf + q));
+                            codes = rec_len_code(r.x) | (rec_len_code(r.y) << 8) | (rec_len_code(r.z) << 16) | (rec_len_code(r.w) << 24);
+                        } else {
+#pragma unroll
+                            for (uint32_t t = 0; t < 4; t++) if (q + t < n) codes |= rec_len_code(A.Mf[q + t]) << (8u * t);
+                        }
+                        S.lc[(uint32_t)j * (kLcWords + 1u) + u * 32u + lane] = codes;
                     }
-                    S.lc[(uint32_t)j * (kLcWords + 1u) + lane] = codes;
                 }
                 if ((want >> lane) & 1u) cb = mine;
                 __syncwarp();
@@ -833,6 +854,7 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                 if (kb != o.k0) resolve_load4(A, o, kb, e);      // chain budgets above 128 only
 #pragma unroll
                 for (uint32_t t = 0; t < 4; t++) {
+                    if (kb + t * 32u >= o.n_vis) break;          // warp-uniform: the owner has no visits in this slot
                     const uint32_t k = kb + t * 32u + lane;
                     const bool val = k < o.n_vis, own = k < o.n_own;
                     const uint32_t ep = entry_pos(e[t].y);
@@ -843,8 +865,10 @@ __device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint3
                         if (cnt + 32u > kCandCap) { __syncwarp(); resolve_compare(A, S, cnt, rq, last_word); cnt = 0; }
                         if (eq) {
                             const uint32_t at = cnt + __popc(mk & ((1u << lane) - 1u));
-                            S.cand_q[at] = (own ? w : w - 1u) * kWindow + ep;
+                            const uint32_t cw = own ? w : w - 1u;
+                            S.cand_q[at] = cw * kWindow + ep;
                             S.cand_meta[at] = (uint32_t)j | (k << 5);
+                            S.cand_b8[at] = __ldg(A.K2 + (size_t)cw * kWindow + (own ? o.rank - 1u - k : o.pe - 1u - (k - o.n_own)));
                         }
                         cnt += __popc(mk);
                     }
@@ -882,8 +906,12 @@ __global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_spec(Pa
     __shared__ ParseShared sh[kParseWarps];
     // The lanes of a warp take segments far apart (stride = number of warps in the grid): the cost of a segment
     // depends on the kind of data, neighbouring segments are of one kind, and a warp is as slow as its slowest lane.
+#ifndef DFL_PARSE_STRIDED
+#define DFL_PARSE_STRIDED 1
+#endif
     const uint32_t n_warps = gridDim.x * kParseWarps;
-    const uint32_t s = lane_id() * n_warps + blockIdx.x * kParseWarps + warp_id();
+    const uint32_t s = DFL_PARSE_STRIDED ? lane_id() * n_warps + blockIdx.x * kParseWarps + warp_id()
+                                         : blockIdx.x * blockDim.x + threadIdx.x;
     const bool work = s < A.n_seg;
     uint32_t a = 0, b = 0;
     ParseState st = parse_state_init(0);
@@ -1709,7 +1737,7 @@ uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 
 static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     ParseArgs A;
     A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
-    A.K = b.K; A.off = b.off;
+    A.K = b.K; A.off = b.off; A.K2 = b.K2;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
@@ -1750,7 +1778,7 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, 
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
-    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.off);
+    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.K2, b.off);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
