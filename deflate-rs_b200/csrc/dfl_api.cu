@@ -338,14 +338,15 @@ struct Context {
     }
     void free_buffers() {
         Buffers& b = buf;
-        dev_free(b.K); dev_free(b.R); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.segtok);
+        dev_free(b.K); dev_free(b.K2); dev_free(b.off); dev_free(b.seq_tab); dev_free(b.Mf); dev_free(b.Mq); dev_free(b.segtok);
         dev_free(b.seg_e_pos); dev_free(b.seg_e_key); dev_free(b.seg_e_tok);
         dev_free(b.seg_x_pos); dev_free(b.seg_x_key); dev_free(b.seg_x_tok);
-        dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad); dev_free(b.seg_bad_list);
+        dev_free(b.seg_start_pos); dev_free(b.seg_start_key); dev_free(b.seg_bad);
         dev_free(b.seg_cnt); dev_free(b.seg_off); dev_free(b.hist); dev_free(b.cost); dev_free(b.tables);
         dev_free(b.blk_type); dev_free(b.blk_bit); dev_free(b.blk_in); dev_free(b.adler_part);
         b.tok = nullptr;
         b.cap_n = 0;
+        b.cap_quarter = false;
     }
     ~Context() {
         if (!ok) return;
@@ -362,23 +363,26 @@ struct Context {
     }
 
     // Scratch for inputs of up to n bytes (history + payload).
-    int ensure(size_t n) {
+    int ensure(size_t n, bool quarter) {
         Buffers& b = buf;
-        if (b.cap_n >= n && b.cap_n > 0) return DFL_OK;
+        if (b.cap_n >= n && b.cap_n > 0 && (b.cap_quarter || !quarter)) return DFL_OK;
         size_t cap = n + n / 8 + 65536;
         if (cap < b.cap_n) cap = b.cap_n;      // growing one kind of scratch never shrinks another
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
         if (cap < n) return DFL_E_ARG;
         cudaStreamSynchronize(stream);
+        quarter = quarter || b.cap_quarter;
         free_buffers();
         size_t n_win = (cap + kWindow - 1) / kWindow + 1;
-        size_t n_seg = parse_max_segments(cap);
+        size_t n_seg = (cap + 1023) / 1024 + 1;   // the shortest parse segment (parse_geom) gives the most segments
         size_t n_blk = max_blocks_for((uint32_t)cap) + 1;
         size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
         int rc = 0;
         if ((rc = dev_alloc(b.K, n_win * kWindow))) return rc;
-        if ((rc = dev_alloc(b.R, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.K2, n_win * kWindow))) return rc;
         if ((rc = dev_alloc(b.off, n_win * kWindow))) return rc;
+        if ((rc = dev_alloc(b.Mf, cap))) return rc;
+        if (quarter && (rc = dev_alloc(b.Mq, cap))) return rc;
         if ((rc = dev_alloc(b.segtok, parse_buffer_words(cap)))) return rc;
         if ((rc = dev_alloc(b.seg_e_pos, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_e_key, n_seg))) return rc;
@@ -389,7 +393,6 @@ struct Context {
         if ((rc = dev_alloc(b.seg_start_pos, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_start_key, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_bad, n_seg))) return rc;
-        if ((rc = dev_alloc(b.seg_bad_list, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_cnt, n_seg))) return rc;
         if ((rc = dev_alloc(b.seg_off, n_seg))) return rc;
         if ((rc = dev_alloc(b.hist, n_blk * 320))) return rc;
@@ -399,8 +402,9 @@ struct Context {
         if ((rc = dev_alloc(b.blk_bit, n_blk + 1))) return rc;
         if ((rc = dev_alloc(b.blk_in, n_blk + 1))) return rc;
         if ((rc = dev_alloc(b.adler_part, 2 * n_chunk))) return rc;
-        b.tok = reinterpret_cast<uint32_t*>(b.K);   // the candidate lists are dead once the parse has run; the token stream reuses them
+        b.tok = reinterpret_cast<uint32_t*>(b.K);   // the candidate lists are dead once k_match has run; the token stream reuses them
         b.cap_n = cap;
+        b.cap_quarter = quarter;
         return DFL_OK;
     }
     int ensure_stage(uint8_t*& p, size_t& cap, size_t need) {
@@ -534,7 +538,7 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     j.carry_bits_v = pin.bits_v;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return DFL_E_ARG;
 
-    int rc = c.ensure(n);
+    int rc = c.ensure(n, j.prm.need_quarter != 0);
     if (rc) return rc;
     Buffers& b = c.buf;
     CK(cudaMemsetAsync(b.meta, 0, sizeof(DevMeta), st));
@@ -550,11 +554,11 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
     const bool need_lz = (d_tokens_override == nullptr) && !seq_lz;
     const bool need_match = need_lz && j.prm.mode != kRle && j.prm.checks > 0;
     if (need_match) {
-        const uint32_t w_end = n_windows(j), w_sort0 = first_sort_window(j);
+        const uint32_t w_end = n_windows(j), w_sort0 = first_sort_window(j), w_match0 = first_match_window(j);
         if (arrival) {
-            // the input is still being copied: sort every window as soon as its bytes (and the 32 bytes behind it
-            // that its entries reach into) are on the device
-            uint32_t w_sorted = w_sort0;
+            // the input is still being copied: sort and match every window as soon as its bytes
+            // (and the 272 bytes of look-ahead behind it) are on the device
+            uint32_t w_sorted = w_sort0, w_matched = w_match0;
             for (size_t k = 0; k < arrival->n_slices; k++) {
                 { int frc = arrival->feed(k); if (frc) return frc; }
                 CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0));
@@ -563,11 +567,17 @@ int issue_pipeline(Context& c, cudaStream_t st, StageTimer& tm, const uint8_t* d
                 if (w_ok > w_end) w_ok = w_end;
                 CK(launch_window_sort(j, b, st, w_sorted, w_ok));
                 if (w_ok > w_sorted) w_sorted = w_ok;
+                CK(launch_match(j, b, st, w_matched, w_sorted));
+                if (w_sorted > w_matched) w_matched = w_sorted;
             }
-            tm.mark("window_sort");
+            tm.mark("window_sort+match");
         } else {
+            if (arrival)
+                for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
             CK(launch_window_sort(j, b, st, w_sort0, w_end));
             tm.mark("window_sort");
+            CK(launch_match(j, b, st, w_match0, w_end));
+            tm.mark("match");
         }
     } else if (arrival && !seq_lz) {
         for (size_t k = 0; k < arrival->n_slices; k++) { { int frc = arrival->feed(k); if (frc) return frc; } CK(cudaStreamWaitEvent(st, (*arrival->ev)[k], 0)); }
@@ -1054,7 +1064,7 @@ extern "C" int dfl_crc32_device(const void* d_in, size_t n, uint32_t* crc, void*
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
-    if ((rc = c.ensure(n ? n : 1))) return rc;
+    if ((rc = c.ensure(n ? n : 1, false))) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     CK(launch_crc32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -1068,7 +1078,7 @@ extern "C" int dfl_adler32_device(const void* d_in, size_t n, uint32_t* adler, v
     Context& c = tls_context();
     int rc = c.init();
     if (rc) return rc;
-    if ((rc = c.ensure(n ? n : 1))) return rc;
+    if ((rc = c.ensure(n ? n : 1, false))) return rc;
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c.stream;
     CK(launch_adler32(reinterpret_cast<const uint8_t*>(d_in), n, c.buf, st));
     CK(cudaMemcpyAsync(c.h_meta, c.buf.meta, sizeof(DevMeta), cudaMemcpyDeviceToHost, st));
@@ -1359,7 +1369,7 @@ int encoder_fold_checksum(dfl_encoder* e, const StreamBuf& b, uint64_t to) {
     if (e->wrap == DFL_RAW || to <= e->sum_off) { if (to > e->sum_off) e->sum_off = to; return DFL_OK; }
     Context& c = *e->ctx;
     const size_t len = (size_t)(to - e->sum_off);
-    int rc = c.ensure(len);
+    int rc = c.ensure(len, false);
     if (rc) return rc;
     CK(cudaEventRecord(e->in_ev, c.copy_stream));
     CK(cudaStreamWaitEvent(c.stream, e->in_ev, 0));

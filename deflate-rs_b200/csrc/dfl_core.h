@@ -98,19 +98,55 @@ DFL_HD uint32_t entry_lcp(uint32_t xlo, uint32_t xhi) {
     return (xhi & 0xffu) ? 7u : 8u;
 }
 
-DFL_HD uint32_t ilog2(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-    return 31u - (uint32_t)__clz((int)x);
-#else
-    return 31u - (uint32_t)__builtin_clz(x);
-#endif
+// ---------------------------------------------------------------- candidate walk
+// One longest_match call (matching.rs:87-166) visits its candidates most recent first and keeps the first one
+// that is strictly longer than the running best, so the nearest candidate wins ties (:148-157).  The pipeline
+// splits that work in two:
+//   * the match stage (kernel k_match) walks the candidate *entries* only.  An entry proves common prefixes of
+//     up to 8 bytes exactly, so every result shorter than 8 bytes is final there; a position whose best
+//     candidate shares all 8 entry bytes is recorded as "long": only its rank in the window's sorted list and
+//     the visit index of the nearest such candidate are kept.
+//   * the parse stage resolves a long record on the data -- but only at the positions the reference's parser
+//     actually searches (lz77.rs:340-377 skips everything inside an emitted match).
+// best_len == 1 means "nothing yet" (matching.rs:108 floors the running best at 1; results shorter than
+// MIN_MATCH are discarded by both parsers, so they are never recorded).
+struct EntryWalk {
+    uint32_t best_len;    // 1, or 3..8 as proven by entries (clamped to the bytes left in the input)
+    uint32_t best_pos;    // position-in-window field of the best candidate
+    uint32_t best_k;      // its visit index (0 = nearest candidate)
+    uint32_t mlo, mhi;    // entry_mask(best_len)
+    uint32_t stop;        // nothing can be longer as far as entries can tell (8 bytes, or the end of the input)
+};
+DFL_HD EntryWalk ewalk_init() {
+    EntryWalk s; s.best_len = 1; s.best_pos = 0; s.best_k = 0; s.stop = 0; entry_mask(1, s.mlo, s.mhi); return s;
+}
+// Visit number k: candidate entry `ce` against target entry `me`; maxl = min(258, bytes left at the target).
+DFL_HD void ewalk_visit(EntryWalk& s, Entry me, Entry ce, uint32_t k, uint32_t maxl) {
+    if (s.stop) return;
+    if ((((ce.lo ^ me.lo) & s.mlo) | ((ce.hi ^ me.hi) & s.mhi)) != 0u) return;
+    uint32_t l = entry_lcp(ce.lo ^ me.lo, ce.hi ^ me.hi);
+    if (l > maxl) l = maxl;
+    if (l > s.best_len) {
+        s.best_len = l; s.best_pos = entry_pos(ce.hi); s.best_k = k;
+        entry_mask(l, s.mlo, s.mhi);
+        if (l >= kEntryBytes || l == maxl) s.stop = 1;
+    }
 }
 
 // ---------------------------------------------------------------- per-position match record
-// len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23; 0 == "no usable match".
+// Final:  len in bits 0..8 (0 or 3..258), dist-1 in bits 9..23; 0 == "no usable match".
+// Long (bit 31): the best candidate shares >= 8 bytes and more bytes are left to compare.  Bits 0..14 = rank
+// of the position in its window's sorted list, bits 15..30 = visit index of the nearest candidate that shares
+// 8 bytes (every nearer one shares fewer, so a resolution starts there).
+constexpr uint32_t kRecLong = 0x80000000u;
+constexpr uint32_t kLenLong = 0xffu;     // length code (one byte per position beside the record): the record is long
 DFL_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return len | ((dist - 1u) << 9); }
 DFL_HD uint32_t match_len(uint32_t m) { return m & 0x1ffu; }
 DFL_HD uint32_t match_dist(uint32_t m) { return ((m >> 9) & 0x7fffu) + 1u; }
+DFL_HD uint32_t rec_long(uint32_t rank, uint32_t k8) { return kRecLong | rank | (k8 << 15); }
+DFL_HD bool rec_is_long(uint32_t m) { return (m & kRecLong) != 0u; }
+DFL_HD uint32_t rec_rank(uint32_t m) { return m & 0x7fffu; }
+DFL_HD uint32_t rec_k8(uint32_t m) { return (m >> 15) & 0xffffu; }
 // lz77.rs:274-278 match_too_far applied to the result of matching.rs:87-166; results shorter than
 // MIN_MATCH are never used by either parser and are recorded as "no match".
 DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
@@ -118,208 +154,20 @@ DFL_HD uint32_t finalize_match(uint32_t len, uint32_t dist) {
     if (len == kMinMatch && dist > kTooFar) return 0u;
     return pack_match(len, dist);
 }
-
-// ---------------------------------------------------------------- one longest_match call
-// The search the reference runs at a position its parser examines (matching.rs:87-166), over the per-window
-// sorted candidate lists instead of the head/prev chains: the candidates of position p are the entries in
-// front of p's own entry in its bucket, most recent first, then the tail of the same bucket of the previous
-// window at distance <= 32768 (matching.rs:102-106,127), at most `budget` (max_hash_checks, or a quarter of
-// it, lz77.rs:351-355) in total.  The first candidate strictly longer than the running best wins, so the
-// nearest one wins ties (:148-157); the running best starts at the floor max(prev_length, 1) (:108).
-//
-// It is written as a resumable state machine because the parse kernel interleaves the searches of the 32
-// lanes of a warp (a lane per parse segment): search_begin sets a search up, search_walk visits up to eight
-// candidate entries (one aligned 64-byte group of the list), search_long compares one candidate that shares
-// all 8 entry bytes with the target on the data, 8 bytes per call.  tests/model drives the same functions
-// sequentially.
-//   A visit costs a masked compare of the 64-bit entries; the masks tighten as the running best grows, so
-// only a candidate that would be strictly longer (as far as 8 bytes can tell) gets a closer look.
-#if defined(__CUDA_ARCH__)
-#define DFL_LDG(ptr) __ldg(ptr)
-#else
-#define DFL_LDG(ptr) (*(ptr))
-#endif
-struct SearchIn {                // what every search of one encode call reads
-    const uint8_t* in; uint32_t n;
-    const uint32_t* last_word;   // last aligned 32-bit word that holds input (device loads stop there)
-    const Entry* K;              // sorted entries, 32768 per window
-    const uint16_t* off;         // bucket starts, 32768 per window
-    const uint16_t* R;           // rank of every position in its window's list
-};
-struct Search {
-    uint32_t p, maxl, floor;     // target, min(258, bytes left), floor of the running best
-    uint32_t me_lo, me_hi;       // the target's entry (position bits zero)
-    uint32_t mlo, mhi;           // entry_mask(best_len)
-    uint32_t best_len, best_dist;
-    uint32_t e, rem;             // next entry to visit (index into K) and entries left in this phase
-    uint32_t prev_e, prev_rem;   // the previous window's phase: first entry to visit, entries allowed (0 = none)
-    uint32_t q, ll;              // candidate being compared on the data, bytes known equal so far
-};
-enum SearchStatus : uint32_t { kSearchDone = 0, kSearchWalk = 1, kSearchLong = 2 };
-
-// 8 bytes at in[idx ..] (idx < n), little endian.  Bytes past the last word of the input read as 0; bytes past
-// the end inside the last word are whatever is there (callers clamp what they derive to the bytes that exist).
-DFL_HD unsigned long long load8(const SearchIn& si, uint32_t idx) {
-#if defined(__CUDA_ARCH__)
-    const uintptr_t a = reinterpret_cast<uintptr_t>(si.in + idx);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-    const uint32_t x0 = __ldg(w);
-    const uint32_t x1 = (w + 1 <= si.last_word) ? __ldg(w + 1) : 0u;
-    const uint32_t x2 = (w + 2 <= si.last_word) ? __ldg(w + 2) : 0u;
-    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
-    return ((unsigned long long)hi << 32) | lo;
-#else
-    unsigned long long v = 0;
-    for (uint32_t k = 0; k < 8u; k++) if (idx + k < si.n) v |= (unsigned long long)si.in[idx + k] << (8u * k);
-    return v;
-#endif
+// Length code of a record, one byte: what the parser needs in order to decide (the distance only matters once a
+// token is written).  0 = no match, 1..253 = length - 2, kLenSeeRecord = a final length of 256..258 (read it from
+// the record), kLenLong = the record is long.
+constexpr uint32_t kLenSeeRecord = 0xfeu;
+DFL_HD uint32_t rec_len_code(uint32_t rec) {
+    if (rec_is_long(rec)) return kLenLong;
+    const uint32_t l = match_len(rec);
+    return l == 0u ? 0u : (l <= 255u ? l - 2u : kLenSeeRecord);
 }
-DFL_HD uint32_t ctz64_bytes(unsigned long long x) {   // index of the lowest non-zero byte (x != 0)
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)(__ffsll((long long)x) - 1) >> 3;
-#else
-    return (uint32_t)__builtin_ctzll(x) >> 3;
-#endif
-}
-// The previous window's candidates, once the own window's are used up.
-DFL_HD bool search_next_phase(Search& S) {
-    if (S.prev_rem == 0u) return false;
-    S.e = S.prev_e; S.rem = S.prev_rem; S.prev_rem = 0u;
-    return true;
-}
-// Sets up the search at position p (p + 2 < n).  floor = prev_length of the lazy parser (0 for the greedy one).
-DFL_HD uint32_t search_begin(Search& S, const SearchIn& si, uint32_t p, uint32_t floor, uint32_t budget) {
-    const uint32_t w = p >> 15, pl = p & kWindowMask;
-    S.p = p;
-    S.maxl = (si.n - p) < kMaxMatch ? (si.n - p) : kMaxMatch;
-    S.floor = floor > 1u ? floor : 1u;                       // matching.rs:108
-    S.best_len = S.floor; S.best_dist = 0u;
-    S.rem = 0u; S.prev_rem = 0u; S.e = 0u; S.prev_e = 0u; S.q = 0u; S.ll = 0u;
-    S.me_lo = 0u; S.me_hi = 0u; S.mlo = 0u; S.mhi = 0u;
-    if (budget == 0u || S.best_len >= S.maxl) return kSearchDone;   // matching.rs:99-101
-    unsigned long long x = load8(si, p);
-    if (S.maxl < 8u) x &= (1ull << (8u * S.maxl)) - 1ull;    // entries hold zeros past the end of the input
-    const uint32_t v0 = (uint32_t)x, v1 = (uint32_t)(x >> 32);
-    const uint32_t b0 = v0 & 0xffu, b1 = (v0 >> 8) & 0xffu, b2 = (v0 >> 16) & 0xffu;
-    const uint32_t h = hash3(b0, b1, b2);
-    S.me_lo = (v0 >> 24) | (v1 << 8);
-    S.me_hi = (v1 >> 24) | (tag9(b0, b1) << 8);
-    entry_mask(S.best_len, S.mlo, S.mhi);
-    const uint32_t i = DFL_LDG(si.R + p);
-    const uint16_t* ow = si.off + (size_t)w * kWindow;
-    const uint32_t s0 = DFL_LDG(ow + h);
-    const uint32_t n_own = i - s0 < budget ? i - s0 : budget;
-    S.e = w * kWindow + i - 1u; S.rem = n_own;
-    if (w > 0u && n_own < budget) {
-        // previous window: the newest entries of the same bucket; those at a distance above 32768 end the walk
-        const uint16_t* op = ow - kWindow;
-        const uint32_t ps = DFL_LDG(op + h);
-        const uint32_t pe = (h + 1u < kWindow) ? (uint32_t)DFL_LDG(op + h + 1u) : kWindow;
-        const uint32_t left = budget - n_own;
-        S.prev_rem = pe - ps < left ? pe - ps : left;
-        S.prev_e = (w - 1u) * kWindow + pe - 1u;
-    }
-    (void)pl;
-    if (S.rem == 0u && !search_next_phase(S)) return kSearchDone;
-#if defined(__CUDA_ARCH__)
-    // the list is read newest to oldest, a 64-byte group per visit: ask for the line behind the first one now
-    if (S.rem > 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(si.K + ((S.e & ~15u) - 16u)));
-#endif
-    return kSearchWalk;
-}
-// Visits the entries of one aligned group of eight (64 bytes of the list), newest first.  All eight are tested
-// against the masks at once -- in almost every group nothing passes.  Once the running best has reached 8 bytes the
-// masks cover the whole entry and what passes are candidates that share all 8 entry bytes; those are thinned out,
-// again all at once, by the reference's quick reject: the byte that would make a candidate longer than the running
-// best (matching.rs:141-143).  Whatever is left is looked at one candidate at a time, nearest first, and after
-// every improvement the rest of the group is tested again with the tighter masks.
-constexpr uint32_t kGroup = 8;
-DFL_HD uint32_t search_walk(Search& S, const SearchIn& si) {
-    const uint32_t g = S.e & ~(kGroup - 1u);
-    const uint32_t hi_u = S.e - g;
-    const uint32_t t = S.rem < hi_u + 1u ? S.rem : hi_u + 1u;       // entries of this group that are visited ...
-    const uint32_t lo_u = hi_u + 1u - t;                            // ... slots lo_u .. hi_u
-    uint32_t valid = ((2u << hi_u) - 1u) & ~((1u << lo_u) - 1u);    // slots still to be looked at
-    uint32_t elo[kGroup], ehi[kGroup];
-#if defined(__CUDA_ARCH__)
-    {
-        const uint4* g4 = reinterpret_cast<const uint4*>(si.K + g);
-        const uint4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2), d = __ldg(g4 + 3);
-        elo[0] = a.x; ehi[0] = a.y; elo[1] = a.z; ehi[1] = a.w; elo[2] = b.x; ehi[2] = b.y; elo[3] = b.z; ehi[3] = b.w;
-        elo[4] = c.x; ehi[4] = c.y; elo[5] = c.z; ehi[5] = c.w; elo[6] = d.x; ehi[6] = d.y; elo[7] = d.z; ehi[7] = d.w;
-    }
-#else
-    for (uint32_t u = 0; u < kGroup; u++) { elo[u] = si.K[g + u].lo; ehi[u] = si.K[g + u].hi; }
-#endif
-    S.e -= t; S.rem -= t;                                           // the whole group, unless a candidate goes to the data
-    for (;;) {
-        uint32_t pm = 0u;                                           // slots whose entry passes the masks
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t u = 0; u < kGroup; u++)
-            pm |= ((((elo[u] ^ S.me_lo) & S.mlo) | ((ehi[u] ^ S.me_hi) & S.mhi)) == 0u) ? (1u << u) : 0u;
-        pm &= valid;
-        if (pm == 0u) break;
-        if (S.best_len >= kEntryBytes) {                            // every one of them shares the 8 entry bytes: quick reject
-            const uint32_t tb = DFL_LDG(si.in + S.p + S.best_len);
-            const uint32_t qb = (g & ~kWindowMask) + S.best_len;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (uint32_t u = 0; u < kGroup; u++)
-                if ((pm >> u) & 1u) { if (DFL_LDG(si.in + qb + entry_pos(ehi[u])) != tb) pm ^= 1u << u; }
-            if (pm == 0u) break;
-        }
-        const uint32_t u = ilog2(pm);                               // the nearest one first
-        valid &= (1u << u) - 1u;
-        const uint32_t idx = g + u;
-        const Entry c = {DFL_LDG(&si.K[idx].lo), DFL_LDG(&si.K[idx].hi)};   // (in L1: the group has just been loaded)
-        const uint32_t xlo = c.lo ^ S.me_lo, xhi = c.hi ^ S.me_hi;
-        // the candidate shares more bytes with the target than the running best, as far as the entries can tell
-        const uint32_t q = (idx & ~kWindowMask) | entry_pos(c.hi);
-        if (S.p - q > kWindow) return kSearchDone;                  // beyond the window, and so is everything older (matching.rs:127)
-        uint32_t l = entry_lcp(xlo, xhi);
-        l = l < S.maxl ? l : S.maxl;
-        if (l >= kEntryBytes && l < S.maxl) {                       // all 8 entry bytes agree and there are more: look at the data
-            S.q = q; S.ll = kEntryBytes;
-            const uint32_t undone = u - lo_u;                       // slots older than this one: back on the list
-            S.e += undone; S.rem += undone;
-            return kSearchLong;
-        }
-        if (l > S.best_len) {                                       // strictly longer: the nearest candidate wins ties
-            S.best_len = l; S.best_dist = S.p - q;
-            entry_mask(l, S.mlo, S.mhi);
-            if (l == S.maxl) return kSearchDone;                    // matching.rs:152-156
-        }
-    }
-    if (S.rem == 0u && !search_next_phase(S)) return kSearchDone;
-    return kSearchWalk;
-}
-// Compares the next 8 bytes of target and candidate.
-DFL_HD uint32_t search_long(Search& S, const SearchIn& si) {
-    const unsigned long long x = load8(si, S.p + S.ll) ^ load8(si, S.q + S.ll);
-    uint32_t l;
-    if (x == 0ull) {
-        S.ll += 8u;
-        if (S.ll < S.maxl) return kSearchLong;
-        l = S.maxl;
-    } else {
-        l = S.ll + ctz64_bytes(x);
-        l = l < S.maxl ? l : S.maxl;
-    }
-    if (l > S.best_len) {
-        S.best_len = l; S.best_dist = S.p - S.q;
-        S.mlo = 0xffffffffu; S.mhi = kEntryKeyHi;            // from 8 bytes on every key bit must agree
-        if (l == S.maxl) return kSearchDone;
-    }
-    if (S.rem == 0u && !search_next_phase(S)) return kSearchDone;
-    return kSearchWalk;
-}
-// The result as longest_match returns it (matching.rs:161-165) with lz77.rs:274-278 applied: a match record, 0 = none.
-DFL_HD uint32_t search_result(const Search& S) {
-    return S.best_len > S.floor ? finalize_match(S.best_len, S.best_dist) : 0u;
+// Record of a finished entry walk.  `rank` = index of the target in its window's sorted list, `dist` = distance
+// of the best candidate.
+DFL_HD uint32_t ewalk_record(const EntryWalk& s, uint32_t rank, uint32_t dist, uint32_t maxl) {
+    if (s.best_len >= kEntryBytes && maxl > kEntryBytes) return rec_long(rank, s.best_k);
+    return finalize_match(s.best_len, dist);
 }
 
 // ---------------------------------------------------------------- tokens
@@ -334,6 +182,13 @@ DFL_HD uint32_t tok_input_len(uint32_t t) { return (t >> 9) ? (t & 0x1ffu) : 1u;
 // Closed forms of the lookup tables in huffman_table.rs:45-111 (LENGTH_CODE/BASE_LENGTH/
 // LENGTH_EXTRA_BITS_LENGTH, DISTANCE_CODES/DISTANCE_BASE and num_extra_bits_for_distance_code);
 // tests/test_model.py checks them against the tables parsed from the reference source.
+DFL_HD uint32_t ilog2(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)x);
+#else
+    return 31u - (uint32_t)__builtin_clz(x);
+#endif
+}
 // length 3..258 -> (code 257..285, extra bit count, extra value)
 DFL_HD void length_symbol(uint32_t len, uint32_t& code, uint32_t& nextra, uint32_t& extra) {
     uint32_t l = len - kMinMatch;

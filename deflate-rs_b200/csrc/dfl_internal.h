@@ -8,47 +8,39 @@
 
 namespace dfl {
 
-// Geometry of the parse stage (see DESIGN.md "parse").  A parse lane walks its segment sequentially and then takes
-// the next one from a counter, so segments are short: the supply of segments is what keeps the lanes of a warp
-// busy while some of them wait for their kind of work to come up, and for small inputs the number of segments is
-// the parallelism there is.  Every segment is started `warm` bytes early from a blank state (any geometry gives
-// the same tokens: hand-offs are verified and repaired); the warm-up is parsed twice, so it is short -- on the
-// benchmark mix 64 bytes already resynchronise 99.9 % of all segments.  seg + warm + 264 tokens of buffer per segment.
+// Tunables of the parse stage (see DESIGN.md "parse").
 #ifndef DFL_PARSE_SEG
-#define DFL_PARSE_SEG 1024
+#define DFL_PARSE_SEG 4096
 #endif
 #ifndef DFL_PARSE_WARM
-#define DFL_PARSE_WARM 128
+#define DFL_PARSE_WARM 512
 #endif
-constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse segment (large inputs)
+constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread (large inputs)
 constexpr uint32_t kParseWarm = DFL_PARSE_WARM;   // speculative warm-up before the segment start
+// One parse thread walks its segment sequentially, so for small inputs the segment length *is* the
+// latency of the stage: shorter segments there (any length gives the same tokens, hand-offs are
+// verified and repaired).  seg + warm + 264 tokens of buffer per segment.
+// The greedy parser (Compression::Fast) does less per position and prefers longer segments on large inputs
+// (1 GiB: 4.5 ms with 8 KiB + 1 KiB, 5.9 ms with 4 KiB + 512 B; the lazy parser 7.8 against 7.1 ms).
 struct ParseGeom { uint32_t seg, warm; };
 inline ParseGeom parse_geom(size_t payload, int mode) {
-    (void)mode;
-    if (payload <= (8u << 20)) return {256u, 64u};
-    if (payload <= (64u << 20)) return {512u, 128u};
+    if (payload <= (32u << 20)) return {1024u, 512u};
+    if (payload <= (256u << 20)) return {2048u, 512u};
+    if (mode == kGreedy) return {2u * kParseSeg, 2u * kParseWarm};
     return {kParseSeg, kParseWarm};
 }
 inline uint32_t parse_tok_cap(ParseGeom g) { return g.seg + g.warm + 264u; }
 inline size_t parse_n_seg(size_t payload, ParseGeom g) { return (payload + g.seg - 1) / g.seg; }
-// u32 words of segment token buffers / number of segments needed for a payload of at most `cap` bytes, whatever its geometry
+// u32 words of segment token buffers needed for a payload of at most `cap` bytes, whatever its geometry
 inline size_t parse_buffer_words(size_t cap) {
     size_t best = 0;
-    const size_t edges[3] = {cap < (8u << 20) ? cap : (8u << 20), cap < (64u << 20) ? cap : (64u << 20), cap};
-    for (size_t e : edges) {
-        ParseGeom g = parse_geom(e, kLazy);
-        size_t w = (parse_n_seg(e, g) + 1) * parse_tok_cap(g);
-        if (w > best) best = w;
-    }
-    return best;
-}
-inline size_t parse_max_segments(size_t cap) {
-    size_t best = 0;
-    const size_t edges[3] = {cap < (8u << 20) ? cap : (8u << 20), cap < (64u << 20) ? cap : (64u << 20), cap};
-    for (size_t e : edges) {
-        size_t w = parse_n_seg(e, parse_geom(e, kLazy)) + 1;
-        if (w > best) best = w;
-    }
+    const size_t edges[3] = {cap < (32u << 20) ? cap : (32u << 20), cap < (256u << 20) ? cap : (256u << 20), cap};
+    for (size_t e : edges)
+        for (int mode : {(int)kGreedy, (int)kLazy}) {
+            ParseGeom g = parse_geom(e, mode);
+            size_t w = (parse_n_seg(e, g) + 1) * parse_tok_cap(g);
+            if (w > best) best = w;
+        }
     return best;
 }
 // Parallel repair rounds before the sequential fallback; every second one predicts the phase of chains of
@@ -66,7 +58,6 @@ struct DevMeta {
     uint32_t adler;
     uint32_t crc;                     // CRC-32 of the payload (gzip)
     uint32_t n_bad;                   // segments whose hand-off check failed in the latest verify
-    uint32_t fetch;                   // segments (or bad-list entries) handed out beyond the first one of every parse lane
     uint32_t n_repaired_par;
     uint32_t n_repaired_seq;
     uint32_t n_stored;
@@ -101,8 +92,10 @@ struct BlockTables {
 
 struct Buffers {   // device scratch of one context, grown on demand
     uint2* K = nullptr;             // candidate entries in bucket order (dfl_core.h Entry), n_windows * 32768
-    uint16_t* R = nullptr;          // rank of every position in its window's list (R[p] indexes K within p's window)
+    uint2* K2 = nullptr;            // bytes 8..15 of every entry of K, same order (the parse stage settles common prefixes below 16 from it)
     uint16_t* off = nullptr;        // bucket start offsets, n_windows * 32768
+    uint32_t* Mf = nullptr;         // per-position match (full chain budget)
+    uint32_t* Mq = nullptr;         // per-position match (quarter budget), only if needed
     uint32_t* segtok = nullptr;     // per parse segment token buffers, n_pseg * parse_tok_cap
     uint32_t* seg_e_pos = nullptr;  // hand-off records (SoA), n_pseg each
     uint32_t* seg_e_key = nullptr;
@@ -113,7 +106,6 @@ struct Buffers {   // device scratch of one context, grown on demand
     uint32_t* seg_start_pos = nullptr;   // repair start states
     uint32_t* seg_start_key = nullptr;
     uint8_t* seg_bad = nullptr;
-    uint32_t* seg_bad_list = nullptr;    // the bad segments of the latest verify, in no particular order
     uint32_t* seg_cnt = nullptr;    // valid tokens per segment
     unsigned long long* seg_off = nullptr;   // exclusive prefix of seg_cnt
     uint32_t* seq_tab = nullptr;    // head / prev chains of the sequential lazy < 3 path (3 x 32768 words), on first use
@@ -127,6 +119,7 @@ struct Buffers {   // device scratch of one context, grown on demand
     unsigned long long* adler_part = nullptr;// per chunk (A, B) sums
     DevMeta* meta = nullptr;
     size_t cap_n = 0;               // input size the buffers were sized for
+    bool cap_quarter = false;
 };
 
 // MatchingType::Lazy with lazy_if_less_than < 3 on a one-shot stream takes the sequential kernel (k_lz77_seq):
@@ -164,8 +157,10 @@ constexpr uint32_t kAdlerChunk = 1u << 16;
 
 // Stage launchers (dfl_kernels.cu).  All asynchronous on `st`.
 uint32_t n_windows(const EncodeJob& j);
+uint32_t first_match_window(const EncodeJob& j);
 uint32_t first_sort_window(const EncodeJob& j);
 cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi);
 cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_lz77_seq(const EncodeJob& j, Buffers& b, cudaStream_t st);
 cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st);

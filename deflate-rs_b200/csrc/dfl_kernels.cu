@@ -4,11 +4,10 @@
 //   k_window_sort   per 32 KiB window: stable counting sort of positions by the reference's 15-bit
 //                   3-byte hash -> contiguous most-recent-first candidate lists (replaces the
 //                   head/prev chains of chained_hash_table.rs)
-//   k_parse*        greedy / lazy / RLE token selection (lz77.rs:305-547, rle.rs:23-71) run speculatively
-//                   per segment with the search at every position the parser examines fused in: the
-//                   longest match among the first `max_hash_checks` candidates, nearest wins ties
-//                   (matching.rs:87-166), too-far rule (lz77.rs:274-278); hand-offs verified,
-//                   mismatches re-parsed
+//   k_match         per sorted entry: longest match among the first `max_hash_checks` candidates,
+//                   nearest wins ties (matching.rs:87-166), too-far rule (lz77.rs:274-278)
+//   k_parse*        greedy / lazy / RLE token selection (lz77.rs:305-547, rle.rs:23-71) run
+//                   speculatively per 8 KiB segment, hand-offs verified, mismatches re-parsed
 //   k_seg_scan, k_compact   token stream layout
 //   k_block_stats   286+30 bin histograms per 31744-token block (output_writer.rs:19,47-65)
 //   k_block_codes   code lengths, canonical codes, header RLE, costs (huffman_lengths.rs:167-287)
@@ -137,7 +136,7 @@ __device__ __forceinline__ uint32_t sort_slot_of(uint32_t w) { return (w & ~31u)
 
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
-                                                                 uint16_t* __restrict__ R, uint16_t* __restrict__ off) {
+                                                                 uint2* __restrict__ K2, uint16_t* __restrict__ off) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* cntw = reinterpret_cast<uint32_t*>(smem);                        // kSortCntWords
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem);
@@ -245,22 +244,13 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
         __syncthreads();
     }
 
-    // ---- ranks: R[pos] = index of the position's entry, gathered in the (dead) counter area and written out coalesced
-    {
-        uint16_t* rs = reinterpret_cast<uint16_t*>(smem);
-        for (uint32_t r = t; r < cnt; r += kSortThreads) rs[buf[r + (r >> 5)] & 0x7fffu] = (uint16_t)r;
-        __syncthreads();
-        uint4* R4 = reinterpret_cast<uint4*>(R + (size_t)w * kWindow);
-        const uint4* s4 = reinterpret_cast<const uint4*>(smem);
-        for (uint32_t i = t; i < kWindow * 2u / 16u; i += kSortThreads) R4[i] = s4[i];
-        __syncthreads();
-    }
     // ---- output: entries in bucket order
     {
-    stage_bytes(smem, in, (long long)base, kWindow + 32, n);   // bytes again
+    stage_bytes(smem, in, (long long)base, kWindow + 32, n);   // counters are dead; bytes again
     __syncthreads();
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
     uint2* Kw = K + (size_t)w * kWindow;
+    uint2* K2w = K2 + (size_t)w * kWindow;
     for (uint32_t r = t; r < kWindow; r += kSortThreads) {
         uint2 e = make_uint2(0u, 0xfffe0000u);               // filler beyond cnt; never read as a candidate
         if (r < cnt) {
@@ -272,6 +262,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
             uint32_t v1 = __funnelshift_r(w1, w2, sh);       // bytes 4..7
             e.x = (v0 >> 24) | (v1 << 8);                    // bytes 3..6
             e.y = (v1 >> 24) | (tag9(v0 & 0xffu, (v0 >> 8) & 0xffu) << 8) | (pos << 17);
+            // bytes 8..15, for the parse stage: what decides between candidates that share the 8 entry bytes
+            const uint32_t w3 = sw[a + 3], w4 = sw[a + 4];
+            K2w[r] = make_uint2(__funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
         }
         Kw[r] = e;
     }
@@ -330,23 +323,234 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
 }
 
 // =====================================================================================
-// parse: the reference's token selection (lz77.rs:305-547, rle.rs:23-71) with its searches (matching.rs:87-166)
-// fused in, one lane per parse segment.
-//   Only the positions the reference's parser examines are ever searched: everything inside an emitted match is
-// skipped (lz77.rs:398-405) -- on the benchmark mix that is 70 % of all positions and 82 % of all candidate
-// visits.  A lane is a small state machine: STEP (one parser iteration: apply the result of the search that has
-// just finished, check the segment bounds, set up the search at the next position), WALK (visit one aligned
-// group of four candidate entries, dfl_core.h search_walk), LONG (compare 8 more bytes of a candidate that
-// shares all 8 entry bytes, search_long).  The warp runs one kind of section at a time for all lanes that are in
-// that state and picks the section that serves the most lanes per instruction (with ageing, so that a few lanes
-// in a rare state are not starved): lanes in different states never execute each other's code.
+// k_match: one CTA per window; a thread owns one sorted entry (the target) and visits its candidates
+// most recent first: the entries before it in its own bucket, then the tail of the same bucket of
+// the previous window (only positions at distance <= 32768), at most max_hash_checks in total.
+//   Entries only: a visit is a coalesced 8-byte load and three logic ops against a pair of masks that
+//   tighten as the running best grows (dfl_core.h EntryWalk).  Results shorter than 8 bytes are final;
+//   a target whose best candidate shares all 8 entry bytes gets a "long" record (rank + visit index of
+//   the nearest such candidate) and is resolved on the data by the parse stage -- if the parser ever
+//   searches there.  No data is touched here beyond the three bytes that give a target its bucket.
+//   shared: the window's bytes (+16)
+// =====================================================================================
+// 8 bytes at in[idx ..] (idx < n), little endian; bytes past the last word of the input read as 0 (callers clamp
+// the lengths they derive to the bytes that exist).  Works for any alignment of `in`.
+__device__ __forceinline__ unsigned long long ld8(const uint8_t* __restrict__ in, const uint32_t* last_word, uint32_t idx) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t x0 = __ldg(w);
+    const uint32_t x1 = (w + 1 <= last_word) ? __ldg(w + 1) : 0u;
+    const uint32_t x2 = (w + 2 <= last_word) ? __ldg(w + 2) : 0u;
+    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+constexpr uint32_t kMatchThreads = 512;
+constexpr uint32_t kMatchStage = kWindow + 16;        // multiple of 16
+constexpr uint32_t kMatchSmem = kMatchStage + 16;
+
+// Per-lane state of one entry walk, kept in registers (the device-side form of dfl_core.h EntryWalk).
+struct Walk {
+    uint32_t me_lo, me_hi;   // the target's entry; me_hi is poisoned once the walk has stopped so that nothing passes
+    uint32_t mlo, mhi;       // entry_mask(best_len)
+    uint32_t best_len;       // 1 = nothing yet
+    uint32_t best_pos, best_k;
+    uint32_t stop;
+    uint32_t q_len, q_pos, q_k;   // state after checks_quarter visits (NEEDQ)
+};
+
+// entry_mask() by best length 3..8 (index 0..2 unused): what a candidate must share to be longer
+__constant__ uint2 c_walk_masks[9] = {
+    {0u, 0u}, {0u, 0u}, {0u, 0u},
+    {0x000000ffu, kEntryTagHi}, {0x0000ffffu, kEntryTagHi}, {0x00ffffffu, kEntryTagHi}, {0xffffffffu, kEntryTagHi},
+    {0xffffffffu, kEntryKeyHi}, {0xffffffffu, kEntryKeyHi}};
+
+// The visit itself: ((v ^ me) & mask) == 0 over both words, one LOP3 per word (written as PTX so that the
+// compiler does not split the xor off for the rare path below and pay for it on every visit).
+__device__ __forceinline__ bool walk_test(const Walk& wk, uint2 v) {
+    uint32_t t1, t2;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t1) : "r"(v.x), "r"(wk.me_lo), "r"(wk.mlo));
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t2) : "r"(v.y), "r"(wk.me_hi), "r"(wk.mhi));
+    return (t1 | t2) == 0u;
+}
+
+// A candidate passed the masks: it shares more bytes with the target than the running best (unless the end
+// of the input clamps it).  kg = visit index.
+template <bool NEEDQ>
+__device__ __forceinline__ void walk_improve(Walk& wk, uint2 v, uint32_t kg, uint32_t maxl, uint32_t qbudget) {
+    if (wk.stop) return;
+    uint32_t l = entry_lcp(v.x ^ wk.me_lo, v.y ^ wk.me_hi);
+    l = l < maxl ? l : maxl;
+    if (l > wk.best_len) {                      // strictly longer: the nearest candidate wins ties
+        wk.best_len = l;
+        wk.best_pos = v.y >> 17;
+        wk.best_k = kg;
+        if (NEEDQ) {
+            if (kg < qbudget) { wk.q_len = l; wk.q_pos = wk.best_pos; wk.q_k = kg; }
+        }
+        const uint2 m = c_walk_masks[l];
+        wk.mlo = m.x; wk.mhi = m.y;
+        if (l >= kEntryBytes || l == maxl) {    // matching.rs:152-156, or nothing longer can be proven from entries
+            wk.stop = 1;
+            wk.mlo = 0xffffffffu; wk.mhi = kEntryKeyHi;
+            wk.me_hi ^= 0x100u;                 // a flipped tag bit: (almost) nothing passes any more; the guard above catches the rest
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+
+#ifndef DFL_MATCH_CTAS
+#define DFL_MATCH_CTAS 4
+#endif
+template <bool NEEDQ>
+__global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
+k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_first, Params prm,
+        const uint2* __restrict__ K, const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf,
+        uint32_t* __restrict__ Mq) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
+    const uint32_t w = w_first + blockIdx.x;
+    const uint32_t base = w * kWindow;
+    const uint32_t cnt = window_count(n, w);
+    stage_bytes(smem, in, (long long)base, kMatchStage, n);
+    __syncthreads();
+
+    const uint2* Kw = K + (size_t)w * kWindow;
+    const uint16_t* ow = off + (size_t)w * kWindow;
+    const uint2* Kp = w > 0 ? K + (size_t)(w - 1) * kWindow : Kw;
+    const uint16_t* op = w > 0 ? off + (size_t)(w - 1) * kWindow : ow;
+    const uint32_t cnt_prev = w > 0 ? window_count(n, w - 1) : 0u;
+    const uint32_t budget = prm.checks;
+    const uint32_t qbudget = prm.checks_quarter;
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
+
+    // gridDim.y CTAs share one window when the input is small (the stage's latency is one CTA's run through
+    // 32768 entries otherwise): each takes a contiguous, 32-aligned slice of the sorted entries
+    const uint32_t slice = ((cnt + gridDim.y - 1) / gridDim.y + 31u) & ~31u;
+    const uint32_t i_lo = blockIdx.y * slice, i_hi = i_lo + slice < cnt ? i_lo + slice : cnt;
+    for (uint32_t i0 = i_lo + (threadIdx.x & ~31u); i0 < i_hi; i0 += blockDim.x) {   // warp-uniform loop
+        const uint32_t i = i0 + lane_id();
+        bool act = i < i_hi;
+        Walk wk;
+        wk.me_lo = 0; wk.me_hi = 0;
+        if (act) { uint2 v = __ldg(Kw + i); wk.me_lo = v.x; wk.me_hi = v.y; }
+        const uint32_t pl = entry_pos(wk.me_hi);
+        const uint32_t p = base + pl;
+        if (p < begin) act = false;
+        uint32_t n_own = 0, n_tot = 0, pe = 0;
+        uint32_t maxl = 0;
+        if (act) {
+            const uint32_t w0 = lds32(sw, pl);
+            const uint32_t h = hash3(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+            maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+            const uint32_t s0 = ow[h];
+            n_own = i - s0 < budget ? i - s0 : budget;
+            n_tot = n_own;
+            if (w > 0 && n_own < budget) {
+                // previous window: entries [ps, pe) of the same bucket whose position is >= pl
+                // (distance <= 32768, matching.rs:102-106,127); they are position sorted.
+                const uint32_t ps = op[h];
+                pe = (h + 1u < kWindow) ? op[h + 1u] : cnt_prev;
+                const uint32_t rem = budget - n_own;
+                uint32_t lo = (pe - ps > rem) ? pe - rem : ps, hi = pe;
+                // first j in [lo, pe) with pos >= pl; the oldest admissible entry is probed first
+                // because usually the whole tail qualifies
+                if (lo < hi) { if (entry_pos(__ldg(&Kp[lo].y)) >= pl) hi = lo; else lo++; }
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (entry_pos(__ldg(&Kp[mid].y)) >= pl) hi = mid; else lo = mid + 1;
+                }
+                n_tot += pe - lo;
+            }
+        }
+        wk.best_len = 1; wk.best_pos = 0; wk.best_k = 0; wk.stop = 0; wk.mlo = 0; wk.mhi = kEntryTagHi;
+        wk.q_len = 1; wk.q_pos = 0; wk.q_k = 0;
+        // Visit k is Kw[i - 1 - k] while k < n_own and Kp[pe - 1 - (k - n_own)] after that: one index space, so
+        // that a warp whose lanes sit on both sides of a bucket boundary runs max(n_tot) steps, not the sum of
+        // the two maxima.  Steps below the warp minimum of n_own need no per-lane case distinction.
+        const uint32_t tA = warp_min(n_own), tB = warp_max(n_own), tmax = warp_max(n_tot);
+        uint32_t k = 0;
+        {   // every lane is inside its own window's list
+            const uint2* ptr = Kw + i - 1;
+            for (; k + 8u <= tA; k += 8u, ptr -= 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint2 v = __ldg(ptr - u);
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k + u, maxl, qbudget);
+                }
+                if (__all_sync(0xffffffffu, wk.stop != 0u)) { k = tmax; break; }
+            }
+        }
+        if (k < tB) {   // some lanes have crossed into the previous window's list, some have not
+            const uint32_t oa = i - 1u + kWindow, ob = pe - 1u + n_own;    // entry index relative to Kw - kWindow, minus k
+            const uint2* Kb = Kw - kWindow;
+#pragma unroll 2
+            for (; k < tB; k++) {
+                if (k < n_tot) {
+                    const uint2 v = __ldg(Kb + ((k < n_own ? oa : ob) - k));
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
+                }
+                if ((k & 15u) == 15u && __all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) { k = tmax; break; }
+            }
+        }
+        if (k < tmax && !__all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) {   // only the previous window's list is left
+            const uint2* ptr = Kp + pe - 1 + n_own - k;
+#pragma unroll 2
+            for (; k < tmax; k++, ptr--) {
+                if (k < n_tot) {
+                    const uint2 v = __ldg(ptr);
+                    if (walk_test(wk, v)) walk_improve<NEEDQ>(wk, v, k, maxl, qbudget);
+                }
+                if ((k & 15u) == 15u && __all_sync(0xffffffffu, wk.stop != 0u || k >= n_tot)) break;
+            }
+        }
+        if (act) {
+            // distance of visit k: own window pl - pos, previous window pl + 32768 - pos
+            const uint32_t d = (wk.best_k < n_own ? pl : pl + kWindow) - wk.best_pos;
+            uint32_t rec = (wk.best_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.best_k) : finalize_match(wk.best_len, d);
+            if (rec_is_long(rec) && n_tot == 1u) {
+                // a single candidate (always so at Compression::Fast, max_hash_checks = 1): nothing to choose from, so the
+                // length is settled here instead of by the parser (the bytes are in L2: this CTA has just staged them)
+                uint32_t l = kEntryBytes;
+                while (l < maxl) {
+                    const unsigned long long x = ld8(in, last_word, p + l) ^ ld8(in, last_word, p - d + l);
+                    if (x != 0ull) { l += (uint32_t)(__ffsll((long long)x) - 1) >> 3; break; }
+                    l += 8u;
+                }
+                rec = finalize_match(l < maxl ? l : maxl, d);
+            }
+            Mf[p] = rec;
+            if (NEEDQ) {
+                const uint32_t dq = (wk.q_k < n_own ? pl : pl + kWindow) - wk.q_pos;
+                uint32_t rq = (wk.q_len >= kEntryBytes && maxl > kEntryBytes) ? rec_long(i, wk.q_k) : finalize_match(wk.q_len, dq);
+                if (rec_is_long(rq) && n_tot == 1u) rq = rec;      // the one candidate there is: settled above
+                Mq[p] = rq;
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// parse: the reference's token selection (lz77.rs:305-547, rle.rs:23-71) over the match records, one lane per
+// segment, with the long records resolved on the data by the whole warp.
+//   A lane runs its parser until the position it examines has a long record; it then parks with a request
+//   (position, candidate range, floor = prev_length).  When few lanes are left running the warp serves the
+//   parked lanes one after the other: 32 candidates per round, lane-private entry test (all 8 entry bytes
+//   equal), the reference's quick reject on the byte that would extend the best match (matching.rs:141-143),
+//   a lock-step byte comparison 8 bytes at a time, and a warp max that keeps the nearest of the longest
+//   (matching.rs:148-157).  Only positions the reference's parser searches are ever resolved: everything
+//   inside an emitted match is skipped (lz77.rs:398-405), which is 70-85 % of all positions on text.
 // =====================================================================================
 __device__ __forceinline__ ParseState state_from_key(uint32_t pos, uint32_t key) { return parse_state_from_key(pos, key); }
 
 struct ParseArgs {
     const uint8_t* in; uint32_t n; uint32_t begin; Params prm;
-    const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window
-    const uint16_t* R;                     // rank of every position in its window's list
+    const uint32_t* Mf; const uint32_t* Mq;
+    const uint2* K; const uint16_t* off;   // sorted entries and bucket offsets per window (long records refer to them)
+    const uint2* K2;                       // bytes 8..15 of every sorted entry
     uint32_t* segtok;
     uint32_t *e_pos, *e_key, *e_tok, *x_pos, *x_key, *x_tok;
     uint32_t n_seg;
@@ -355,155 +559,372 @@ struct ParseArgs {
     uint32_t init_key;             // state at `begin`
 };
 
+// What a parked lane asks for.  Filled by the lane itself; all parked lanes of a warp prepare at the same time.
+struct Resolve {
+    uint32_t p;        // position
+    uint32_t rank;     // index of the position in its window's sorted list
+    uint32_t k0;       // first visit to look at (rec_k8)
+    uint32_t start;    // max(prev_length, 7): only a longer result is of use (matching.rs:161-165)
+    uint32_t maxl;     // min(258, bytes left)
+    uint32_t n_own;    // visits k < n_own are Kw[rank - 1 - k]
+    uint32_t n_vis;    // visits allowed in total (chain budget; the previous window's share may end earlier)
+    uint32_t pe;       // visit k >= n_own is Kp[pe - 1 - (k - n_own)]
+    uint32_t me_lo, me_hi;
+    uint32_t b8_lo, b8_hi;   // bytes 8..15 of the target
+};
+
+__device__ __forceinline__ void resolve_prepare(const ParseArgs& A, Resolve& r, uint32_t budget, bool quarter) {
+    const uint32_t p = r.p, w = p >> 15;
+    const uint32_t rec = quarter ? A.Mq[p] : A.Mf[p];   // a long record: rank of p in its window's list, first visit to look at
+    r.rank = rec_rank(rec); r.k0 = rec_k8(rec);
+    const uint2 me = __ldg(A.K + (size_t)w * kWindow + r.rank);
+    const uint2 b8 = __ldg(A.K2 + (size_t)w * kWindow + r.rank);
+    r.me_lo = me.x; r.me_hi = me.y; r.b8_lo = b8.x; r.b8_hi = b8.y;
+    const uint32_t h = hash3(A.in[p], A.in[p + 1], A.in[p + 2]);
+    const uint16_t* ow = A.off + (size_t)w * kWindow;
+    const uint32_t full = A.prm.checks;
+    const uint32_t s0 = __ldg(ow + h);
+    r.n_own = r.rank - s0 < full ? r.rank - s0 : full;
+    uint32_t n_tot = r.n_own;
+    r.pe = 0;
+    if (w > 0 && r.n_own < full) {
+        const uint16_t* op = ow - kWindow;
+        const uint32_t ps = __ldg(op + h);
+        r.pe = (h + 1u < kWindow) ? (uint32_t)__ldg(op + h + 1u) : window_count(A.n, w - 1);
+        const uint32_t rem = full - r.n_own;
+        n_tot += (r.pe - ps > rem) ? rem : r.pe - ps;   // entries with a position below pl are cut off during the scan
+    }
+    r.n_vis = n_tot < budget ? n_tot : budget;
+    if (r.start >= r.maxl) r.n_vis = 0;                 // nothing can be longer than the floor (matching.rs:99-101)
+}
+
+// Entry of visit k of a request (warp-uniform request, lane-private k).
+__device__ __forceinline__ const uint2* resolve_entry(const ParseArgs& A, uint32_t w, uint32_t rank, uint32_t n_own, uint32_t pe,
+                                                      uint32_t k) {
+    const uint2* Kw = A.K + (size_t)w * kWindow;
+    return k < n_own ? Kw + (rank - 1u - k) : Kw - kWindow + (pe - 1u - (k - n_own));
+}
+
 #ifndef DFL_PARSE_CTAS
-#define DFL_PARSE_CTAS 8      // CTAs of 128 threads per SM the parse kernels are compiled for (64 registers)
+#define DFL_PARSE_CTAS 7      // CTAs of 128 threads per SM the parse kernels are compiled for (72 registers)
+#endif
+#ifndef DFL_PARSE_KEEP
+#define DFL_PARSE_KEEP 6      // keep parsing while at least this many lanes of a warp are running
 #endif
 constexpr uint32_t kParseThreads = 128;
 constexpr uint32_t kParseWarps = kParseThreads / 32;
+constexpr uint32_t kCandCap = 128;       // candidates a warp collects before it compares them
+#ifndef DFL_LC_BYTES
+#define DFL_LC_BYTES 128
+#endif
+constexpr uint32_t kLcBytes = DFL_LC_BYTES;   // length codes (dfl_core.h rec_len_code, one byte per position) a lane keeps in shared memory
+constexpr uint32_t kLcWords = kLcBytes / 4;
+constexpr uint32_t kLcHalf = kLcBytes / 2;
+struct ParseShared {
+    uint32_t cand_q[kCandCap];           // absolute position of a candidate that shares the target's 8 entry bytes
+    uint32_t cand_meta[kCandCap];        // owner lane | visit index << 5
+    uint2 cand_b8[kCandCap];             // the candidate's bytes 8..15
+    uint32_t res_key[32];                // per owner lane: best length << 16 | (0xffff - visit index)
+    uint32_t lc[32 * (kLcWords + 1)];    // per lane kLcWords words of length codes (+1: rows fall on different banks)
+};
 
-// Tokens as the parser writes them into its segment buffer.  The byte of a literal is not loaded by the parser:
-// such a token names a position instead and k_compact, fully parallel, fills it in.  Positions are relative to
-// (segment start - origin_back).
+// Tokens as the parser writes them into its segment buffer.  What the parser does not need in order to decide --
+// the byte of a literal, the distance of a match whose record is final -- is not loaded by it (a dependent load
+// per step is what bounds a sequential parser on a GPU): such tokens name a position instead and k_compact,
+// fully parallel, fills them in.  Positions are relative to (segment start - origin_back).
 constexpr uint32_t kTokLitAt = 0x80000000u;       // | relative position
+constexpr uint32_t kTokMatchAt = 0x40000000u;     // | quarter-budget record << 29 | length << 14 | relative position
+constexpr uint32_t kTokQuarter = 0x20000000u;
 constexpr uint32_t kTokRelMask = 0x3fffu;
 __host__ __device__ inline uint32_t parse_origin_back(uint32_t warm) { return warm + 300u; }
 struct DeferSink {
     uint32_t* tk; uint32_t nt, cap; long long origin;
     __device__ __forceinline__ void put(uint32_t t) { if (nt < cap) tk[nt] = t; nt++; }
     __device__ __forceinline__ void literal(uint32_t pos) { put(kTokLitAt | (uint32_t)((long long)pos - origin)); }
-    __device__ __forceinline__ void match(uint32_t len, uint32_t ref, uint32_t) { put(tok_match(len, ref)); }
+    __device__ __forceinline__ void match(uint32_t len, uint32_t ref, uint32_t kind) {
+        if (kind == kRefDist) put(tok_match(len, ref));
+        else put(kTokMatchAt | (kind == kRefQuarter ? kTokQuarter : 0u) | (len << 14) | (uint32_t)((long long)ref - origin));
+    }
 };
 
-enum LaneState : uint32_t { kLaneStep = 0, kLaneWalk = 1, kLaneLong = 2, kLaneDone = 3 };
-// What a lane served is worth when sections compete: roughly the inverse of what one execution of the section
-// costs (instructions).  No section can be starved for long: every lane passes through STEP once per search, so the
-// sections that win drain into it.
-#ifndef DFL_W_WALK
-#define DFL_W_WALK 2
-#endif
-#ifndef DFL_W_STEP
-#define DFL_W_STEP 1
-#endif
-#ifndef DFL_W_LONG
-#define DFL_W_LONG 3
-#endif
-
-// Every lane of the calling warp enters.  `next(s, st, a, b)` hands the calling lane its next segment -- index,
-// start state, [a, b) -- or returns false when there is none left; a lane runs the reference's token selection
-// from `st` until the first iteration position >= b, then asks for the next segment.  Lanes are persistent: a warp
-// is busy until the supply runs out, so lanes that wait for their kind of section to come up cost nothing.
-template <class Next>
-__device__ __forceinline__ void parse_lanes(const ParseArgs& A, Next next) {
-    const uint32_t n = A.n;
-    const int mode = A.prm.mode;
-    const bool has_m = (mode != kRle) && (A.prm.checks > 0);
-    SearchIn si;
-    si.in = A.in; si.n = n;
-    si.last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
-    si.K = reinterpret_cast<const Entry*>(A.K); si.off = A.off; si.R = A.R;
-    Search S;
-    S.p = S.maxl = S.floor = S.me_lo = S.me_hi = S.mlo = S.mhi = S.best_len = S.best_dist = 0u;
-    S.e = S.rem = S.prev_e = S.prev_rem = S.q = S.ll = 0u;
-    DeferSink out;
-    out.tk = nullptr; out.nt = 0; out.cap = A.tok_cap; out.origin = 0;
-    uint32_t s = 0, a = 0, b = 0;
-    ParseState st = parse_state_init(0);
-    bool have_e = false, have_res = false;   // have_res: the search at st.pos has finished, its result is in S
-    auto take_segment = [&]() -> bool {
-        if (!next(s, st, a, b)) return false;
-        out.tk = A.segtok + (size_t)s * A.tok_cap; out.nt = 0;
-        out.origin = (long long)A.begin + (long long)s * A.seg - (long long)parse_origin_back(A.warm);
-        have_e = false; have_res = false;
-        return true;
-    };
-    uint32_t state = take_segment() ? kLaneStep : kLaneDone;
-    auto state_key = [&](const ParseState& x) -> uint32_t { return parse_state_key(x, x.prev_len ? x.prev_ref : 0u); };
-    auto do_step = [&](uint32_t m_rec) {
-        const uint32_t m_len = match_len(m_rec), m_dist = m_len ? match_dist(m_rec) : 0u;
-        if (mode == kLazy) lazy_step(st, n, m_len, m_dist, kRefDist, A.prm.lazy, out);
-        else if (mode == kGreedy) greedy_step(st, n, m_len, m_dist, kRefDist, out);
-        else rle_step(st, n, A.in, out);       // rle.rs runs over the buffer from its first byte
-    };
-    // checks the segment bounds at st.pos; true = the segment is finished (its hand-off records are written)
-    auto at_end = [&]() -> bool {
-        bool stop_here = st.pos >= n;
-        if (!stop_here) {
-            if (!have_e && st.pos >= a) { A.e_pos[s] = st.pos; A.e_key[s] = state_key(st); A.e_tok[s] = out.nt; have_e = true; }
-            stop_here = st.pos >= b;
+// Compares the collected candidates of all owners, one candidate per lane and round.  Bytes 8..15 of target and
+// candidate are at hand (K2), so a common prefix below 16 bytes is settled without touching the input; only a
+// candidate that shares all 16 goes on: the byte that would extend the owner's running best
+// (matching.rs:141-143), then a lock-step comparison 8 bytes at a time.  The longest candidate wins, the nearest
+// among equals (matching.rs:148-157): a max over length << 16 | ~visit.
+__device__ __forceinline__ void resolve_compare(const ParseArgs& A, ParseShared& S, uint32_t cnt, const Resolve& rq,
+                                                const uint32_t* last_word) {
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t c = base + lane;
+        const bool have = c < cnt;
+        const uint32_t meta = have ? S.cand_meta[c] : 0u;
+        const uint32_t q = have ? S.cand_q[c] : 0u;
+        const uint2 cb8 = have ? S.cand_b8[c] : make_uint2(0u, 0u);
+        const uint32_t owner = meta & 31u, k = meta >> 5;
+        const uint32_t po = __shfl_sync(0xffffffffu, rq.p, owner);
+        const uint32_t st = __shfl_sync(0xffffffffu, rq.start, owner);
+        const uint32_t ml = __shfl_sync(0xffffffffu, rq.maxl, owner);
+        const uint32_t tlo = __shfl_sync(0xffffffffu, rq.b8_lo, owner), thi = __shfl_sync(0xffffffffu, rq.b8_hi, owner);
+        const uint32_t cur = S.res_key[owner] >> 16;          // the owner's best from earlier rounds: all of them nearer
+        const uint32_t s0 = st > cur ? st : cur;
+        uint32_t mine = 0;
+        bool alive = false;
+        if (have && s0 < ml) {
+            const uint32_t xlo = cb8.x ^ tlo, xhi = cb8.y ^ thi;
+            if (xlo) mine = kEntryBytes + ((uint32_t)(__ffs((int)xlo) - 1) >> 3);
+            else if (xhi) mine = kEntryBytes + 4u + ((uint32_t)(__ffs((int)xhi) - 1) >> 3);
+            else if (ml <= 2u * kEntryBytes) mine = ml;
+            else alive = (s0 < 2u * kEntryBytes) || (A.in[q + s0] == A.in[po + s0]);
         }
-        if (stop_here) {
-            if (!have_e) { A.e_pos[s] = st.pos; A.e_key[s] = state_key(st); A.e_tok[s] = out.nt; have_e = true; }
-            A.x_pos[s] = st.pos; A.x_key[s] = state_key(st); A.x_tok[s] = out.nt;
-        }
-        return stop_here;
-    };
-    if (!has_m) {   // no searches (rle(), huffman_only()): nothing to interleave
-        while (state != kLaneDone) {
-            if (at_end()) { if (!take_segment()) state = kLaneDone; }
-            else do_step(0u);
-        }
-        return;
-    }
-    for (;;) {
-        const uint32_t m_walk = __ballot_sync(0xffffffffu, state == kLaneWalk);
-        const uint32_t m_step = __ballot_sync(0xffffffffu, state == kLaneStep);
-        const uint32_t m_long = __ballot_sync(0xffffffffu, state == kLaneLong);
-        if ((m_walk | m_step | m_long) == 0u) break;
-        const uint32_t sc_w = (uint32_t)__popc(m_walk) * DFL_W_WALK, sc_s = (uint32_t)__popc(m_step) * DFL_W_STEP,
-                       sc_l = (uint32_t)__popc(m_long) * DFL_W_LONG;
-        if (sc_w >= sc_s && sc_w >= sc_l) {
-            if (state == kLaneWalk) {
-                const uint32_t r = search_walk(S, si);
-                state = r == kSearchWalk ? kLaneWalk : (r == kSearchLong ? kLaneLong : kLaneStep);
-                have_res = r == kSearchDone;
+        uint32_t l = 2u * kEntryBytes;
+        while (__any_sync(0xffffffffu, alive)) {              // lock step: l is the same in every lane that is alive
+            if (alive) {
+                const unsigned long long x = ld8(A.in, last_word, po + l) ^ ld8(A.in, last_word, q + l);
+                if (x != 0ull) { mine = l + ((uint32_t)(__ffsll((long long)x) - 1) >> 3); alive = false; }
+                else if (l + 8u >= ml) { mine = ml; alive = false; }
             }
-        } else if (sc_l >= sc_s) {
-            if (state == kLaneLong) {
-                const uint32_t r = search_long(S, si);
-                state = r == kSearchWalk ? kLaneWalk : (r == kSearchLong ? kLaneLong : kLaneStep);
-                have_res = r == kSearchDone;
-            }
-        } else {
-            if (state == kLaneStep) {
-                // a lane comes here with a finished search (apply its result) or at a fresh position
-                if (have_res) { do_step(search_result(S)); have_res = false; }
-                if (at_end()) {
-                    if (!take_segment()) state = kLaneDone;
-                } else {
-                    const uint32_t p = st.pos;
-                    if (p + 2u < n && (mode != kLazy || !st.ign)) {          // the reference searches here (lz77.rs:347,505)
-                        const uint32_t floor = mode == kLazy ? st.prev_len : 0u;
-                        const uint32_t budget = (mode == kLazy && st.prev_len >= 32u) ? A.prm.checks_quarter : A.prm.checks;   // lz77.rs:351-355
-                        const uint32_t r = search_begin(S, si, p, floor, budget);
-                        if (r == kSearchDone) do_step(0u);
-                        else state = kLaneWalk;
-                    } else {
-                        do_step(0u);
-                    }
-                }
-            }
+            l += 8u;
         }
+        mine = mine < ml ? mine : ml;
+        if (mine > s0) atomicMax(&S.res_key[owner], (mine << 16) | (0xffffu - k));
+        __syncwarp();
     }
 }
 
-// Speculative parse of every segment: a blank state `warm` bytes in front of the segment start (the true state for
-// segment 0).  The first segment of a lane is its thread index, further ones come from a counter.
-__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_spec(ParseArgs A, DevMeta* meta) {
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, n_thr = gridDim.x * blockDim.x;
-    bool first = true;
-    parse_lanes(A, [&](uint32_t& s, ParseState& st, uint32_t& a, uint32_t& b) -> bool {
-        s = first ? gtid : n_thr + atomicAdd(&meta->fetch, 1u);
-        first = false;
-        if (s >= A.n_seg) return false;
+// One owner's request, broadcast to the warp.
+struct Owner { uint32_t p, rank, k0, n_own, n_vis, pe, lo, hi; };
+__device__ __forceinline__ Owner resolve_owner(const Resolve& rq, int j) {
+    Owner o;
+    o.p = __shfl_sync(0xffffffffu, rq.p, j); o.rank = __shfl_sync(0xffffffffu, rq.rank, j);
+    o.k0 = __shfl_sync(0xffffffffu, rq.k0, j); o.n_own = __shfl_sync(0xffffffffu, rq.n_own, j);
+    o.n_vis = __shfl_sync(0xffffffffu, rq.n_vis, j); o.pe = __shfl_sync(0xffffffffu, rq.pe, j);
+    o.lo = __shfl_sync(0xffffffffu, rq.me_lo, j); o.hi = __shfl_sync(0xffffffffu, rq.me_hi, j);
+    return o;
+}
+// Entries of visits kb + 32 t + lane, t = 0..3 (up to 128 entries of one owner in flight); slots past the owner's
+// last visit are not touched.
+__device__ __forceinline__ void resolve_load4(const ParseArgs& A, const Owner& o, uint32_t kb, uint2 e[4]) {
+    const uint2* Kw = A.K + (size_t)(o.p >> 15) * kWindow;
+    const uint2* pa = Kw + (o.rank - 1u);                 // visit k of the own window: pa - k
+    const uint2* pb = Kw - kWindow + (o.pe - 1u + o.n_own);   // visit k of the previous window: pb - k
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+        const uint32_t k = kb + t * 32u + lane_id();
+        e[t] = make_uint2(0u, 0u);
+        if (k < o.n_vis) e[t] = __ldg((k < o.n_own ? pa : pb) - k);
+    }
+}
+
+// Every lane of the calling warp enters (work == false: the lane only helps with resolutions).  A lane with work
+// runs the reference's token selection from `st` until the first iteration position >= b.
+__device__ void parse_lanes(const ParseArgs& A, ParseShared& S, bool work, uint32_t s, ParseState st, uint32_t a, uint32_t b) {
+    DeferSink out;
+    out.tk = A.segtok + (size_t)s * A.tok_cap; out.nt = 0; out.cap = A.tok_cap;
+    out.origin = (long long)A.begin + (long long)s * A.seg - (long long)parse_origin_back(A.warm);
+    bool have_e = false;
+    uint32_t epos = 0, ekey = 0, etok = 0;
+    const uint32_t n = A.n;
+    const int mode = A.prm.mode;
+    const bool has_m = (mode != kRle) && (A.prm.checks > 0);
+    const uint32_t lane = lane_id();
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
+    uint32_t* lc = S.lc + lane * (kLcWords + 1u);
+    uint32_t cb = 0xffffff00u;                       // position of the first cached length code (a multiple of kLcHalf); nothing yet
+    bool running = work, parked = false, have_m = false, rq_quarter = false;
+    uint32_t m_ready = 0, rq_budget = 0;
+    Resolve rq;
+    rq.p = rq.rank = rq.k0 = rq.start = rq.maxl = rq.n_own = rq.n_vis = rq.pe = rq.me_lo = rq.me_hi = rq.b8_lo = rq.b8_hi = 0;
+    // the hand-off key carries the pending match's distance: looked up here, once per segment boundary
+    auto state_key = [&](const ParseState& x) -> uint32_t {
+        uint32_t d = 0;
+        if (x.prev_len) d = x.prev_kind == kRefDist ? x.prev_ref : match_dist((x.prev_kind == kRefQuarter ? A.Mq : A.Mf)[x.prev_ref]);
+        return parse_state_key(x, d);
+    };
+    for (;;) {
+        // ---- parse: every running lane takes one step per iteration
+        for (;;) {
+            bool miss = false;
+            if (running && !parked) {
+                bool stop_here = st.pos >= n;
+                if (!stop_here) {
+                    if (!have_e && st.pos >= a) { epos = st.pos; ekey = state_key(st); etok = out.nt; have_e = true; }
+                    stop_here = st.pos >= b;
+                }
+                if (stop_here) {
+                    if (!have_e) { epos = st.pos; ekey = state_key(st); etok = out.nt; }
+                    A.e_pos[s] = epos; A.e_key[s] = ekey; A.e_tok[s] = etok;
+                    A.x_pos[s] = st.pos; A.x_key[s] = state_key(st); A.x_tok[s] = out.nt;
+                    running = false;
+                } else {
+                    const uint32_t p = st.pos;
+                    uint32_t m_len = 0, m_ref = 0, m_kind = kRefDist;
+                    if (have_m) {                                            // the answer to this lane's request
+                        m_len = match_len(m_ready); m_ref = m_len ? match_dist(m_ready) : 0u; have_m = false;
+                    } else if (has_m && p + 2u < n && (mode != kLazy || !st.ign)) {   // the reference searches here (lz77.rs:347,505)
+                        const bool quarter = mode == kLazy && st.prev_len >= 32u;        // lz77.rs:351-355
+                        if (!quarter || A.prm.need_quarter) {
+                            uint32_t code;
+                            if (quarter) code = rec_len_code(A.Mq[p]);
+                            else if (p - cb < kLcBytes) code = (lc[(p - cb) >> 2] >> (8u * (p & 3u))) & 0xffu;   // cb is a multiple of 4
+                            else { code = 0; miss = true; }
+                            if (code == kLenLong) {
+                                rq.p = p;
+                                const uint32_t floor = mode == kLazy ? st.prev_len : 0u;
+                                rq.start = floor > kEntryBytes - 1u ? floor : kEntryBytes - 1u;
+                                rq.maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                                rq_budget = quarter ? A.prm.checks_quarter : A.prm.checks;
+                                rq_quarter = quarter;
+                                parked = true;
+                            } else {
+                                m_len = code == 0u ? 0u : (code == kLenSeeRecord ? match_len(quarter ? A.Mq[p] : A.Mf[p]) : code + 2u);
+                                m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
+                            }
+                        }
+                    }
+                    if (!parked && !miss) {
+                        if (mode == kLazy) lazy_step(st, n, m_len, m_ref, m_kind, A.prm.lazy, out);
+                        else if (mode == kGreedy) greedy_step(st, n, m_len, m_ref, m_kind, out);
+                        else rle_step(st, n, A.in, out);       // rle.rs runs over the buffer from its first byte
+                    }
+                }
+            }
+            // Length codes: the match records of the next kLcBytes positions of a lane, one byte each, fetched by the
+            // whole warp (coalesced 16-byte loads, four records per lane and load) when the lane runs out; lanes that
+            // are past the middle of what they hold are refreshed in the same round, so that round trips are shared.
+            uint32_t want = __ballot_sync(0xffffffffu, miss);
+            if (want) {
+                want |= __ballot_sync(0xffffffffu, running && !parked && has_m && st.pos - cb >= kLcHalf);
+                const uint32_t mine = st.pos & ~(kLcHalf - 1u);
+                for (uint32_t left = want; left;) {
+                    const int j = __ffs((int)left) - 1;
+                    left &= left - 1u;
+                    const uint32_t base = __shfl_sync(0xffffffffu, mine, j);
+#pragma unroll
+                    for (uint32_t u = 0; u < kLcWords / 32u; u++) {
+                        const uint32_t q = base + 4u * (u * 32u + lane);      // this lane converts records q .. q + 3
+                        uint32_t codes = 0;
+                        if (q + 4u <= n && ((reinterpret_cast<uintptr_t>(A.Mf + q) & 15u) == 0)) {
+                            const uint4 r = __ldg(reinterpret_cast<const uint4*>(A.Mf + q));
+                            codes = rec_len_code(r.x) | (rec_len_code(r.y) << 8) | (rec_len_code(r.z) << 16) | (rec_len_code(r.w) << 24);
+                        } else {
+#pragma unroll
+                            for (uint32_t t = 0; t < 4; t++) if (q + t < n) codes |= rec_len_code(A.Mf[q + t]) << (8u * t);
+                        }
+                        S.lc[(uint32_t)j * (kLcWords + 1u) + u * 32u + lane] = codes;
+                    }
+                }
+                if ((want >> lane) & 1u) cb = mine;
+                __syncwarp();
+            }
+            const uint32_t going = __ballot_sync(0xffffffffu, running && !parked);
+            if (going == 0u) break;
+            if ((uint32_t)__popc(going) < DFL_PARSE_KEEP && __any_sync(0xffffffffu, parked)) break;
+        }
+        // ---- resolve the parked lanes' long records together
+        const uint32_t waiting = __ballot_sync(0xffffffffu, parked);
+        if (waiting == 0u) {
+            if (!__any_sync(0xffffffffu, running)) break;
+            continue;
+        }
+        if (parked) resolve_prepare(A, rq, rq_budget, rq_quarter);   // every parked lane at once: their loads overlap
+        S.res_key[lane] = 0u;
+        __syncwarp();
+        // scan: per owner, every candidate from visit k0 on whose 8 entry bytes equal the target's goes on the list;
+        // the entries of the next owner are requested before the current one's are looked at
+        uint32_t cnt = 0;
+        uint32_t left = waiting;
+        int j = __ffs((int)left) - 1;
+        left &= left - 1u;
+        Owner o = resolve_owner(rq, j);
+        uint2 e[4];
+        resolve_load4(A, o, o.k0, e);
+        for (;;) {
+            const int jn = left ? __ffs((int)left) - 1 : -1;
+            Owner on = o;
+            uint2 en[4];
+            if (jn >= 0) {
+                left &= left - 1u;
+                on = resolve_owner(rq, jn);
+                resolve_load4(A, on, on.k0, en);
+            }
+            const uint32_t w = o.p >> 15, pl = o.p & kWindowMask;
+            bool over = false;
+            for (uint32_t kb = o.k0; kb < o.n_vis && !over; kb += 128u) {
+                if (kb != o.k0) resolve_load4(A, o, kb, e);      // chain budgets above 128 only
+#pragma unroll
+                for (uint32_t t = 0; t < 4; t++) {
+                    if (kb + t * 32u >= o.n_vis) break;          // warp-uniform: the owner has no visits in this slot
+                    const uint32_t k = kb + t * 32u + lane;
+                    const bool val = k < o.n_vis, own = k < o.n_own;
+                    const uint32_t ep = entry_pos(e[t].y);
+                    const bool ended = val && !own && ep < pl;   // beyond the window (matching.rs:102-106); so is everything older
+                    const bool eq = val && !ended && e[t].x == o.lo && (((e[t].y ^ o.hi) & kEntryKeyHi) == 0u);
+                    const uint32_t mk = __ballot_sync(0xffffffffu, eq);
+                    if (mk) {
+                        if (cnt + 32u > kCandCap) { __syncwarp(); resolve_compare(A, S, cnt, rq, last_word); cnt = 0; }
+                        if (eq) {
+                            const uint32_t at = cnt + __popc(mk & ((1u << lane) - 1u));
+                            const uint32_t cw = own ? w : w - 1u;
+                            S.cand_q[at] = cw * kWindow + ep;
+                            S.cand_meta[at] = (uint32_t)j | (k << 5);
+                            S.cand_b8[at] = __ldg(A.K2 + (size_t)cw * kWindow + (own ? o.rank - 1u - k : o.pe - 1u - (k - o.n_own)));
+                        }
+                        cnt += __popc(mk);
+                    }
+                    if (__any_sync(0xffffffffu, ended)) { over = true; break; }
+                }
+            }
+            if (jn < 0) break;
+            j = jn; o = on;
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) e[t] = en[t];
+        }
+        __syncwarp();
+        resolve_compare(A, S, cnt, rq, last_word);
+        // every owner picks up its result; the distance comes from the winning visit's entry
+        if (parked) {
+            const uint32_t key = S.res_key[lane];
+            m_ready = 0u;
+            if (key != 0u) {
+                const uint32_t k = 0xffffu - (key & 0xffffu);
+                const uint32_t w = rq.p >> 15;
+                const uint2 e = __ldg(resolve_entry(A, w, rq.rank, rq.n_own, rq.pe, k));
+                const uint32_t q = (k < rq.n_own ? w : w - 1u) * kWindow + entry_pos(e.y);
+                m_ready = finalize_match(key >> 16, rq.p - q);
+            }
+            have_m = true;
+            parked = false;
+        }
+        __syncwarp();
+    }
+}
+
+
+
+__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_spec(ParseArgs A) {
+    __shared__ ParseShared sh[kParseWarps];
+    // The lanes of a warp take segments far apart (stride = number of warps in the grid): the cost of a segment
+    // depends on the kind of data, neighbouring segments are of one kind, and a warp is as slow as its slowest lane.
+#ifndef DFL_PARSE_STRIDED
+#define DFL_PARSE_STRIDED 1
+#endif
+    const uint32_t n_warps = gridDim.x * kParseWarps;
+    const uint32_t s = DFL_PARSE_STRIDED ? lane_id() * n_warps + blockIdx.x * kParseWarps + warp_id()
+                                         : blockIdx.x * blockDim.x + threadIdx.x;
+    const bool work = s < A.n_seg;
+    uint32_t a = 0, b = 0;
+    ParseState st = parse_state_init(0);
+    if (work) {
         a = A.begin + s * A.seg;
         b = a + A.seg < A.end ? a + A.seg : A.end;
         const uint32_t start = (s == 0) ? A.begin : (a - A.begin > A.warm ? a - A.warm : A.begin);
         st = (s == 0) ? state_from_key(A.begin, A.init_key) : parse_state_init(start);
-        return true;
-    });
+    }
+    parse_lanes(A, sh[warp_id()], work, s, st, a, b);
 }
 
-__global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* bad_list, uint32_t* start_pos,
+__global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad, uint32_t* start_pos,
                                                       uint32_t* start_key, DevMeta* meta) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n_seg) return;
@@ -514,36 +935,34 @@ __global__ void __launch_bounds__(128) k_parse_verify(ParseArgs A, uint8_t* bad,
             is_bad = 1;
             start_pos[s] = xp;
             start_key[s] = xk;
-            bad_list[atomicAdd(&meta->n_bad, 1u)] = s;
+            atomicAdd(&meta->n_bad, 1u);
         }
     }
     bad[s] = is_bad;
 }
 
-// Re-parses the segments on the bad list from the exit state of their predecessors.
-__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_repair(ParseArgs A, const uint32_t* bad_list, const uint32_t* start_pos,
+__global__ void __launch_bounds__(kParseThreads, DFL_PARSE_CTAS) k_parse_repair(ParseArgs A, const uint8_t* bad, const uint32_t* start_pos,
                                                                 const uint32_t* start_key, DevMeta* meta) {
-    const uint32_t n_bad = meta->n_bad;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, n_thr = gridDim.x * blockDim.x;
-    if ((gtid & ~31u) >= n_bad) return;          // the whole warp has nothing to do
-    bool first = true;
-    parse_lanes(A, [&](uint32_t& s, ParseState& st, uint32_t& a, uint32_t& b) -> bool {
-        const uint32_t i = first ? gtid : n_thr + atomicAdd(&meta->fetch, 1u);
-        first = false;
-        if (i >= n_bad) return false;
-        s = bad_list[i];
+    __shared__ ParseShared sh[kParseWarps];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool work = s < A.n_seg && bad[s];
+    if (!__any_sync(0xffffffffu, work)) return;
+    uint32_t a = 0, b = 0;
+    ParseState st = parse_state_init(0);
+    if (work) {
         a = A.begin + s * A.seg;
         b = a + A.seg < A.end ? a + A.seg : A.end;
         st = state_from_key(start_pos[s], start_key[s]);
         atomicAdd(&meta->n_repaired_par, 1u);
-        return true;
-    });
+    }
+    parse_lanes(A, sh[warp_id()], work, s, st, a, b);
 }
 
-// Sequential fallback (one warp; lane 0 parses): walks the segments in order and re-parses every one whose entry
-// does not continue its predecessor's exit.  Exact for any input; only slow on inputs whose speculative parses
-// never resynchronise.
+// Sequential fallback (one warp; lane 0 parses, the others help with resolutions): walks the segments in order
+// and re-parses every one whose entry does not continue its predecessor's exit.  Exact for any input; only slow
+// on inputs whose speculative parses never resynchronise (e.g. megabytes of a single repeated byte).
 __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* meta) {
+    __shared__ ParseShared sh;
     if (meta->n_bad == 0) return;
     const uint32_t lane = lane_id();
     for (uint32_t s = 1; s < A.n_seg; s++) {
@@ -554,16 +973,9 @@ __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* m
         }
         isbad = __shfl_sync(0xffffffffu, isbad, 0);
         if (isbad) {
-            bool first = lane == 0;
-            parse_lanes(A, [&](uint32_t& so, ParseState& st, uint32_t& a, uint32_t& b) -> bool {
-                if (!first) return false;
-                first = false;
-                so = s;
-                a = A.begin + s * A.seg;
-                b = a + A.seg < A.end ? a + A.seg : A.end;
-                st = state_from_key(xp, xk);
-                return true;
-            });
+            const uint32_t a = A.begin + s * A.seg;
+            const uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
+            parse_lanes(A, sh, lane == 0, s, state_from_key(xp, xk), a, b);
             if (lane == 0) meta->n_repaired_seq++;
             __threadfence();
             __syncwarp();
@@ -572,7 +984,7 @@ __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* m
     if (lane == 0) meta->n_bad = 0;
 }
 
-__global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; meta->fetch = 0; }
+__global__ void k_reset_bad(DevMeta* meta) { meta->n_bad = 0; }
 
 // Repair start states for chains of bad segments.  A speculative parse resynchronises with the true one at the
 // end of a match -- except inside a chain of maximum-length matches (runs of one byte, short periods): every
@@ -678,21 +1090,24 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t n_seg, const uint32_
 }
 
 // Copies every segment's tokens to their place in the stream and fills in what the parser left open: the byte of a
-// literal (kTokLitAt).
-constexpr uint32_t kCompactWarps = 8;
-__global__ void __launch_bounds__(32 * kCompactWarps) k_compact(ParseArgs A, const uint32_t* __restrict__ seg_cnt,
-                                                                const unsigned long long* __restrict__ seg_off, uint32_t* __restrict__ tok,
-                                                                DevMeta* meta) {
-    const uint32_t s = blockIdx.x * kCompactWarps + warp_id();   // a warp per segment
-    if (s >= A.n_seg) return;
+// literal (kTokLitAt) and the distance of a match whose record is final (kTokMatchAt).
+__global__ void __launch_bounds__(128) k_compact(ParseArgs A, const uint32_t* __restrict__ seg_cnt,
+                                                 const unsigned long long* __restrict__ seg_off, uint32_t* __restrict__ tok,
+                                                 DevMeta* meta) {
+    const uint32_t s = blockIdx.x;
     const uint32_t c = seg_cnt[s], e0 = A.e_tok[s];
-    if (e0 + c > A.tok_cap) { if (lane_id() == 0) meta->err = 1; return; }
+    if (e0 + c > A.tok_cap) { if (threadIdx.x == 0) meta->err = 1; return; }
     const uint32_t* src = A.segtok + (size_t)s * A.tok_cap + e0;
     uint32_t* dst = tok + seg_off[s];
     const long long origin = (long long)A.begin + (long long)s * A.seg - (long long)parse_origin_back(A.warm);
-    for (uint32_t i = lane_id(); i < c; i += 32u) {
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
         uint32_t t = src[i];
         if (t & kTokLitAt) t = tok_literal(A.in[origin + (long long)(t & kTokRelMask)]);
+        else if (t & kTokMatchAt) {
+            const long long q = origin + (long long)(t & kTokRelMask);
+            const uint32_t rec = (t & kTokQuarter) ? A.Mq[q] : A.Mf[q];
+            t = tok_match((t >> 14) & 0x1ffu, match_dist(rec));
+        }
         dst[i] = t;
     }
 }
@@ -1321,8 +1736,8 @@ uint32_t max_blocks_for(uint32_t n_payload) { return n_payload / kBlockTokens + 
 
 static ParseArgs make_parse_args(const EncodeJob& j, Buffers& b) {
     ParseArgs A;
-    A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.segtok = b.segtok;
-    A.K = b.K; A.off = b.off; A.R = b.R;
+    A.in = j.d_in; A.n = j.n; A.begin = j.begin; A.prm = j.prm; A.Mf = b.Mf; A.Mq = b.Mq; A.segtok = b.segtok;
+    A.K = b.K; A.off = b.off; A.K2 = b.K2;
     A.e_pos = b.seg_e_pos; A.e_key = b.seg_e_key; A.e_tok = b.seg_e_tok;
     A.x_pos = b.seg_x_pos; A.x_key = b.seg_x_key; A.x_tok = b.seg_x_tok;
     const ParseGeom g = parse_geom(j.n - j.begin, j.prm.mode);
@@ -1343,21 +1758,44 @@ static cudaError_t ensure_attrs() {
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
+    if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) done[dev] = true;
     return cudaSuccess;
 }
 
-// Window ranges: the sort needs windows [first_sort_window(j), n_windows(j)) -- a search in window w reads the
-// sorted lists of w - 1 and w -- and can be issued in pieces [w_lo, w_hi) as the input arrives (dfl_compress
-// overlaps the host-to-device copy with it).
+// Window ranges: the sort needs windows [first_sort_window(j), n_windows(j)), the match stage
+// [first_match_window(j), n_windows(j)).  Both can be issued in pieces [w_lo, w_hi) as the input
+// arrives (dfl_compress overlaps the host-to-device copy with them); matching window w needs the
+// sorted lists of w - 1 and w.
 uint32_t n_windows(const EncodeJob& j) { return (j.n + kWindow - 1) / kWindow; }
+uint32_t first_match_window(const EncodeJob& j) { return j.begin / kWindow; }
 uint32_t first_sort_window(const EncodeJob& j) { uint32_t w = j.begin / kWindow; return w > 0 ? w - 1 : 0; }
 
 cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
-    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.R, b.off);
+    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.K2, b.off);
+    DFL_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32_t w_lo, uint32_t w_hi) {
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    if (w_hi <= w_lo) return cudaSuccess;
+    // enough CTAs to fill the chip even for a handful of windows
+    const uint32_t n_w = w_hi - w_lo;
+    uint32_t parts = (148u * DFL_MATCH_CTAS + n_w - 1) / n_w / (j.peers ? j.peers : 1u);
+    parts = parts > 16u ? 16u : (parts < 1u ? 1u : parts);
+    const dim3 grid(n_w, parts);
+    if (j.prm.need_quarter)
+        k_match<true><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
+    else
+        k_match<false><<<grid, kMatchThreads, kMatchSmem, st>>>(j.d_in, j.n, j.begin, w_lo, j.prm, b.K, b.off, b.Mf, b.Mq);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1365,30 +1803,25 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, 
 cudaError_t launch_parse(const EncodeJob& j, Buffers& b, cudaStream_t st) {
     ParseArgs A = make_parse_args(j, b);
     if (A.n_seg == 0) return cudaSuccess;
-    // persistent lanes: enough CTAs to fill the chip (less what the pipelines running beside this one take), fewer when
-    // there are fewer segments than that
-    const uint32_t n_cta = (A.n_seg + kParseThreads - 1) / kParseThreads;
-    const uint32_t fill = 148u * DFL_PARSE_CTAS / (j.peers ? j.peers : 1u);
-    const uint32_t grid = n_cta < fill ? n_cta : (fill ? fill : 1u);
-    const uint32_t vgrid = n_cta;
-    k_parse_spec<<<grid, kParseThreads, 0, st>>>(A, b.meta);   // (DevMeta::fetch is zero: the pipeline starts with a cleared DevMeta)
+    uint32_t grid = (A.n_seg + kParseThreads - 1) / kParseThreads;
+    k_parse_spec<<<grid, kParseThreads, 0, st>>>(A);
     DFL_LAUNCH_CHECK();
     if (A.n_seg == 1) return cudaSuccess;
     for (uint32_t r = 0, nr = repair_rounds(j.n - j.begin); r < nr; r++) {
         k_reset_bad<<<1, 1, 0, st>>>(b.meta);
         DFL_LAUNCH_CHECK();
-        k_parse_verify<<<vgrid, 128, 0, st>>>(A, b.seg_bad, b.seg_bad_list, b.seg_start_pos, b.seg_start_key, b.meta);
+        k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
         if (r & 1u) {   // the round before has given every chain of bad segments a true head; now the rest of each chain
             k_chain_predict<<<1, 1024, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key);
             DFL_LAUNCH_CHECK();
         }
-        k_parse_repair<<<grid, kParseThreads, 0, st>>>(A, b.seg_bad_list, b.seg_start_pos, b.seg_start_key, b.meta);
+        k_parse_repair<<<grid, kParseThreads, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
         DFL_LAUNCH_CHECK();
     }
     k_reset_bad<<<1, 1, 0, st>>>(b.meta);
     DFL_LAUNCH_CHECK();
-    k_parse_verify<<<vgrid, 128, 0, st>>>(A, b.seg_bad, b.seg_bad_list, b.seg_start_pos, b.seg_start_key, b.meta);
+    k_parse_verify<<<grid, 128, 0, st>>>(A, b.seg_bad, b.seg_start_pos, b.seg_start_key, b.meta);
     DFL_LAUNCH_CHECK();
     k_parse_repair_seq<<<1, 32, 0, st>>>(A, b.meta);
     DFL_LAUNCH_CHECK();
@@ -1412,7 +1845,7 @@ cudaError_t launch_token_layout(const EncodeJob& j, Buffers& b, cudaStream_t st)
     DFL_LAUNCH_CHECK();
     if (n_seg > 0) {
         ParseArgs A = make_parse_args(j, b);
-        k_compact<<<(n_seg + kCompactWarps - 1) / kCompactWarps, 32 * kCompactWarps, 0, st>>>(A, b.seg_cnt, b.seg_off, b.tok, b.meta);
+        k_compact<<<n_seg, 128, 0, st>>>(A, b.seg_cnt, b.seg_off, b.tok, b.meta);
         DFL_LAUNCH_CHECK();
     }
     return cudaSuccess;

@@ -29,10 +29,9 @@ struct Cfg {
 
 // ---- stage 1: per-window stable sort by hash3 into 64-bit entries (kernel k_window_sort)
 void window_sort(const uint8_t* d, uint32_t n, std::vector<Entry>& K, std::vector<uint16_t>& off,
-                 std::vector<uint16_t>& R, std::vector<uint32_t>& cnt) {
+                 std::vector<uint32_t>& cnt) {
     uint32_t nseg = (n + kWindow - 1) / kWindow;
-    K.assign((size_t)nseg * kWindow + 4, Entry{0, 0xfffe0000u});   // fillers as the kernel writes them (+ one group of slack)
-    R.assign((size_t)nseg * kWindow, 0);
+    K.assign((size_t)nseg * kWindow, Entry{0, 0});
     off.assign((size_t)nseg * kWindow, 0);
     cnt.assign(nseg, 0);
     uint32_t hashable = n >= 2 ? n - 2 : 0;   // positions p with p + 2 < n
@@ -50,32 +49,115 @@ void window_sort(const uint8_t* d, uint32_t n, std::vector<Entry>& K, std::vecto
             uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
             uint8_t b[8];
             for (uint32_t k = 0; k < 8; k++) b[k] = p + k < n ? d[p + k] : 0;   // bytes past the end are 0
-            R[p] = (uint16_t)cur[h];
             K[(size_t)s * kWindow + cur[h]++] = make_entry(i, b);
         }
     }
 }
 
-// ---- stage 2: one search (dfl_core.h search_begin / search_walk / search_long -- the functions the lanes of the parse
-// kernels step through), run to completion
-struct MatchData {            // what the sort leaves for the parser
-    std::vector<Entry> K;
-    std::vector<uint16_t> off, R;
-    std::vector<uint32_t> cnt;
-};
-uint64_t g_search_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // searches, group visits, long compares (8-byte steps), results
-uint32_t search_at(const uint8_t* d, uint32_t n, const MatchData& md, uint32_t p, uint32_t floor, uint32_t budget) {
-    SearchIn si{d, n, nullptr, md.K.data(), md.off.data(), md.R.data()};
-    Search S;
-    uint32_t st = search_begin(S, si, p, floor, budget);
-    g_search_stats[0]++;
-    while (st != kSearchDone) {
-        if (st == kSearchWalk) { g_search_stats[1]++; st = search_walk(S, si); }
-        else { g_search_stats[2]++; st = search_long(S, si); }
+// Candidates of sorted entry i of window s, most recent first (matching.rs:102-106,127): the entries in front of
+// it in its own bucket, then the tail of the same bucket of the previous window at distance <= 32768, at most
+// `budget` in total.  Visit k < n_own is Kw[i - 1 - k], visit k >= n_own is Kp[pe - 1 - (k - n_own)].
+struct CandRange { uint32_t n_own, n_tot, pe; const Entry* Kw; const Entry* Kp; };
+CandRange cand_range(const std::vector<Entry>& K, const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
+                     uint32_t s, uint32_t i, uint32_t h, uint32_t pl, uint32_t budget) {
+    CandRange c;
+    c.Kw = &K[(size_t)s * kWindow];
+    c.Kp = nullptr;
+    const uint16_t* ow = &off[(size_t)s * kWindow];
+    uint32_t s0 = ow[h];
+    c.n_own = std::min(budget, i - s0);
+    c.n_tot = c.n_own;
+    c.pe = 0;
+    if (s > 0 && c.n_own < budget) {
+        c.Kp = &K[(size_t)(s - 1) * kWindow];
+        const uint16_t* op = &off[(size_t)(s - 1) * kWindow];
+        uint32_t ps = op[h];
+        c.pe = (h + 1 < kWindow) ? op[h + 1] : cnt[s - 1];
+        uint32_t rem = budget - c.n_own;
+        uint32_t lo = (c.pe - ps > rem) ? c.pe - rem : ps;
+        while (lo < c.pe && entry_pos(c.Kp[lo].hi) < pl) lo++;
+        c.n_tot = c.n_own + (c.pe - lo);
     }
-    const uint32_t r = search_result(S);
-    if (r) g_search_stats[3]++;
-    return r;
+    return c;
+}
+
+// ---- stage 2: entry walk per sorted entry (kernel k_match): final records below 8 bytes, "long" records otherwise
+void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vector<Entry>& K,
+               const std::vector<uint16_t>& off, const std::vector<uint32_t>& cnt,
+               std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
+    Mf.assign(n, 0);
+    if (prm.need_quarter) Mq.assign(n, 0);
+    uint32_t nseg = (uint32_t)cnt.size();
+    for (uint32_t s = 0; s < nseg; s++) {
+        const Entry* Kw = &K[(size_t)s * kWindow];
+        for (uint32_t i = 0; i < cnt[s]; i++) {
+            Entry me = Kw[i];
+            uint32_t pl = entry_pos(me.hi);
+            uint32_t p = s * kWindow + pl;
+            uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
+            uint32_t maxl = std::min(kMaxMatch, n - p);
+            CandRange c = cand_range(K, off, cnt, s, i, h, pl, prm.checks);
+            EntryWalk st = ewalk_init(), sq = st;
+            uint32_t dist = 0, qdist = 0;
+            for (uint32_t k = 0; k < c.n_tot; k++) {
+                if (prm.need_quarter && k == prm.checks_quarter) { sq = st; qdist = dist; }
+                Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+                uint32_t before = st.best_len;
+                ewalk_visit(st, me, ce, k, maxl);
+                if (st.best_len != before) dist = (k < c.n_own ? pl : pl + kWindow) - entry_pos(ce.hi);
+            }
+            if (prm.need_quarter && c.n_tot <= prm.checks_quarter) { sq = st; qdist = dist; }
+            Mf[p] = ewalk_record(st, i, dist, maxl);
+            if (prm.need_quarter) Mq[p] = ewalk_record(sq, i, qdist, maxl);
+        }
+    }
+}
+
+// ---- stage 3a: resolution of a long record at a position the parser searches (warp-cooperative in k_parse*)
+// Every candidate from visit k8 on that shares the target's 8 entry bytes is compared on the data; the first
+// strictly longer one wins (matching.rs:148-157), starting from max(floor, 7): the caller only uses a result
+// longer than `floor` (= prev_length, matching.rs:161-165) and the record proves a length of at least 8.
+uint64_t g_resolve_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // resolutions, candidates compared, bytes compared, visits scanned
+uint32_t resolve_long(const uint8_t* d, uint32_t n, const std::vector<Entry>& K, const std::vector<uint16_t>& off,
+                      const std::vector<uint32_t>& cnt, uint32_t p, uint32_t rec, uint32_t floor, uint32_t budget,
+                      uint32_t full_budget) {
+    const uint32_t s = p / kWindow, pl = p % kWindow, i = rec_rank(rec);
+    const Entry me = K[(size_t)s * kWindow + i];
+    const uint32_t h = hash3(d[p], d[p + 1], d[p + 2]);
+    const uint32_t maxl = std::min(kMaxMatch, n - p);
+    CandRange c = cand_range(K, off, cnt, s, i, h, pl, full_budget);
+    const uint32_t n_vis = std::min(c.n_tot, budget);
+    uint32_t best = std::max(floor, kEntryBytes - 1u), best_q = 0;
+    g_resolve_stats[0]++;
+    for (uint32_t k = rec_k8(rec); k < n_vis; k++) {
+        g_resolve_stats[3]++;
+        Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+        if (ce.lo != me.lo || ((ce.hi ^ me.hi) & kEntryKeyHi) != 0u) continue;
+        uint32_t q = (k < c.n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
+        g_resolve_stats[1]++;
+        if (best < maxl && d[q + best] != d[p + best]) continue;   // cannot be longer than the running best
+        uint32_t l = kEntryBytes;
+        while (l < maxl && d[p + l] == d[q + l]) l++;
+        g_resolve_stats[2] += l - kEntryBytes;
+        if (l > best) { best = l; best_q = q; if (l == maxl) break; }
+    }
+    {   // statistics: is the nearest candidate that shares the 8 entry bytes already the answer?
+        uint32_t k = rec_k8(rec);
+        Entry ce = k < c.n_own ? c.Kw[i - 1 - k] : c.Kp[c.pe - 1 - (k - c.n_own)];
+        uint32_t q = (k < c.n_own ? s * kWindow : (s - 1) * kWindow) + entry_pos(ce.hi);
+        uint32_t l = 0; while (l < maxl && d[p + l] == d[q + l]) l++;
+        uint32_t want = best > std::max(floor, kEntryBytes - 1u) ? best : 0, got = l > std::max(floor, kEntryBytes - 1u) ? l : 0;
+        if (want == got) g_resolve_stats[4]++;
+        if (floor >= 8) g_resolve_stats[5]++;
+        if (want == 0) g_resolve_stats[6]++;
+    }
+    return best > std::max(floor, kEntryBytes - 1u) ? finalize_match(best, p - best_q) : 0u;
+}
+
+void find_matches(const uint8_t* in, uint32_t n, const Params& prm, std::vector<Entry>& S, std::vector<uint16_t>& off,
+                  std::vector<uint32_t>& cnt, std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
+    window_sort(in, n, S, off, cnt);
+    match_all(in, n, prm, S, off, cnt, Mf, Mq);
 }
 
 // ---- stage 3: speculative segment parse + hand-off verification + repair (k_parse*, k_verify)
@@ -85,25 +167,45 @@ struct SegRec {
     std::vector<uint32_t> toks;
 };
 
-// Token sink of the model: literal bytes are looked up as the token is written (the kernels defer exactly this
-// look-up to k_compact).
+// What the match stage leaves for the parser: the records and the sorted lists they refer to.
+struct MatchData {
+    std::vector<Entry> K;
+    std::vector<uint16_t> off;
+    std::vector<uint32_t> cnt, Mf, Mq;
+};
+
+// Token sink of the model: distances and literal bytes are looked up as the token is written (the kernels defer
+// exactly these two look-ups to k_compact).
 struct ModelSink {
-    const uint8_t* d; std::vector<uint32_t>* toks;
+    const uint8_t* d; const MatchData* md; std::vector<uint32_t>* toks;
+    uint32_t dist_of(uint32_t ref, uint32_t kind) const {
+        return kind == kRefDist ? ref : match_dist((kind == kRefQuarter ? md->Mq : md->Mf)[ref]);
+    }
     void literal(uint32_t pos) { toks->push_back(tok_literal(d[pos])); }
-    void match(uint32_t len, uint32_t ref, uint32_t) { toks->push_back(tok_match(len, ref)); }
+    void match(uint32_t len, uint32_t ref, uint32_t kind) { toks->push_back(tok_match(len, dist_of(ref, kind))); }
 };
 
 void step(const Params& prm, ParseState& st, uint32_t n, const uint8_t* d, const MatchData& md, ModelSink& out) {
     uint32_t p = st.pos;
-    const bool has_m = prm.mode != kRle && prm.checks > 0 && p + 2 < n;
-    uint32_t m = 0;
+    const bool has_m = prm.mode != kRle && p + 2 < n && !md.Mf.empty();
+    uint32_t m_len = 0, m_ref = 0, m_kind = kRefDist;
+    auto take = [&](uint32_t rec, bool quarter, uint32_t floor) {
+        if (rec_is_long(rec)) {      // resolved now: the distance is known
+            uint32_t m = resolve_long(d, n, md.K, md.off, md.cnt, p, rec, floor, quarter ? prm.checks_quarter : prm.checks, prm.checks);
+            m_len = match_len(m); m_ref = m_len ? match_dist(m) : 0; m_kind = kRefDist;
+        } else {                     // final record: only its length is needed to decide; the distance stays behind `p`
+            m_len = match_len(rec); m_ref = p; m_kind = quarter ? kRefQuarter : kRefFull;
+        }
+    };
     if (prm.mode == kLazy) {
-        if (has_m && !st.ign)                         // the only case in which the reference searches (lz77.rs:347)
-            m = search_at(d, n, md, p, st.prev_len, st.prev_len >= 32u ? prm.checks_quarter : prm.checks);   // lz77.rs:351-355
-        lazy_step(st, n, match_len(m), m ? match_dist(m) : 0u, kRefDist, prm.lazy, out);
+        if (has_m && !st.ign) {                       // the only case in which the reference searches (lz77.rs:347)
+            const bool quarter = st.prev_len >= 32u;  // lz77.rs:351-355
+            if (!quarter || prm.need_quarter) take(quarter ? md.Mq[p] : md.Mf[p], quarter, st.prev_len);
+        }
+        lazy_step(st, n, m_len, m_ref, m_kind, prm.lazy, out);
     } else if (prm.mode == kGreedy) {
-        if (has_m) m = search_at(d, n, md, p, 0u, prm.checks);
-        greedy_step(st, n, match_len(m), m ? match_dist(m) : 0u, kRefDist, out);
+        if (has_m) take(md.Mf[p], false, 0);
+        greedy_step(st, n, m_len, m_ref, m_kind, out);
     } else {
         rle_step(st, n, d, out);
     }
@@ -114,8 +216,8 @@ void parse_segment(const Params& prm, const uint8_t* d, uint32_t n, const MatchD
     // runs from `st` until the first iteration position >= b (or the end of data)
     r.toks.clear();
     bool have_e = false;
-    ModelSink out{d, &r.toks};
-    auto key = [&](const ParseState& s) { return parse_state_key(s, s.prev_len ? s.prev_ref : 0u); };
+    ModelSink out{d, &md, &r.toks};
+    auto key = [&](const ParseState& s) { return parse_state_key(s, s.prev_len ? out.dist_of(s.prev_ref, s.prev_kind) : 0u); };
     while (st.pos < n) {
         if (!have_e && st.pos >= a) { r.e_pos = st.pos; r.e_key = key(st); r.e_tok = (uint32_t)r.toks.size(); have_e = true; }
         if (st.pos >= b) break;
@@ -306,7 +408,7 @@ int dflm_compress(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy,
     if (prm.mode == kLazy && prm.lazy < 3) {          // the library's dispatch: k_lz77_seq
         sequential_tokens(in, n, prm, tokens);
     } else {
-        if (prm.mode != kRle && prm.checks > 0) window_sort(in, n, md.K, md.off, md.R, md.cnt);
+        if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
         parse_all(prm, cfg, in, n, md, tokens);
     }
     std::vector<uint8_t> o;
@@ -328,7 +430,7 @@ int dflm_tokens(const uint8_t* in, uint32_t n, uint16_t checks, uint16_t lazy, u
     if (prm.mode == kLazy && prm.lazy < 3) {          // the library's dispatch: k_lz77_seq
         sequential_tokens(in, n, prm, tokens);
     } else {
-        if (prm.mode != kRle && prm.checks > 0) window_sort(in, n, md.K, md.off, md.R, md.cnt);
+        if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
         parse_all(prm, cfg, in, n, md, tokens);
     }
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
@@ -344,7 +446,7 @@ int dflm_tokens_from(const uint8_t* in, uint32_t n, uint32_t begin, uint16_t che
     Cfg cfg{8192, 1024, 3};
     std::vector<uint32_t> tokens;
     MatchData md;
-    if (prm.mode != kRle && prm.checks > 0) window_sort(in, n, md.K, md.off, md.R, md.cnt);
+    if (prm.mode != kRle && prm.checks > 0) find_matches(in, n, prm, md.K, md.off, md.cnt, md.Mf, md.Mq);
     parse_all(prm, cfg, in, n, md, tokens, begin);
     *toks = (uint32_t*)malloc(tokens.size() * 4 + 4);
     memcpy(*toks, tokens.data(), tokens.size() * 4);
@@ -360,88 +462,8 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 void dflm_free(void* p) { free(p); }
 uint32_t dflm_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return crc32_combine(c1, c2, len2); }
 uint32_t dflm_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
-void dflm_search_stats(uint64_t* o /*[8]*/, int reset) {
-    for (int i = 0; i < 8; i++) { o[i] = g_search_stats[i]; if (reset) g_search_stats[i] = 0; }
+void dflm_resolve_stats(uint64_t* o /*[8]*/, int reset) {
+    for (int i = 0; i < 8; i++) { o[i] = g_resolve_stats[i]; if (reset) g_resolve_stats[i] = 0; }
 }
 
-}
-
-// ---- diagnostics: the section scheduler of parse_lanes (dfl_kernels.cu), simulated for one warp at a time.
-// Counts section executions and lanes served under a given policy; no output is produced.
-namespace {
-struct SimLane {
-    ParseState st; uint32_t a, b; uint32_t state; bool have_res; Search S; std::vector<uint32_t> toks;
-};
-}
-extern "C" void dflm_simulate(const uint8_t* d, uint32_t n, uint16_t checks, uint16_t lazy, uint8_t mtype, uint32_t pseg,
-                              uint32_t warm, int policy, const uint32_t* w /*[4] weights walk, step, long, age*/, int dynamic,
-                              uint32_t n_warps, uint64_t* o /*[16]*/) {
-    Params prm = make_params(checks, lazy, mtype);
-    MatchData md;
-    window_sort(d, n, md.K, md.off, md.R, md.cnt);
-    SearchIn si{d, n, nullptr, md.K.data(), md.off.data(), md.R.data()};
-    const uint32_t nseg = (n + pseg - 1) / pseg;
-    for (int i = 0; i < 16; i++) o[i] = 0;
-    uint32_t next_seg = 0;   // dynamic fetching: shared by the simulated warps in turn (approximation)
-    for (uint32_t wi = 0; wi < n_warps; wi++) {
-        std::vector<SimLane> L(32);
-        auto start_seg = [&](SimLane& ln, uint32_t s) {
-            ln.a = s * pseg; ln.b = std::min(n, ln.a + pseg);
-            uint32_t start = ln.a > warm ? ln.a - warm : 0;
-            ln.st = parse_state_init(start); ln.state = 0; ln.have_res = false; ln.toks.clear();
-        };
-        for (uint32_t l = 0; l < 32; l++) {
-            uint32_t s = dynamic ? next_seg++ : l * n_warps + wi;
-            if (s < nseg) start_seg(L[l], s); else L[l].state = 3;
-        }
-        uint32_t age[3] = {0, 0, 0};
-        for (;;) {
-            uint32_t c[3] = {0, 0, 0};   // step, walk, long
-            for (auto& ln : L) if (ln.state < 3) c[ln.state]++;
-            if (c[0] + c[1] + c[2] == 0) break;
-            int sel;
-            if (policy == 0) {   // weighted count + ageing
-                uint32_t sw = c[1] ? c[1] * w[0] + age[1] : 0, ss = c[0] ? c[0] * w[1] + age[0] : 0, sl = c[2] ? c[2] * w[2] + age[2] : 0;
-                sel = (sw >= ss && sw >= sl) ? 1 : (sl >= ss ? 2 : 0);
-            } else if (policy == 2) {   // warp-synchronous rounds: walk while anybody can, then the waiting compares, then everybody steps
-                sel = c[1] ? 1 : (c[2] ? 2 : 0);
-            } else if (policy == 3) {   // like 2, but compares are served as soon as a quarter of the searching lanes wait for one
-                sel = (c[2] && c[2] * 3 >= c[1]) ? 2 : (c[1] ? 1 : (c[2] ? 2 : 0));
-            } else {             // everything that is non-empty runs every iteration
-                sel = -1;
-            }
-            for (int x = 0; x < 3; x++) {
-                if (sel >= 0 && x != sel) { if (c[x]) age[x] += w[3]; continue; }
-                if (!c[x]) continue;
-                age[x] = 0;
-                o[x * 2]++; o[x * 2 + 1] += c[x];
-            }
-            o[6]++;
-            for (auto& ln : L) {
-                if (ln.state == 3 || (sel >= 0 && (int)ln.state != sel)) continue;
-                ModelSink out{d, &ln.toks};
-                auto do_step = [&](uint32_t m) {
-                    if (prm.mode == kLazy) lazy_step(ln.st, n, match_len(m), m ? match_dist(m) : 0u, kRefDist, prm.lazy, out);
-                    else greedy_step(ln.st, n, match_len(m), m ? match_dist(m) : 0u, kRefDist, out);
-                };
-                if (ln.state == 1) { uint32_t r = search_walk(ln.S, si); ln.state = r == kSearchWalk ? 1 : (r == kSearchLong ? 2 : 0); ln.have_res = r == kSearchDone; }
-                else if (ln.state == 2) { uint32_t r = search_long(ln.S, si); ln.state = r == kSearchWalk ? 1 : (r == kSearchLong ? 2 : 0); ln.have_res = r == kSearchDone; }
-                else {
-                    if (ln.have_res) { do_step(search_result(ln.S)); ln.have_res = false; }
-                    if (ln.st.pos >= n || ln.st.pos >= ln.b) {
-                        o[7] += ln.b - ln.a;
-                        uint32_t s = dynamic ? next_seg++ : nseg;
-                        if (s < nseg) start_seg(ln, s); else ln.state = 3;
-                    } else {
-                        uint32_t p = ln.st.pos;
-                        if (p + 2 < n && (prm.mode != kLazy || !ln.st.ign)) {
-                            uint32_t r = search_begin(ln.S, si, p, prm.mode == kLazy ? ln.st.prev_len : 0u,
-                                                      (prm.mode == kLazy && ln.st.prev_len >= 32u) ? prm.checks_quarter : prm.checks);
-                            if (r == kSearchDone) do_step(0); else ln.state = 1;
-                        } else do_step(0);
-                    }
-                }
-            }
-        }
-    }
 }

@@ -29,16 +29,17 @@ def lib():
         L.dflm_crc32_combine.restype = ctypes.c_uint32
         L.dflm_adler32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
         L.dflm_adler32_combine.restype = ctypes.c_uint32
-        L.dflm_search_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
+        L.dflm_resolve_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
         _lib = L
     return _lib
 
 
-def search_stats(reset=True):
-    """Counters of the searches the parser ran since the last reset."""
+def resolve_stats(reset=True):
+    """Counters of the long-match resolutions the parser asked for since the last reset."""
     st = (ctypes.c_uint64 * 8)()
-    lib().dflm_search_stats(st, 1 if reset else 0)
-    return {"searches": st[0], "group_visits": st[1], "long_steps": st[2], "results": st[3]}
+    lib().dflm_resolve_stats(st, 1 if reset else 0)
+    return {"resolutions": st[0], "candidates": st[1], "bytes": st[2], "visits": st[3], "nearest_is_answer": st[4],
+            "floor_ge_8": st[5], "no_result": st[6]}
 
 
 def compress(data, opts, pseg=8192, warm=1024, rounds=4):
