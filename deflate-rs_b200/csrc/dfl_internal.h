@@ -10,37 +10,54 @@ namespace dfl {
 
 // Tunables of the parse stage (see DESIGN.md "parse").
 #ifndef DFL_PARSE_SEG
-#define DFL_PARSE_SEG 4096
+#define DFL_PARSE_SEG 8192
 #endif
 #ifndef DFL_PARSE_WARM
-#define DFL_PARSE_WARM 512
+#define DFL_PARSE_WARM 256
 #endif
 constexpr uint32_t kParseSeg = DFL_PARSE_SEG;     // positions owned by one parse thread (large inputs)
 constexpr uint32_t kParseWarm = DFL_PARSE_WARM;   // speculative warm-up before the segment start
+#ifndef DFL_PARSE_WARM_GREEDY
+#define DFL_PARSE_WARM_GREEDY 256
+#endif
+constexpr uint32_t kParseSegGreedy = kParseSeg, kParseWarmGreedy = DFL_PARSE_WARM_GREEDY;   // the greedy parser (large inputs)
+static_assert(kParseSeg + kParseWarm + 300u + 264u < 16384u && kParseSegGreedy + kParseWarmGreedy + 564u < 16384u,
+              "deferred literal tokens carry a 14-bit position relative to the segment (kTokRelMask)");
 // One parse thread walks its segment sequentially, so for small inputs the segment length *is* the
 // latency of the stage: shorter segments there (any length gives the same tokens, hand-offs are
 // verified and repaired).  seg + warm + 264 tokens of buffer per segment.
-// The greedy parser (Compression::Fast) does less per position and prefers longer segments on large inputs
-// (1 GiB: 4.5 ms with 8 KiB + 1 KiB, 5.9 ms with 4 KiB + 512 B; the lazy parser 7.8 against 7.1 ms).
+// Large inputs, 1 GiB at Default on B200 (tools/tune_variants.sh): 8 KiB + 256 B parses in 74 ms, 8 KiB + 512 B
+// in 78, 4 KiB + 512 B in 80, 8 KiB + 1 KiB in 82, 6 KiB or 10 KiB + 512 B in 96 / 89 (segments that are not a
+// power of two fall across the strided segment order of a warp).  The warm-up is parsed twice; 256 bytes
+// resynchronise all but a few segments per GiB, which the repair rounds re-parse.
 struct ParseGeom { uint32_t seg, warm; };
+#ifndef DFL_PARSE_WARM_MID
+#define DFL_PARSE_WARM_MID 256
+#endif
 inline ParseGeom parse_geom(size_t payload, int mode) {
     if (payload <= (32u << 20)) return {1024u, 512u};
-    if (payload <= (256u << 20)) return {2048u, 512u};
-    if (mode == kGreedy) return {2u * kParseSeg, 2u * kParseWarm};
-    return {kParseSeg, kParseWarm};
+    // about one segment per parse lane (148 SMs x 7 CTAs x 128 threads = 132 608), a power of two from 2 KiB up to the
+    // large-input segment: 256 MiB in 8 KiB segments leaves three quarters of the lanes without work (parse 69 ms
+    // against 30 ms with 2 KiB segments, CompressionOptions::high())
+    uint32_t seg = 2048u;
+    while (seg < kParseSeg && payload / seg > 196608u) seg <<= 1;
+    if (seg < kParseSeg) return {seg, (uint32_t)DFL_PARSE_WARM_MID};
+    return {kParseSeg, mode == kGreedy ? kParseWarmGreedy : kParseWarm};
 }
 inline uint32_t parse_tok_cap(ParseGeom g) { return g.seg + g.warm + 264u; }
 inline size_t parse_n_seg(size_t payload, ParseGeom g) { return (payload + g.seg - 1) / g.seg; }
 // u32 words of segment token buffers needed for a payload of at most `cap` bytes, whatever its geometry
 inline size_t parse_buffer_words(size_t cap) {
     size_t best = 0;
-    const size_t edges[3] = {cap < (32u << 20) ? cap : (32u << 20), cap < (256u << 20) ? cap : (256u << 20), cap};
-    for (size_t e : edges)
+    const size_t edges[5] = {(size_t)32u << 20, (size_t)384u << 20, (size_t)768u << 20, (size_t)1536u << 20, cap};   // sizes at which the geometry changes
+    for (size_t e0 : edges) {
+        const size_t e = e0 < cap ? e0 : cap;
         for (int mode : {(int)kGreedy, (int)kLazy}) {
             ParseGeom g = parse_geom(e, mode);
             size_t w = (parse_n_seg(e, g) + 1) * parse_tok_cap(g);
             if (w > best) best = w;
         }
+    }
     return best;
 }
 // Parallel repair rounds before the sequential fallback; every second one predicts the phase of chains of
@@ -127,6 +144,11 @@ struct Buffers {   // device scratch of one context, grown on demand
 inline bool use_seq_lz77(const Params& p, uint32_t begin, int open_piece, uint32_t init_key, uint32_t n_carry_tok) {
     return p.mode == kLazy && p.lazy < 3u && begin == 0 && !open_piece && init_key == 0 && n_carry_tok == 0;
 }
+
+// max_hash_checks == 1 (Compression::Fast): the one candidate of a position is its predecessor in the bucket; the
+// sort kernel settles the matches itself (k_window_sort<true>, k_match_first).  Not with a quarter-budget record
+// (lazy_if_less_than > 32: that budget is 0).
+inline bool one_candidate(const Params& p) { return p.checks == 1u && p.mode != kRle && !p.need_quarter; }
 
 struct EncodeJob {
     const uint8_t* d_in;     // device input (history + payload)

@@ -134,9 +134,18 @@ static_assert(kWindow + 32 <= kSortCntWords * 4, "byte staging must fit in the c
 // word w of a counter row is stored at slot_of(w): its 32-word group rotated by the group number
 __device__ __forceinline__ uint32_t sort_slot_of(uint32_t w) { return (w & ~31u) | ((w + (w >> 5)) & 31u); }
 
+//   ONE (max_hash_checks == 1, e.g. Compression::Fast): the only candidate of a position is its predecessor in the
+//   bucket (chained_hash_table.rs:148-158: the head of the chain when the position is inserted), and that is the
+//   neighbouring item of the sorted order.  So the match is settled right here, on the bytes that are staged
+//   anyway: the kernel writes the per-position match records instead of candidate lists, and `off` receives the
+//   last position of every bucket (0xffff: none) for k_match_first, which settles the positions whose predecessor
+//   lies in the previous window.  No lists, no k_match.
+constexpr uint32_t kRecFirst = 0xffffffffu;   // ONE: provisional record of the first position of a bucket in its window
+template <bool ONE>
 __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* __restrict__ in, uint32_t n,
                                                                  uint32_t w_first, uint2* __restrict__ K,
-                                                                 uint2* __restrict__ K2, uint16_t* __restrict__ off) {
+                                                                 uint2* __restrict__ K2, uint16_t* __restrict__ off,
+                                                                 uint32_t* __restrict__ Mf) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* cntw = reinterpret_cast<uint32_t*>(smem);                        // kSortCntWords
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem);
@@ -244,6 +253,47 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_window_sort(const uint8_t* 
         __syncthreads();
     }
 
+    if (ONE) {
+        // ---- match records: every item against its predecessor in the sorted order, if that is in the same bucket
+        stage_bytes(smem, in, (long long)base, kWindow + 272, n);   // counters are dead; bytes again, with the look-ahead
+        __syncthreads();
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem);
+        for (uint32_t r = t; r < cnt; r += kSortThreads) {
+            const uint32_t it = buf[r + (r >> 5)];
+            const uint32_t pos = it & 0x7fffu, h = it >> 15;
+            uint32_t rec = kRecFirst;
+            if (r > 0) {
+                const uint32_t itp = buf[(r - 1) + ((r - 1) >> 5)];
+                if ((itp >> 15) == h) {
+                    const uint32_t q = itp & 0x7fffu;                 // q < pos: the sort is stable
+                    const uint32_t left = n - (base + pos), maxl = left < kMaxMatch ? left : kMaxMatch;
+                    uint32_t l = 0;
+                    while (l < maxl) {
+                        const uint32_t x = lds32(sw, pos + l) ^ lds32(sw, q + l);
+                        if (x != 0u) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        l += 4u;
+                    }
+                    rec = finalize_match(l < maxl ? l : maxl, pos - q);
+                }
+            }
+            Mf[base + pos] = rec;
+        }
+        __syncthreads();
+        // ---- last position of every bucket
+        uint16_t* st = reinterpret_cast<uint16_t*>(smem);
+        for (uint32_t i = t; i < kWindow / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(st)[i] = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t r = t; r < cnt; r += kSortThreads) {
+            const uint32_t it = buf[r + (r >> 5)];
+            const uint32_t hn = r + 1u < cnt ? (buf[(r + 1) + ((r + 1) >> 5)] >> 15) : 0xffffffffu;
+            if ((it >> 15) != hn) st[it >> 15] = (uint16_t)(it & 0x7fffu);
+        }
+        __syncthreads();
+        uint4* o4 = reinterpret_cast<uint4*>(off + (size_t)w * kWindow);
+        const uint4* s4 = reinterpret_cast<const uint4*>(smem);
+        for (uint32_t i = t; i < kWindow * 2u / 16u; i += kSortThreads) o4[i] = s4[i];
+        return;
+    }
     // ---- output: entries in bucket order
     {
     stage_bytes(smem, in, (long long)base, kWindow + 32, n);   // counters are dead; bytes again
@@ -403,7 +453,7 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_s
 __device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 
 #ifndef DFL_MATCH_CTAS
-#define DFL_MATCH_CTAS 4
+#define DFL_MATCH_CTAS 3      // CTAs of 512 threads per SM k_match is compiled for: 40 registers (at 4, 32 registers, the walk is 7 % slower)
 #endif
 template <bool NEEDQ>
 __global__ void __launch_bounds__(kMatchThreads, DFL_MATCH_CTAS)
@@ -529,6 +579,44 @@ k_match(const uint8_t* __restrict__ in, uint32_t n, uint32_t begin, uint32_t w_f
                 if (rec_is_long(rq) && n_tot == 1u) rq = rec;      // the one candidate there is: settled above
                 Mq[p] = rq;
             }
+        }
+    }
+}
+
+// k_match_first (max_hash_checks == 1): the positions k_window_sort<true> left open -- the first of their bucket in
+// their window -- have their one candidate in the previous window: the last position of the same bucket there, if
+// it is within the window (matching.rs:102-106,127).
+__global__ void __launch_bounds__(256) k_match_first(const uint8_t* __restrict__ in, uint32_t n, uint32_t w_first,
+                                                     const uint16_t* __restrict__ off, uint32_t* __restrict__ Mf) {
+    const uint32_t w = w_first + blockIdx.x / 4u, part = blockIdx.x % 4u;   // four CTAs per window
+    const uint32_t base = w * kWindow, cnt = window_count(n, w);
+    const uint32_t* last_word = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(in + (n ? n - 1 : 0)) & ~(uintptr_t)3);
+    // four records per thread and load: almost all of them are settled already, so this is a streaming pass
+    for (uint32_t g = part * (kWindow / 4u) + threadIdx.x * 4u; g < (part + 1u) * (kWindow / 4u) && g < cnt; g += blockDim.x * 4u) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(Mf + base + g));
+        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++) {
+            const uint32_t pl = g + k;
+            if (rr[k] != kRecFirst || pl >= cnt) continue;
+            const uint32_t p = base + pl;
+            uint32_t rec = 0u;
+            if (w > 0u) {
+                const uint32_t h = hash3(in[p], in[p + 1u], in[p + 2u]);
+                const uint32_t ql = off[(size_t)(w - 1u) * kWindow + h];
+                if (ql != 0xffffu && ql >= pl) {                            // distance <= 32768
+                    const uint32_t d = pl + kWindow - ql;
+                    const uint32_t maxl = (n - p) < kMaxMatch ? (n - p) : kMaxMatch;
+                    uint32_t l = 0;
+                    while (l < maxl) {
+                        const unsigned long long x = ld8(in, last_word, p + l) ^ ld8(in, last_word, p - d + l);
+                        if (x != 0ull) { l += (uint32_t)(__ffsll((long long)x) - 1) >> 3; break; }
+                        l += 8u;
+                    }
+                    rec = finalize_match(l < maxl ? l : maxl, d);
+                }
+            }
+            Mf[p] = rec;
         }
     }
 }
@@ -1756,7 +1844,9 @@ static cudaError_t ensure_attrs() {
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lk(mu);
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-    e = cudaFuncSetAttribute(k_window_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    e = cudaFuncSetAttribute(k_window_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_window_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem);
     if (e != cudaSuccess) return e;
@@ -1778,7 +1868,10 @@ cudaError_t launch_window_sort(const EncodeJob& j, Buffers& b, cudaStream_t st, 
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
-    k_window_sort<<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.K2, b.off);
+    if (one_candidate(j.prm))
+        k_window_sort<true><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.K2, b.off, b.Mf);
+    else
+        k_window_sort<false><<<w_hi - w_lo, kSortThreads, kSortSmem, st>>>(j.d_in, j.n, w_lo, b.K, b.K2, b.off, b.Mf);
     DFL_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1787,6 +1880,11 @@ cudaError_t launch_match(const EncodeJob& j, Buffers& b, cudaStream_t st, uint32
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     if (w_hi <= w_lo) return cudaSuccess;
+    if (one_candidate(j.prm)) {   // the sort has settled everything but the first position of every bucket
+        k_match_first<<<(w_hi - w_lo) * 4u, 256, 0, st>>>(j.d_in, j.n, w_lo, b.off, b.Mf);
+        DFL_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     // enough CTAs to fill the chip even for a handful of windows
     const uint32_t n_w = w_hi - w_lo;
     uint32_t parts = (148u * DFL_MATCH_CTAS + n_w - 1) / n_w / (j.peers ? j.peers : 1u);
