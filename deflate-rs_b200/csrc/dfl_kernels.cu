@@ -1053,21 +1053,25 @@ __global__ void __launch_bounds__(32) k_parse_repair_seq(ParseArgs A, DevMeta* m
     __shared__ ParseShared sh;
     if (meta->n_bad == 0) return;
     const uint32_t lane = lane_id();
-    for (uint32_t s = 1; s < A.n_seg; s++) {
-        uint32_t xp = 0, xk = 0, isbad = 0;
-        if (lane == 0) {
-            xp = A.x_pos[s - 1]; xk = A.x_key[s - 1];
-            isbad = (xp != A.e_pos[s] || xk != A.e_key[s]) ? 1u : 0u;
-        }
-        isbad = __shfl_sync(0xffffffffu, isbad, 0);
-        if (isbad) {
-            const uint32_t a = A.begin + s * A.seg;
-            const uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
-            parse_lanes(A, sh, lane == 0, s, state_from_key(xp, xk), a, b);
-            if (lane == 0) meta->n_repaired_seq++;
-            __threadfence();
-            __syncwarp();
-        }
+    // The hand-offs are checked 32 at a time (on an input of a few byte values, issue_44-like, a handful of bad
+    // segments per MiB survive the parallel rounds: walking 131 072 hand-offs one by one took 64 ms per 256 MiB).
+    // A repair changes the exit of its segment, so the scan goes on right behind it.  (__ldcg: what lane 0 has just
+    // written must be seen by the other lanes.)
+    uint32_t s = 1;
+    while (s < A.n_seg) {
+        const uint32_t t = s + lane;
+        const bool isbad = t < A.n_seg && (__ldcg(A.x_pos + t - 1) != __ldcg(A.e_pos + t) || __ldcg(A.x_key + t - 1) != __ldcg(A.e_key + t));
+        const uint32_t m = __ballot_sync(0xffffffffu, isbad);
+        if (m == 0u) { s += 32u; continue; }
+        s += (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t xp = __ldcg(A.x_pos + s - 1), xk = __ldcg(A.x_key + s - 1);
+        const uint32_t a = A.begin + s * A.seg;
+        const uint32_t b = a + A.seg < A.end ? a + A.seg : A.end;
+        parse_lanes(A, sh, lane == 0, s, state_from_key(xp, xk), a, b);
+        if (lane == 0) meta->n_repaired_seq++;
+        __threadfence();
+        __syncwarp();
+        s += 1u;
     }
     if (lane == 0) meta->n_bad = 0;
 }

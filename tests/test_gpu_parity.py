@@ -391,20 +391,23 @@ def test_pieces_concatenate_to_the_flushed_reference_stream(dfl, pg11):
     cases = ((pg11, sharding.piece_bounds(len(pg11), 3, 4096)),
              (datagen.silesia_mix(3 << 20), sharding.piece_bounds(3 << 20, 4, 1 << 16)),
              (pg11, small))
-    for data, bounds in cases:
-        src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
-        bounds = [b for b in bounds if b[1] > b[0]]
-        s = o.Stream(o.opts_default(), o.RAW)
-        got = b""
-        for g, (lo, hi) in enumerate(bounds):
-            last = g + 1 == len(bounds)
-            out, n = sharding.encode_piece_device(src, lo, hi, dfl.Compression.Default, last)
-            got += bytes(out[:n].cpu().numpy())
-            s.write(data[lo:hi])
-            if not last:
-                s.flush()
-        assert got == s.finish(), (len(data), len(bounds))
-        assert zlib.decompress(got, -15) == data
+    # Compression::Fast takes the one-candidate path (the sort kernel settles the matches; the candidate of the first
+    # position of a bucket lies in the window in front, which for a piece may be dictionary only)
+    for preset, oopts in ((dfl.Compression.Default, o.opts_default()), (dfl.Compression.Fast, o.opts_fast())):
+        for data, bounds in cases:
+            src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+            bounds = [b for b in bounds if b[1] > b[0]]
+            s = o.Stream(oopts, o.RAW)
+            got = b""
+            for g, (lo, hi) in enumerate(bounds):
+                last = g + 1 == len(bounds)
+                out, n = sharding.encode_piece_device(src, lo, hi, preset, last)
+                got += bytes(out[:n].cpu().numpy())
+                s.write(data[lo:hi])
+                if not last:
+                    s.flush()
+            assert got == s.finish(), (len(data), len(bounds), preset)
+            assert zlib.decompress(got, -15) == data
 
 
 def test_sync_flush_inside_first_window_is_valid_but_not_the_reference_quirk(dfl, pg11):
