@@ -181,7 +181,7 @@ def run_reference(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{args.size_mib} MiB {cfg['desc']}, {cfg['opts']}",
                    "sample": f"first {sample >> 20} MiB per step", "ratio": csize / sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "flags": "gcc -O2 (oracle/Makefile; built in the dev container, so no -march=native: the binary travels to the GPU box)",
                          "sample": f"first {sample >> 20} MiB of the workload per step, oracle/ (C port of the reference "
                                    "algorithm; the Rust crate is single-threaded and cannot be built here)",
                          "independent_streams_all_cores": {"value": all_cores, "unit": UNIT, "cores": cores,
@@ -329,7 +329,7 @@ def run_chunks(args):
             "e2e": {"value": total_in / float(te.item()) / 2 ** 20, "unit": UNIT, "h2d_bytes_per_step": chunk * len(mine),
                     "d2h_bytes_per_step": int(csize)},
             "gpu_launches": None, "clocks": clk,
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "flags": "gcc -O2 (oracle/Makefile; built in the dev container, so no -march=native: the binary travels to the GPU box)",
                              "sample": f"one chunk ({chunk >> 20} MiB), oracle/, {cpu_dt:.1f} s", "ratio": cpu_csize / min(chunk, args.cpu_sample_mib << 20)},
         }
         emit(line)
@@ -527,7 +527,7 @@ def run_ours(args):
             "stage_ms": {k: v / args.steps for k, v in stage_tot.items()},
             "per_rank": per_rank,
             "bounded_mode": bounded,
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "flags": "gcc -O2 (oracle/Makefile; built in the dev container, so no -march=native: the binary travels to the GPU box)",
                              "sample": f"first {cpu_sample >> 20} MiB of the same input, oracle/ (C port of the reference "
                                        f"algorithm), {cpu_dt:.1f} s", "ratio": cpu_csize / cpu_sample},
         }

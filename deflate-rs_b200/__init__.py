@@ -184,6 +184,12 @@ def deflate_bytes_gzip(input):
     return deflate_bytes_gzip_conf(input, Compression.Default, GzBuilder())
 
 
+def trim() -> None:
+    """dfl_trim: gives back the device scratch the library keeps between calls for the calling thread (one-shot
+    context, batch pools) and the process-wide pool of parked handle resources."""
+    _native.lib().dfl_trim()
+
+
 def compress_device(src, options=Compression.Default, wrap=RAW, out=None, stream=None):
     """Device-resident encode: `src` and `out` are CUDA uint8 torch tensors.  Returns (out, n_bytes).
 

@@ -20,7 +20,7 @@ COMM_ID_BYTES = 128
 # every symbol include/deflate_b200.h declares
 EXPORTS = [
     "dfl_options_preset", "dfl_strerror", "dfl_last_cuda_error", "dfl_version", "dfl_device_count", "dfl_bound",
-    "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_compress_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters",
+    "dfl_compress", "dfl_compress_device", "dfl_compress_device_piece", "dfl_compress_device_batch", "dfl_compress_batch", "dfl_set_profiling", "dfl_last_stage_times", "dfl_last_counters", "dfl_trim",
     "dfl_encoder_new", "dfl_encoder_write", "dfl_encoder_flush", "dfl_encoder_set_piece_bytes", "dfl_encoder_take_output",
     "dfl_encoder_advance_output", "dfl_encoder_checksum", "dfl_encoder_reset", "dfl_encoder_free",
     "dfl_adler32_device", "dfl_crc32_device", "dfl_encode_tokens", "dfl_lz77_tokens",

@@ -442,9 +442,18 @@ struct InputArrival {
     }
 };
 
-Context& tls_context() {   // one per calling thread and device
+// Scratch that outlives a call, per calling thread and device: the context of the one-shot calls and the two pools
+// of 16 the batch calls rotate over.  dfl_trim() gives all of it back.
+std::map<int, std::unique_ptr<Context>>& tls_contexts() {
     thread_local std::map<int, std::unique_ptr<Context>> ctxs;
-    std::unique_ptr<Context>& ctx = ctxs[current_device()];
+    return ctxs;
+}
+std::map<int, std::vector<std::unique_ptr<Context>>>& tls_batch_pools(int which) {
+    thread_local std::map<int, std::vector<std::unique_ptr<Context>>> pools[2];
+    return pools[which];
+}
+Context& tls_context() {   // one per calling thread and device
+    std::unique_ptr<Context>& ctx = tls_contexts()[current_device()];
     if (!ctx) ctx.reset(new Context());
     return *ctx;
 }
@@ -968,8 +977,7 @@ extern "C" int dfl_compress_device_batch(size_t count, const void* const* d_in, 
                                          int* status) {
     if (!opt || !valid_wrap(wrap) || (count && (!d_in || !n || !d_out || !out_cap || !out_len))) return DFL_E_ARG;
     constexpr size_t kBatchLanes = 16;
-    thread_local std::map<int, std::vector<std::unique_ptr<Context>>> pools;   // per device
-    std::vector<std::unique_ptr<Context>>& pool = pools[current_device()];
+    std::vector<std::unique_ptr<Context>>& pool = tls_batch_pools(0)[current_device()];
     const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
     while (pool.size() < lanes) pool.emplace_back(new Context());
     int first_err = DFL_OK;
@@ -1009,8 +1017,7 @@ extern "C" int dfl_compress_batch(size_t count, const uint8_t* const* in, const 
                                   uint8_t* const* out, const size_t* out_cap, size_t* out_len, int* status) {
     if (!opt || !valid_wrap(wrap) || (count && (!in || !n || !out || !out_cap || !out_len))) return DFL_E_ARG;
     constexpr size_t kBatchLanes = 16;
-    thread_local std::map<int, std::vector<std::unique_ptr<Context>>> pools;   // per device
-    std::vector<std::unique_ptr<Context>>& pool = pools[current_device()];
+    std::vector<std::unique_ptr<Context>>& pool = tls_batch_pools(1)[current_device()];
     const size_t lanes = count < kBatchLanes ? count : kBatchLanes;
     while (pool.size() < lanes) pool.emplace_back(new Context());
     std::vector<size_t> member(lanes, SIZE_MAX);   // the member in flight on each lane
@@ -1720,4 +1727,33 @@ extern "C" void dfl_encoder_free(dfl_encoder* e) {
     if (!e) return;
     DeviceGuard on_device(e->device);
     delete e;
+}
+
+// ============================================================================ scratch
+// Everything the library keeps between calls on behalf of the calling thread -- the one-shot context (29 B of
+// device scratch per input byte of the largest call so far, staging buffers, streams), the batch pools -- and the
+// process-wide pool of parked handle resources is released; the next call builds what it needs again (cudaMalloc
+// of a GiB-sized context costs 0.1 - 2 s on the B200 hosts, which is why nothing is freed unasked).  Live
+// dfl_encoder handles are not touched.
+extern "C" int dfl_trim(void) {
+    int saved = -1;
+    const bool have_dev = device_count_cached() > 0 && cudaGetDevice(&saved) == cudaSuccess;
+    auto on_device = [&](int dev) { if (have_dev && dev >= 0) cudaSetDevice(dev); };
+    for (auto& kv : tls_contexts()) { on_device(kv.first); kv.second.reset(); }
+    tls_contexts().clear();
+    for (int which = 0; which < 2; which++) {
+        for (auto& kv : tls_batch_pools(which)) { on_device(kv.first); kv.second.clear(); }
+        tls_batch_pools(which).clear();
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_handle_pool_mu);
+        for (HandleRes& r : g_handle_pool) {
+            on_device(r.device);
+            r.ctx.reset();
+            for (int i = 0; i < 2; i++) { dev_free(r.d[i]); r.cap[i] = 0; }
+        }
+        g_handle_pool.clear();
+    }
+    if (have_dev) cudaSetDevice(saved);
+    return DFL_OK;
 }

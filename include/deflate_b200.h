@@ -143,6 +143,13 @@ int dfl_last_stage_times(const char **names, float *ms, int cap);
  * [5] kernels launched, [6] stored blocks, [7] fixed blocks. */
 int dfl_last_counters(uint64_t *out, int cap);
 
+/* Releases the scratch the library keeps between calls: the calling thread's one-shot context (about 29 bytes of
+ * device memory per input byte of its largest call so far) and batch pools, and the process-wide pool of parked
+ * handle resources.  Nothing in the reference corresponds to it (a Vec is dropped when deflate_bytes returns,
+ * lib.rs:141-146); here allocations are kept because cudaMalloc of a context costs more than encoding with it.
+ * Live dfl_encoder handles are not touched.  Always DFL_OK. */
+int dfl_trim(void);
+
 /* ---- streaming: write::{DeflateEncoder,ZlibEncoder,GzEncoder} (writer.rs:89-467) ----------
  * The generic sink W cannot cross an FFI, so output is pulled: the shim forwards the bytes lent
  * by dfl_encoder_take_output to its `inner.write(..)` and reports progress with

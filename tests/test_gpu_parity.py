@@ -489,6 +489,26 @@ def test_host_batch_reports_overflow_per_member(dfl):
         assert bytes(outs[i][:out_len[i]]) == want[i]
 
 
+def test_trim_releases_the_scratch_and_the_next_call_rebuilds_it(dfl, pg11):
+    """dfl_trim (the reference drops its Vec when deflate_bytes returns, lib.rs:141-146; the library keeps its device
+    scratch between calls because allocating it costs more than encoding with it, and gives it back on request)."""
+    import datagen
+    import torch
+    data = datagen.silesia_mix(64 << 20)
+    want = dfl.deflate_bytes(data)
+    sink = bytearray()
+    enc = dfl.write.ZlibEncoder(sink, dfl.Compression.Default)   # parks its resources in the handle pool when dropped
+    enc.write_all(pg11); enc.finish(); del enc
+    dfl.compress_batch([pg11, pg11[:50000]], dfl.Compression.Default, dfl.ZLIB)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    dfl.trim()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 - free0 > 20 * len(data), (free0, free1)           # the 64 MiB context alone held about 29 bytes per input byte
+    assert dfl.deflate_bytes(data) == want
+    assert dfl.deflate_bytes(pg11) == o.compress(pg11, o.opts_default(), o.RAW)
+
+
 # ---------------------------------------------------------------- BASELINE.json's full sizes
 def _inflate_equals(comp: bytes, data: bytes, wbits: int) -> bool:
     d = zlib.decompressobj(wbits)
