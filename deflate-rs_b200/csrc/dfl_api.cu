@@ -374,7 +374,7 @@ struct Context {
         quarter = quarter || b.cap_quarter;
         free_buffers();
         size_t n_win = (cap + kWindow - 1) / kWindow + 1;
-        size_t n_seg = (cap + 1023) / 1024 + 1;   // the shortest parse segment (parse_geom) gives the most segments
+        size_t n_seg = parse_max_segments(cap) + 1;
         size_t n_blk = max_blocks_for((uint32_t)cap) + 1;
         size_t n_chunk = (cap + kAdlerChunk - 1) / kAdlerChunk + 1;
         int rc = 0;

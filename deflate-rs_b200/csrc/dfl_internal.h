@@ -31,34 +31,47 @@ static_assert(kParseSeg + kParseWarm + 300u + 264u < 16384u && kParseSegGreedy +
 // power of two fall across the strided segment order of a warp).  The warm-up is parsed twice; 256 bytes
 // resynchronise all but a few segments per GiB, which the repair rounds re-parse.
 struct ParseGeom { uint32_t seg, warm; };
-#ifndef DFL_PARSE_WARM_MID
-#define DFL_PARSE_WARM_MID 256
-#endif
+// About one segment per parse lane (148 SMs x 7 CTAs x 128 threads = 132 608): a power of two between 256 bytes and
+// the large-input segment, such that the input has between 98 304 and 196 608 of them.  A parse lane walks its
+// segment (and the warm-up in front of it) sequentially, resolving long records on the way, so on inputs that do not
+// fill the chip the segment length is the latency of the whole stage -- tools/latency.py, one Default call on
+// Silesia-mix text, 1 KiB + 512 B segments against these: 64 KiB 4.9 -> 1.6 ms, 1 MiB 10.4 -> 2.2 ms, 4 MiB 7.9 ->
+// 3.1 ms, 16 MiB 12.2 -> 7.2 ms; 256 x 4 MiB PNG-like chunks through the batch call 5 242 -> 6 994 MiB/s.
+//   256 MiB in 8 KiB segments would leave three quarters of the lanes without work (parse 69 ms against 30 ms with
+// 2 KiB segments, CompressionOptions::high()).  The warm-up is parsed twice, so it is short: 64 bytes resynchronise
+// all but a few segments (the repair rounds re-parse those).
 inline ParseGeom parse_geom(size_t payload, int mode) {
-    if (payload <= (32u << 20)) return {1024u, 512u};
-    // about one segment per parse lane (148 SMs x 7 CTAs x 128 threads = 132 608), a power of two from 2 KiB up to the
-    // large-input segment: 256 MiB in 8 KiB segments leaves three quarters of the lanes without work (parse 69 ms
-    // against 30 ms with 2 KiB segments, CompressionOptions::high())
-    uint32_t seg = 2048u;
+    if (payload <= (2u << 20)) return {128u, 64u};
+    uint32_t seg = 256u;
     while (seg < kParseSeg && payload / seg > 196608u) seg <<= 1;
-    if (seg < kParseSeg) return {seg, (uint32_t)DFL_PARSE_WARM_MID};
+    if (seg <= 512u) return {seg, 64u};
+    if (seg <= 1024u) return {seg, 128u};
+    if (seg < kParseSeg) return {seg, 256u};
     return {kParseSeg, mode == kGreedy ? kParseWarmGreedy : kParseWarm};
 }
 inline uint32_t parse_tok_cap(ParseGeom g) { return g.seg + g.warm + 264u; }
 inline size_t parse_n_seg(size_t payload, ParseGeom g) { return (payload + g.seg - 1) / g.seg; }
-// u32 words of segment token buffers needed for a payload of at most `cap` bytes, whatever its geometry
-inline size_t parse_buffer_words(size_t cap) {
+// u32 words of segment token buffers / number of segments needed for a payload of at most `cap` bytes, whatever its
+// geometry: the largest payload of every geometry (the sizes at which parse_geom changes) is what counts
+template <class F>
+inline size_t parse_max_over_geometries(size_t cap, F f) {
     size_t best = 0;
-    const size_t edges[5] = {(size_t)32u << 20, (size_t)384u << 20, (size_t)768u << 20, (size_t)1536u << 20, cap};   // sizes at which the geometry changes
+    const size_t edges[8] = {(size_t)2u << 20, (size_t)196608u * 256u, (size_t)196608u * 512u, (size_t)196608u * 1024u,
+                             (size_t)196608u * 2048u, (size_t)196608u * 4096u, (size_t)196608u * 8192u, cap};
     for (size_t e0 : edges) {
         const size_t e = e0 < cap ? e0 : cap;
         for (int mode : {(int)kGreedy, (int)kLazy}) {
-            ParseGeom g = parse_geom(e, mode);
-            size_t w = (parse_n_seg(e, g) + 1) * parse_tok_cap(g);
-            if (w > best) best = w;
+            const size_t v = f(e, parse_geom(e, mode));
+            if (v > best) best = v;
         }
     }
     return best;
+}
+inline size_t parse_buffer_words(size_t cap) {
+    return parse_max_over_geometries(cap, [](size_t e, ParseGeom g) { return (parse_n_seg(e, g) + 1) * (size_t)parse_tok_cap(g); });
+}
+inline size_t parse_max_segments(size_t cap) {
+    return parse_max_over_geometries(cap, [](size_t e, ParseGeom g) { return parse_n_seg(e, g) + 1; });
 }
 // Parallel repair rounds before the sequential fallback; every second one predicts the phase of chains of
 // maximum-length matches (k_chain_predict).  A round is three small launches; short inputs, where launch latency
