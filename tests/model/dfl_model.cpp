@@ -113,6 +113,39 @@ void match_all(const uint8_t* d, uint32_t n, const Params& prm, const std::vecto
     }
 }
 
+// ---- stage 1' + 2': max_hash_checks == 1 (kernels k_window_sort<true>, k_match_first).  The one candidate of a position is
+// its predecessor in the bucket: the neighbouring item of the sorted order if that has the same hash, else the last
+// position of the same bucket in the previous window, if it is within the window.
+void match_one(const uint8_t* d, uint32_t n, const std::vector<Entry>& K, const std::vector<uint16_t>& off,
+               const std::vector<uint32_t>& cnt, std::vector<uint32_t>& Mf) {
+    Mf.assign(n, 0);
+    const uint32_t nseg = (uint32_t)cnt.size();
+    auto lcp = [&](uint32_t p, uint32_t q) { uint32_t maxl = std::min(kMaxMatch, n - p), l = 0; while (l < maxl && d[p + l] == d[q + l]) l++; return l; };
+    std::vector<uint16_t> last_prev, last_cur;       // last position of every bucket of a window, 0xffff = none
+    for (uint32_t s = 0; s < nseg; s++) {
+        const Entry* Kw = &K[(size_t)s * kWindow];
+        const uint16_t* ow = &off[(size_t)s * kWindow];
+        last_cur.assign(kWindow, 0xffff);
+        for (uint32_t h = 0; h < kWindow; h++) {
+            const uint32_t lo = ow[h], hi = h + 1 < kWindow ? ow[h + 1] : cnt[s];
+            for (uint32_t i = lo; i < hi; i++) {
+                const uint32_t pl = entry_pos(Kw[i].hi), p = s * kWindow + pl;
+                uint32_t rec = 0;
+                if (i > lo) {                                    // the neighbour in the sorted order, same bucket
+                    const uint32_t q = s * kWindow + entry_pos(Kw[i - 1].hi);
+                    rec = finalize_match(lcp(p, q), p - q);
+                } else if (s > 0 && last_prev[h] != 0xffff && last_prev[h] >= pl) {   // k_match_first
+                    const uint32_t q = (s - 1) * kWindow + last_prev[h];
+                    rec = finalize_match(lcp(p, q), p - q);
+                }
+                Mf[p] = rec;
+            }
+            if (hi > lo) last_cur[h] = (uint16_t)entry_pos(Kw[hi - 1].hi);
+        }
+        last_prev.swap(last_cur);
+    }
+}
+
 // ---- stage 3a: resolution of a long record at a position the parser searches (warp-cooperative in k_parse*)
 // Every candidate from visit k8 on that shares the target's 8 entry bytes is compared on the data; the first
 // strictly longer one wins (matching.rs:148-157), starting from max(floor, 7): the caller only uses a result
@@ -154,10 +187,12 @@ uint32_t resolve_long(const uint8_t* d, uint32_t n, const std::vector<Entry>& K,
     return best > std::max(floor, kEntryBytes - 1u) ? finalize_match(best, p - best_q) : 0u;
 }
 
+int g_force_generic = 0;   // test hook: 1 = the generic walk also for max_hash_checks == 1
 void find_matches(const uint8_t* in, uint32_t n, const Params& prm, std::vector<Entry>& S, std::vector<uint16_t>& off,
                   std::vector<uint32_t>& cnt, std::vector<uint32_t>& Mf, std::vector<uint32_t>& Mq) {
     window_sort(in, n, S, off, cnt);
-    match_all(in, n, prm, S, off, cnt, Mf, Mq);
+    if (prm.checks == 1u && prm.mode != kRle && !prm.need_quarter && !g_force_generic) match_one(in, n, S, off, cnt, Mf);   // dfl_internal.h one_candidate()
+    else match_all(in, n, prm, S, off, cnt, Mf, Mq);
 }
 
 // ---- stage 3: speculative segment parse + hand-off verification + repair (k_parse*, k_verify)
@@ -462,6 +497,7 @@ void dflm_symbols(uint32_t len, uint32_t dist, uint32_t* o /*[6]*/) {
 void dflm_free(void* p) { free(p); }
 uint32_t dflm_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return crc32_combine(c1, c2, len2); }
 uint32_t dflm_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
+void dflm_force_generic_match(int on) { g_force_generic = on; }
 void dflm_resolve_stats(uint64_t* o /*[8]*/, int reset) {
     for (int i = 0; i < 8; i++) { o[i] = g_resolve_stats[i]; if (reset) g_resolve_stats[i] = 0; }
 }

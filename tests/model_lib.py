@@ -34,6 +34,12 @@ def lib():
     return _lib
 
 
+def force_generic_match(on: bool):
+    """Test hook: run the generic candidate walk also for max_hash_checks == 1 (the kernels and the model take the
+    one-candidate path there: the match is settled against the predecessor in the sorted order)."""
+    lib().dflm_force_generic_match(1 if on else 0)
+
+
 def resolve_stats(reset=True):
     """Counters of the long-match resolutions the parser asked for since the last reset."""
     st = (ctypes.c_uint64 * 8)()

@@ -90,6 +90,28 @@ def test_model_lazy_below_three(pg11):
             assert got == o.compress(data, opts, o.RAW), (checks, lazy, name)
 
 
+def test_model_one_candidate_path_equals_the_generic_walk_and_the_oracle(pg11):
+    """max_hash_checks == 1 (Compression::Fast): k_window_sort<true> settles every position against its predecessor in
+    the sorted order and k_match_first the first position of every bucket against the last one of the same bucket in
+    the previous window.  Same tokens as the generic walk with a budget of one, and as the oracle, across window
+    boundaries (inputs of several windows), for the greedy and the lazy parser."""
+    import datagen
+    inputs = [pg11, datagen.silesia_mix(1 << 20), bytes(100000), datagen.enwik_like(300000)]
+    for data in inputs:
+        for lazy, mt in ((0, 0), (32, 1), (4, 1)):
+            opts = o.Options(1, lazy, mt, 0)
+            want = o.compress(data, opts, o.RAW)
+            m.force_generic_match(False)
+            got, _ = m.compress(data, opts)
+            assert got == want, (len(data), lazy, mt, "one-candidate path")
+            m.force_generic_match(True)
+            try:
+                gen, _ = m.compress(data, opts)
+            finally:
+                m.force_generic_match(False)
+            assert gen == want, (len(data), lazy, mt, "generic walk")
+
+
 def test_checksum_combine_arithmetic():
     """dfl_core.h crc32_combine / adler32_combine (used by the kernels' tree reductions and by the
     streaming handle) against CPython zlib on random splits, incl. empty and > 4 GiB-style lengths."""
