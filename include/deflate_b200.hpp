@@ -84,6 +84,8 @@ inline std::vector<uint8_t> deflate_bytes_gzip_conf(const uint8_t* in, size_t n,
     return detail::oneshot(in, n, o, DFL_GZIP, gz_header, "deflate_bytes_gzip_conf");
 }
 inline std::vector<uint8_t> deflate_bytes_gzip(const uint8_t* in, size_t n) { return deflate_bytes_gzip_conf(in, n, Compression::Default); }   // lib.rs:284
+/// Gives back the device scratch the library keeps between calls (dfl_trim); the next call allocates again.
+inline void trim() { dfl_trim(); }
 
 // write::{DeflateEncoder, ZlibEncoder, GzEncoder} (writer.rs:89-467).  The sink plays the role of `W: io::Write`:
 // it is handed bytes and returns how many it took (0 = error, like io::ErrorKind::WriteZero).

@@ -53,6 +53,7 @@ pub mod ffi {
         pub fn dfl_last_cuda_error() -> *const c_char;
         pub fn dfl_device_count() -> i32;
         pub fn dfl_bound(n: usize, wrap: i32) -> usize;
+        pub fn dfl_trim() -> i32;
         pub fn dfl_compress(input: *const u8, n: usize, opt: *const dfl_options, wrap: i32, gz_hdr: *const u8,
                             gz_hdr_len: usize, out: *mut u8, out_cap: usize, out_len: *mut usize) -> i32;
         pub fn dfl_compress_batch(count: usize, input: *const *const u8, n: *const usize, opt: *const dfl_options,
@@ -196,6 +197,12 @@ pub fn deflate_bytes_conf<O: Into<CompressionOptions>>(input: &[u8], options: O)
     oneshot(input, options.into(), DFL_RAW, &[], "Write error!")
 }
 /// `src/lib.rs:163`
+/// Not part of the crate's API: releases the device scratch the library keeps between calls for the calling
+/// thread (and the pool of parked encoder resources); the next call allocates again.
+pub fn trim_device_scratch() {
+    unsafe { ffi::dfl_trim() };
+}
+
 pub fn deflate_bytes(input: &[u8]) -> Vec<u8> {
     deflate_bytes_conf(input, Compression::Default)
 }
